@@ -1,0 +1,207 @@
+/*
+ * snacb.h - C ABI of the B200-native SNAC-24k token->waveform engine (libsnacb.so).
+ *
+ * The reference (DocWobble/Project_Morpheus) is pure Python and has NO FFI: its hot path is
+ *   Morpheus_Client/tts_engine/speechpipe.py:64-137   convert_to_audio(multiframe, count)
+ *   Morpheus_Client/tts_engine/speechpipe.py:118       model.decode(codes)   (third-party `snac`)
+ * so this header is the boundary a maintainer would bind with ctypes; every
+ * entry point cites the reference lines it replaces.  Plain C types only: pointers and sizes, no
+ * C++/torch types, no exceptions across the boundary.
+ *
+ * Conventions
+ *   - "d_" pointers are device memory on the engine's GPU, "h_" pointers are host memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work is
+ *     enqueued asynchronously on it unless stated; a handle is bound to one device and is not
+ *     re-entrant (one handle per GPU worker).
+ *   - Return value: 0 (SNACB_OK) or a negative SNACB_E* code; snacb_last_error() gives the text.
+ *   - The caller owns every buffer it passes; the engine owns packed weights and its workspace.
+ *   - There is no CPU fallback: without a CUDA device snacb_create() fails.
+ */
+#ifndef SNACB_H
+#define SNACB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNACB_ABI_VERSION 1
+
+/* return codes */
+#define SNACB_OK 0
+#define SNACB_EINVAL (-1)   /* bad argument */
+#define SNACB_ECUDA (-2)    /* CUDA runtime / driver error */
+#define SNACB_ESTATE (-3)   /* weights not loaded, engine misuse */
+#define SNACB_ENOMEM (-4)
+
+/* per-window status written by the integer kernel (speechpipe.py:69-70,108-111,122) */
+#define SNACB_WIN_OK 0        /* decoded, 2048 int16 samples written                               */
+#define SNACB_WIN_REJECTED 1  /* reference returns None: < 7 tokens, or a code < 0 or > 4096        */
+#define SNACB_WIN_CODE4096 2  /* code == 4096 passes the reference validator, then F.embedding raises */
+#define SNACB_WIN_EMPTY 3     /* one whole frame only: slice [2048:4096) is empty, reference returns b'' */
+
+/* noise modes for NoiseBlock (x + randn[B,1,T] * W_n x inside the third-party decoder) */
+#define SNACB_NOISE_OFF 0     /* zeros                                                  */
+#define SNACB_NOISE_TENSOR 1  /* caller-provided noise, layout below (parity mode A)    */
+#define SNACB_NOISE_PHILOX 2  /* counter-based Philox4x32-10 keyed by (seed,key,block,t) */
+
+/* arithmetic recipes for the GEMM-shaped layers (1x1 convs, ConvTranspose1d) */
+#define SNACB_PREC_FP32 0     /* CUDA-core fp32 FMA: the exact/bring-up path              */
+#define SNACB_PREC_FP16 1     /* tcgen05 kind::f16, fp16 operands, fp32 TMEM accumulators */
+
+/* fixed geometry of hubertsiuzdak/snac_24khz (the only model the reference loads, speechpipe.py:42) */
+#define SNACB_LATENT 768
+#define SNACB_DECODER_DIM 1024
+#define SNACB_CODEBOOK_SIZE 4096
+#define SNACB_CODEBOOK_DIM 8
+#define SNACB_TOKENS_PER_FRAME 7
+#define SNACB_SAMPLES_PER_FRAME 2048
+#define SNACB_NOISE_PER_FRAME 3360 /* 32+256+1024+2048 noise values per frame per window */
+
+typedef struct snacb_engine snacb_engine;
+
+typedef struct snacb_config {
+  int32_t abi_version;   /* SNACB_ABI_VERSION */
+  int32_t device;        /* CUDA ordinal */
+  int32_t precision;     /* SNACB_PREC_* */
+  int32_t chunk_items;   /* windows processed per pass through the layer stack (0 = default);
+                            sized so one pass's activations stay L2-resident */
+  int32_t trim;          /* 1 = compute only the dependency cone of the emitted slice (exact) */
+  int32_t reserved[11];
+} snacb_config;
+
+/* One residual unit: x + W_pw * Snake(dw7_dil(Snake(x))) */
+typedef struct snacb_ru_weights {
+  const float* alpha1; /* [C]      Snake alpha before the depthwise conv           */
+  const float* dw_w;   /* [C][7]   depthwise k=7 weight, weight-norm folded        */
+  const float* dw_b;   /* [C]                                                       */
+  const float* alpha2; /* [C]                                                       */
+  const float* pw_w;   /* [C][C]   1x1 conv weight [Cout][Cin], folded             */
+  const float* pw_b;   /* [C]                                                       */
+} snacb_ru_weights;
+
+typedef struct snacb_block_weights {
+  const float* alpha;    /* [Cin]                block-head Snake                            */
+  const float* convt_w;  /* [Cin][Cout][2*s]     ConvTranspose1d weight, PyTorch layout,
+                                                 folded per INPUT channel (weight_norm dim 0) */
+  const float* convt_b;  /* [Cout]                                                           */
+  const float* noise_w;  /* [Cout][Cout]         NoiseBlock 1x1, no bias                     */
+  snacb_ru_weights ru[3]; /* dilations 1, 3, 9 */
+} snacb_block_weights;
+
+/* Host pointers to fp32 arrays, weight-norm already folded (w = g*v/||v||).  Copied and
+ * re-packed by snacb_load_weights(); may be freed afterwards. */
+typedef struct snacb_weights {
+  const float* codebook[3];  /* [4096][8]  RVQ level l codebook                      */
+  const float* outproj_w[3]; /* [768][8]   out_proj 1x1 (8 -> latent)                */
+  const float* outproj_b[3]; /* [768]                                                */
+  const float* head_dw_w;    /* [768][7]   decoder.model.0 (depthwise k7)            */
+  const float* head_dw_b;    /* [768]                                                */
+  const float* head_pw_w;    /* [1024][768] decoder.model.1                          */
+  const float* head_pw_b;    /* [1024]                                               */
+  snacb_block_weights block[4]; /* strides 8,8,4,2; channels 1024->512->256->128->64 */
+  const float* tail_alpha;   /* [64]       decoder.model.6                           */
+  const float* tail_w;       /* [64][7]    decoder.model.7 (64 -> 1, k7)             */
+  const float* tail_b;       /* [1]                                                  */
+} snacb_weights;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+
+/* Replaces the module-level model load + device placement, speechpipe.py:38-61. */
+int snacb_create(snacb_engine** out, const snacb_config* cfg);
+void snacb_destroy(snacb_engine* e);
+/* Text of the last error on this engine (or of the last failed snacb_create when e == NULL). */
+const char* snacb_last_error(const snacb_engine* e);
+/* Replaces SNAC.from_pretrained(...).to(device) weight upload, speechpipe.py:43,49 (weight-norm
+ * folded once instead of on every forward). Synchronous. */
+int snacb_load_weights(snacb_engine* e, const snacb_weights* w);
+/* Bytes of device workspace currently held by the engine. */
+size_t snacb_workspace_bytes(const snacb_engine* e);
+/* Number of kernels this engine has launched since creation (bench.py's gpu_launches claim). */
+int64_t snacb_launch_count(const snacb_engine* e);
+
+/* ---- NS-1: integer de-interleave + validate ------------------------------------------------ */
+
+/* Replaces speechpipe.py:72-111 (frame truncation, de-interleave loop, range validator), batched.
+ *   d_tokens  [n_win][tokens_stride] int32 token ids (offsets already removed, i.e. what
+ *             turn_token_into_id returns); window i uses its first h_ntok[i] entries
+ *             (h_ntok == NULL: every window has ntok_uniform tokens).
+ *   F_i = ntok_i / 7 whole frames; codes are written densely at row pitch max_frames:
+ *   d_c0 [n_win][max_frames], d_c1 [n_win][2*max_frames], d_c2 [n_win][4*max_frames] (int32,
+ *   entries beyond F_i zeroed), d_status [n_win] = SNACB_WIN_*.  Bit-exact vs the reference. */
+int snacb_deinterleave(snacb_engine* e, const int32_t* d_tokens, int32_t tokens_stride,
+                       const int32_t* h_ntok, int32_t ntok_uniform, int32_t n_win,
+                       int32_t max_frames, int32_t* d_c0, int32_t* d_c1, int32_t* d_c2,
+                       int32_t* d_status, void* stream);
+
+/* Raw-token variant (north_star item 1): d_raw holds N of "<custom_token_N>" for ALIGNED streams,
+ * position p of window i has slot (p % 7); id = N - 10 - 4096*(p%7) (speechpipe.py:181). */
+int snacb_deinterleave_raw(snacb_engine* e, const int32_t* d_raw, int32_t tokens_stride,
+                           const int32_t* h_ntok, int32_t ntok_uniform, int32_t n_win,
+                           int32_t max_frames, int32_t* d_c0, int32_t* d_c1, int32_t* d_c2,
+                           int32_t* d_status, void* stream);
+
+/* ---- the streaming path: tokens -> PCM ------------------------------------------------------ */
+
+/* Replaces convert_to_audio (speechpipe.py:64-137) for a whole decode tick: de-interleave +
+ * validate + SNAC decode + slice [2048:4096) + trunc(x*32767) int16 pack, one call for all windows.
+ *   d_tokens/h_ntok/ntok_uniform as above (any mix of window lengths; windows are grouped by
+ *   frame count internally).
+ *   d_noise   SNACB_NOISE_TENSOR: [n_win][noise_stride] float32, window i holds the four noise
+ *             rows of an F_i-frame decode back to back (lengths 32F,256F,1024F,2048F), i.e.
+ *             torch.cat([n_b[i,0,:] for b in 0..3]); noise_stride >= 3360*max F.  Else NULL.
+ *   seed      SNACB_NOISE_PHILOX key; h_keys (optional, [n_win] uint64) distinguishes streams.
+ *   d_pcm     [n_win][2048] int16; rows of windows whose status != SNACB_WIN_OK are zeroed.
+ *   d_status  [n_win] int32 SNACB_WIN_*.  A bad window never poisons the batch. */
+int snacb_decode_windows(snacb_engine* e, const int32_t* d_tokens, int32_t tokens_stride,
+                         const int32_t* h_ntok, int32_t ntok_uniform, int32_t n_win,
+                         int32_t noise_mode, const float* d_noise, int64_t noise_stride,
+                         uint64_t seed, const uint64_t* h_keys, int16_t* d_pcm, int32_t* d_status,
+                         void* stream);
+
+/* Same contract with HOST buffers (pageable or pinned): stages through the engine's pinned
+ * buffers, H2D + kernels + D2H on `stream`, returns after the PCM and status are in h_pcm/h_status.
+ * This is the call the Python convert_to_audio / convert_to_audio_batch make. */
+int snacb_decode_windows_host(snacb_engine* e, const int32_t* h_tokens, int32_t tokens_stride,
+                              const int32_t* h_ntok, int32_t ntok_uniform, int32_t n_win,
+                              int32_t noise_mode, const float* h_noise, int64_t noise_stride,
+                              uint64_t seed, const uint64_t* h_keys, int16_t* h_pcm,
+                              int32_t* h_status, void* stream);
+
+/* ---- the one-shot path: codes -> waveform --------------------------------------------------- */
+
+/* Replaces model.decode(codes) (speechpipe.py:118; quantizer.from_codes + decoder) for B sequences
+ * of F frames: d_c0 [B][F], d_c1 [B][2F], d_c2 [B][4F] int32 in [0,4095] (caller validated).
+ * Writes d_wav [B][2048F] float32 and/or d_pcm [B][2048F] int16 (either may be NULL).  Long
+ * sequences are time-tiled with halo recompute internally.  d_noise: [B][3360F] as above. */
+int snacb_decode_codes(snacb_engine* e, const int32_t* d_c0, const int32_t* d_c1,
+                       const int32_t* d_c2, int32_t B, int32_t F, int32_t noise_mode,
+                       const float* d_noise, uint64_t seed, float* d_wav, int16_t* d_pcm,
+                       void* stream);
+
+/* Writes the noise SNACB_NOISE_PHILOX would use for (seed, keys) in the SNACB_NOISE_TENSOR layout,
+ * so the oracle can replay a production decode (byte-identical replay under a fixed seed). */
+int snacb_fill_noise(snacb_engine* e, uint64_t seed, const uint64_t* h_keys, int32_t n_win,
+                     int32_t F, float* d_noise, int64_t noise_stride, void* stream);
+
+/* ---- bring-up / parity taps ----------------------------------------------------------------- */
+
+/* Layer-wise parity: after the next decode, d_buf receives the fp32 activation of `stage`
+ * (channels-last [items][rows][channels]) for the first chunk. stage < 0 disables the tap.
+ * Stage ids: 0 z, 1 head dw, 2 head 1x1, 3+9b+{0 snake,1 convT,2 noise,3..8 (dw,out) of RU 0..2}. */
+int snacb_set_tap(snacb_engine* e, int32_t stage, float* d_buf, size_t capacity_floats);
+/* Geometry of the last captured tap: rows per item, channels, first row's time index, items. */
+int snacb_get_tap_shape(const snacb_engine* e, int32_t* rows, int32_t* channels, int32_t* t_lo,
+                        int32_t* items);
+
+/* Host-only: the row ranges the engine computes for an F-frame sequence when samples
+ * [out_lo, out_hi) are requested (exact dependency cone).  ranges receives 26
+ * (lo, hi) pairs: z, head, then per decoder block: in, q, convT, ru0, ru1, ru2. Needs no GPU. */
+int snacb_plan(int32_t frames, int32_t out_lo, int32_t out_hi, int32_t clip, int32_t* ranges);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNACB_H */

@@ -1,0 +1,106 @@
+"""ctypes binding of ``libsnacb.so`` (the C ABI declared in ``include/snacb.h``).
+
+There is no CPU fallback: if the shared library is missing this module raises, and
+``snacb_create`` itself fails without a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+ABI_VERSION = 1
+OK = 0
+WIN_OK, WIN_REJECTED, WIN_CODE4096, WIN_EMPTY = 0, 1, 2, 3
+NOISE_OFF, NOISE_TENSOR, NOISE_PHILOX = 0, 1, 2
+PREC_FP32, PREC_FP16 = 0, 1
+NOISE_PER_FRAME = 3360
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsnacb.so")
+
+_f32p = C.POINTER(C.c_float)
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("device", C.c_int32),
+        ("precision", C.c_int32),
+        ("chunk_items", C.c_int32),
+        ("trim", C.c_int32),
+        ("reserved", C.c_int32 * 11),
+    ]
+
+
+class RuWeights(C.Structure):
+    _fields_ = [(n, _f32p) for n in ("alpha1", "dw_w", "dw_b", "alpha2", "pw_w", "pw_b")]
+
+
+class BlockWeights(C.Structure):
+    _fields_ = [("alpha", _f32p), ("convt_w", _f32p), ("convt_b", _f32p), ("noise_w", _f32p), ("ru", RuWeights * 3)]
+
+
+class Weights(C.Structure):
+    _fields_ = [
+        ("codebook", _f32p * 3),
+        ("outproj_w", _f32p * 3),
+        ("outproj_b", _f32p * 3),
+        ("head_dw_w", _f32p),
+        ("head_dw_b", _f32p),
+        ("head_pw_w", _f32p),
+        ("head_pw_b", _f32p),
+        ("block", BlockWeights * 4),
+        ("tail_alpha", _f32p),
+        ("tail_w", _f32p),
+        ("tail_b", _f32p),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/snacb.h declares
+_vp, _i32, _i64, _u64, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_size_t
+SIGNATURES = {
+    "snacb_create": (_i32, [C.POINTER(_vp), C.POINTER(Config)]),
+    "snacb_destroy": (None, [_vp]),
+    "snacb_last_error": (C.c_char_p, [_vp]),
+    "snacb_load_weights": (_i32, [_vp, C.POINTER(Weights)]),
+    "snacb_workspace_bytes": (_sz, [_vp]),
+    "snacb_launch_count": (_i64, [_vp]),
+    "snacb_deinterleave": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "snacb_deinterleave_raw": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "snacb_decode_windows": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _i64, _u64, _vp, _vp, _vp, _vp]),
+    "snacb_decode_windows_host": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _i64, _u64, _vp, _vp, _vp, _vp]),
+    "snacb_decode_codes": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _u64, _vp, _vp, _vp]),
+    "snacb_fill_noise": (_i32, [_vp, _u64, _vp, _i32, _i32, _vp, _i64, _vp]),
+    "snacb_set_tap": (_i32, [_vp, _i32, _vp, _sz]),
+    "snacb_plan": (_i32, [_i32, _i32, _i32, _i32, C.POINTER(_i32)]),
+    "snacb_get_tap_shape": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library and bind every declared symbol (raises if anything is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m project_morpheus_b200.build` "
+            "(or __graft_entry__.build()); there is no CPU fallback for the SNAC decode path"
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+class SnacbError(RuntimeError):
+    pass
+
+
+def check(lib, handle, rc: int, what: str) -> None:
+    if rc != OK:
+        msg = lib.snacb_last_error(handle)
+        raise SnacbError(f"{what} failed ({rc}): {msg.decode() if msg else 'unknown error'}")

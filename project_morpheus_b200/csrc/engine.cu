@@ -1,0 +1,672 @@
+// libsnacb engine: weight packing, the plan-driven layer pipeline and the C-ABI entry points
+// declared in include/snacb.h.  Replaces the reference's convert_to_audio / model.decode path
+// (Morpheus_Client/tts_engine/speechpipe.py:64-137) for whole decode ticks.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "kernels.h"
+#include "snacb.h"
+
+using namespace snacb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct RuDev {
+  float *a1, *i1, *dw_w, *dw_b, *a2, *i2, *pw_w, *pw_b;
+};
+struct BlockDev {
+  float *alpha, *inv, *ct_w /*[s*Cout][2*Cin]*/, *ct_b, *noise_w;
+  RuDev ru[3];
+};
+struct DevWeights {
+  QuantW q;
+  float *head_dw_w /*[7][768]*/, *head_dw_b, *head_pw_w, *head_pw_b;
+  BlockDev blk[4];
+  float *tail_alpha, *tail_inv, *tail_w /*[7][64]*/, *tail_b;
+};
+
+}  // namespace
+
+struct snacb_engine {
+  snacb_config cfg{};
+  int device = 0;
+  std::string err;
+  bool loaded = false;
+  DevWeights w{};
+  void* warena = nullptr;
+  size_t warena_bytes = 0;
+  char* ws = nullptr;
+  size_t ws_bytes = 0;
+  // pinned + device staging for the host-buffer API and the item tables
+  char* pin = nullptr;
+  size_t pin_bytes = 0;
+  char* dstage = nullptr;
+  size_t dstage_bytes = 0;
+  Item* pin_items = nullptr;
+  size_t pin_items_cap = 0;
+  cudaEvent_t items_ev = nullptr;
+  int64_t launches = 0;
+  // tap
+  int tap_stage = -1;
+  float* tap_buf = nullptr;
+  size_t tap_cap = 0;
+  int tap_rows = 0, tap_ch = 0, tap_lo = 0, tap_items = 0;
+};
+
+namespace {
+
+int fail(snacb_engine* e, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (e) e->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CU(e, call)                                                                                   \
+  do {                                                                                                \
+    cudaError_t _c = (call);                                                                          \
+    if (_c != cudaSuccess)                                                                            \
+      return fail(e, SNACB_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_c), __FILE__, __LINE__); \
+  } while (0)
+
+int check_launch(snacb_engine* e, const char* what) {
+  cudaError_t c = cudaGetLastError();
+  if (c != cudaSuccess) return fail(e, SNACB_ECUDA, "%s: launch failed: %s", what, cudaGetErrorString(c));
+  return SNACB_OK;
+}
+
+int ensure_ws(snacb_engine* e, size_t bytes, cudaStream_t st) {
+  if (bytes <= e->ws_bytes) return SNACB_OK;
+  if (e->ws) {
+    CU(e, cudaStreamSynchronize(st));
+    CU(e, cudaDeviceSynchronize());
+    CU(e, cudaFree(e->ws));
+    e->ws = nullptr; e->ws_bytes = 0;
+  }
+  bytes = (bytes + (size_t(1) << 20)) & ~((size_t(1) << 20) - 1);
+  cudaError_t c = cudaMalloc((void**)&e->ws, bytes);
+  if (c != cudaSuccess) return fail(e, SNACB_ENOMEM, "workspace cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(c));
+  e->ws_bytes = bytes;
+  return SNACB_OK;
+}
+
+struct Bump {
+  char* p; size_t off = 0;
+  explicit Bump(char* base) : p(base) {}
+  template <class T> T* take(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    T* r = reinterpret_cast<T*>(p + off);
+    off += n * sizeof(T);
+    return r;
+  }
+};
+inline size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
+
+// ---------------------------------------------------------------------------------- weights
+struct HostPack {
+  std::vector<float> data;
+  size_t add(const float* src, size_t n) {
+    size_t off = (data.size() + 63) & ~size_t(63);
+    data.resize(off + n);
+    if (src) memcpy(data.data() + off, src, n * sizeof(float));
+    return off;
+  }
+};
+
+size_t add_inv(HostPack& hp, const float* alpha, int n) {
+  size_t off = hp.add(nullptr, n);
+  for (int i = 0; i < n; ++i) hp.data[off + i] = 1.0f / (alpha[i] + 1e-9f);  // (alpha + 1e-9).reciprocal()
+  return off;
+}
+size_t add_transposed(HostPack& hp, const float* w, int C, int k) {  // [C][k] -> [k][C]
+  size_t off = hp.add(nullptr, (size_t)C * k);
+  for (int c = 0; c < C; ++c)
+    for (int j = 0; j < k; ++j) hp.data[off + (size_t)j * C + c] = w[(size_t)c * k + j];
+  return off;
+}
+// ConvTranspose1d weight [Cin][Cout][2s] -> polyphase GEMM operand [s*Cout][2*Cin] (see k_gemm_f32).
+size_t add_convt(HostPack& hp, const float* w, int Cin, int Cout, int s) {
+  const int p = (s + 1) / 2, k = 2 * s;
+  size_t off = hp.add(nullptr, (size_t)s * Cout * 2 * Cin);
+  for (int r = 0; r < s; ++r) {
+    const int k_main = r + p;
+    const int k_side = (r < s - p) ? r + p + s : r + p - s;
+    for (int co = 0; co < Cout; ++co) {
+      float* row = hp.data.data() + off + ((size_t)r * Cout + co) * 2 * Cin;
+      for (int ci = 0; ci < Cin; ++ci) {
+        row[ci] = w[((size_t)ci * Cout + co) * k + k_main];
+        row[Cin + ci] = w[((size_t)ci * Cout + co) * k + k_side];
+      }
+    }
+  }
+  return off;
+}
+
+// ---------------------------------------------------------------------------------- pipeline
+struct NoiseCfg {
+  int mode; const float* tensor; long long stride; uint64_t seed; const unsigned long long* d_keys;
+};
+
+void tap(snacb_engine* e, int stage, const float* p, Rng r, int C, int n_items, bool first_chunk, cudaStream_t st) {
+  if (e->tap_stage != stage || !first_chunk || !e->tap_buf) return;
+  size_t n = (size_t)n_items * r.n() * C;
+  if (n > e->tap_cap) n = e->tap_cap;
+  cudaMemcpyAsync(e->tap_buf, p, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  e->tap_rows = r.n(); e->tap_ch = C; e->tap_lo = r.lo; e->tap_items = n_items;
+}
+
+// Runs one uniform group of items through the layer stack (fp32 recipe).
+int run_group_f32(snacb_engine* e, const Plan& P, const Item* d_items, int n_total, int out_len, Rng tail_out,
+                  const int32_t* c0, const int32_t* c1, const int32_t* c2, int pitch0, const NoiseCfg& nz,
+                  const int32_t* d_status, float* wav, int16_t* pcm, char* ws_free, size_t ws_avail,
+                  cudaStream_t st) {
+  const DevWeights& W = e->w;
+  const size_t Zf = (size_t)P.z.n() * kLatent, Hf = (size_t)P.h.n() * kLatent, S = P.max_stage_floats;
+  const size_t per_item = (pad256(Zf * 4) + pad256(Hf * 4) + 3 * pad256(S * 4)) + 1024;
+  int chunk = e->cfg.chunk_items > 0 ? e->cfg.chunk_items : 32;
+  if ((size_t)chunk * per_item > ws_avail) chunk = (int)(ws_avail / per_item);
+  if (chunk < 1) return fail(e, SNACB_ENOMEM, "workspace too small for one item");
+  const int F = P.T0 / 4;
+  const int noise_off[4] = {0, 32 * F, 288 * F, 1312 * F};
+
+  for (int start = 0; start < n_total; start += chunk) {
+    const int n = std::min(chunk, n_total - start);
+    const bool first = start == 0;
+    Bump bp(ws_free);
+    float* Z = bp.take<float>(Zf * n);
+    float* H0 = bp.take<float>(Hf * n);
+    float* X = bp.take<float>(S * n);
+    float* Y = bp.take<float>(S * n);
+    float* A = bp.take<float>(S * n);
+    GroupCtx g{d_items ? d_items + start : nullptr, start, n, out_len, P.T0, st, &e->launches};
+
+    launch_from_codes(g, W.q, c0, c1, c2, pitch0, P.z, Z);
+    tap(e, 0, Z, P.z, kLatent, n, first, st);
+    {
+      DwArgs d{Z, P.z, H0, P.h, kLatent, 1, 1, W.head_dw_w, W.head_dw_b, nullptr, nullptr, nullptr, nullptr};
+      launch_dwconv(g, d);
+      tap(e, 1, H0, P.h, kLatent, n, first, st);
+    }
+    {
+      GemmArgs a{};
+      a.epi = EPI_BIAS; a.A = H0; a.lda = kLatent; a.a_r = P.h; a.W = W.head_pw_w; a.ldw = kLatent;
+      a.bias = W.head_pw_b; a.K = kLatent; a.N = kDecDim; a.m_r = P.h; a.out = X; a.o_r = P.h; a.ldo = kDecDim;
+      a.up = 1;
+      launch_gemm_f32(g, a);
+      tap(e, 2, X, P.h, kDecDim, n, first, st);
+    }
+    for (int b = 0; b < 4; ++b) {
+      const BlockPlan& B = P.b[b];
+      const BlockDev& Wb = W.blk[b];
+      const int sid = 3 + 9 * b;
+      launch_snake(g, X, A, B.in, B.Cin, Wb.alpha, Wb.inv);
+      tap(e, sid + 0, A, B.in, B.Cin, n, first, st);
+      {
+        GemmArgs a{};
+        a.epi = EPI_CONVT; a.A = A; a.lda = B.Cin; a.a_r = B.in; a.W = Wb.ct_w; a.ldw = 2 * B.Cin;
+        a.bias = Wb.ct_b; a.K = B.Cin; a.N = B.s * B.Cout; a.m_r = B.q; a.s = B.s; a.p = B.p; a.Cout = B.Cout;
+        a.out = Y; a.o_r = B.ct; a.ldo = B.Cout; a.up = B.up_out;
+        launch_gemm_f32(g, a);
+        tap(e, sid + 1, Y, B.ct, B.Cout, n, first, st);
+      }
+      if (nz.mode != SNACB_NOISE_OFF) {
+        GemmArgs a{};
+        a.epi = EPI_NOISE; a.A = Y; a.lda = B.Cout; a.a_r = B.ct; a.W = Wb.noise_w; a.ldw = B.Cout;
+        a.K = B.Cout; a.N = B.Cout; a.m_r = B.ct; a.out = X; a.o_r = B.ct; a.ldo = B.Cout;
+        a.R = Y; a.r_r = B.ct; a.ldr = B.Cout; a.up = B.up_out;
+        a.noise = NoiseSrc{nz.mode, nz.tensor, nz.stride, noise_off[b], (unsigned long long)nz.seed, nz.d_keys, b};
+        launch_gemm_f32(g, a);
+      } else {
+        std::swap(X, Y);  // x + 0 * h == x
+      }
+      tap(e, sid + 2, X, B.ct, B.Cout, n, first, st);
+      Rng cur = B.ct;
+      for (int r = 0; r < 3; ++r) {
+        const RuDev& R = Wb.ru[r];
+        DwArgs d{X, cur, A, B.r[r], B.Cout, kDil[r], B.up_out, R.dw_w, R.dw_b, R.a1, R.i1, R.a2, R.i2};
+        launch_dwconv(g, d);
+        tap(e, sid + 3 + 2 * r, A, B.r[r], B.Cout, n, first, st);
+        GemmArgs a{};
+        a.epi = EPI_RESID; a.A = A; a.lda = B.Cout; a.a_r = B.r[r]; a.W = R.pw_w; a.ldw = B.Cout; a.bias = R.pw_b;
+        a.K = B.Cout; a.N = B.Cout; a.m_r = B.r[r]; a.out = Y; a.o_r = B.r[r]; a.ldo = B.Cout;
+        a.R = X; a.r_r = cur; a.ldr = B.Cout; a.up = B.up_out;
+        launch_gemm_f32(g, a);
+        tap(e, sid + 4 + 2 * r, Y, B.r[r], B.Cout, n, first, st);
+        std::swap(X, Y);
+        cur = B.r[r];
+      }
+    }
+    TailArgs t{X, P.b[3].r[2], tail_out, W.tail_alpha, W.tail_inv, W.tail_w, W.tail_b, d_status, wav, pcm};
+    launch_tail(g, t);
+    int rc = check_launch(e, "layer pipeline");
+    if (rc) return rc;
+  }
+  return SNACB_OK;
+}
+
+int upload_items(snacb_engine* e, const std::vector<Item>& items, Item* d_dst, cudaStream_t st) {
+  if (!e->items_ev) CU(e, cudaEventCreateWithFlags(&e->items_ev, cudaEventDisableTiming));
+  else CU(e, cudaEventSynchronize(e->items_ev));
+  if (items.size() > e->pin_items_cap) {
+    if (e->pin_items) CU(e, cudaFreeHost(e->pin_items));
+    e->pin_items_cap = items.size() * 2 + 64;
+    CU(e, cudaMallocHost((void**)&e->pin_items, e->pin_items_cap * sizeof(Item)));
+  }
+  memcpy(e->pin_items, items.data(), items.size() * sizeof(Item));
+  CU(e, cudaMemcpyAsync(d_dst, e->pin_items, items.size() * sizeof(Item), cudaMemcpyHostToDevice, st));
+  CU(e, cudaEventRecord(e->items_ev, st));
+  return SNACB_OK;
+}
+
+constexpr size_t kActBudget = size_t(6) << 30;  // activation workspace cap per engine
+
+}  // namespace
+
+// ====================================================================================== C ABI
+extern "C" {
+
+int snacb_create(snacb_engine** out, const snacb_config* cfg) {
+  if (!out || !cfg) return fail(nullptr, SNACB_EINVAL, "snacb_create: null argument");
+  if (cfg->abi_version != SNACB_ABI_VERSION) return fail(nullptr, SNACB_EINVAL, "snacb_create: ABI version mismatch");
+  int ndev = 0;
+  cudaError_t c = cudaGetDeviceCount(&ndev);
+  if (c != cudaSuccess || ndev == 0)
+    return fail(nullptr, SNACB_ECUDA, "snacb_create: no CUDA device (%s); there is no CPU fallback",
+                c == cudaSuccess ? "device count 0" : cudaGetErrorString(c));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, SNACB_EINVAL, "snacb_create: bad device ordinal %d", cfg->device);
+  cudaDeviceProp prop{};
+  cudaGetDeviceProperties(&prop, cfg->device);
+  if (prop.major != 10)
+    return fail(nullptr, SNACB_ECUDA, "snacb_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                cfg->device, prop.major, prop.minor);
+  if (cfg->precision != SNACB_PREC_FP32 && cfg->precision != SNACB_PREC_FP16)
+    return fail(nullptr, SNACB_EINVAL, "snacb_create: unknown precision %d", cfg->precision);
+  c = cudaSetDevice(cfg->device);
+  if (c != cudaSuccess) return fail(nullptr, SNACB_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(c));
+  snacb_engine* e = new snacb_engine();
+  e->cfg = *cfg;
+  e->device = cfg->device;
+  *out = e;
+  return SNACB_OK;
+}
+
+void snacb_destroy(snacb_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  if (e->warena) cudaFree(e->warena);
+  if (e->ws) cudaFree(e->ws);
+  if (e->dstage) cudaFree(e->dstage);
+  if (e->pin) cudaFreeHost(e->pin);
+  if (e->pin_items) cudaFreeHost(e->pin_items);
+  if (e->items_ev) cudaEventDestroy(e->items_ev);
+  delete e;
+}
+
+const char* snacb_last_error(const snacb_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+size_t snacb_workspace_bytes(const snacb_engine* e) { return e ? e->ws_bytes + e->dstage_bytes : 0; }
+
+int64_t snacb_launch_count(const snacb_engine* e) { return e ? e->launches : 0; }
+
+int snacb_load_weights(snacb_engine* e, const snacb_weights* w) {
+  if (!e || !w) return fail(e, SNACB_EINVAL, "snacb_load_weights: null argument");
+  CU(e, cudaSetDevice(e->device));
+  HostPack hp;
+  struct Fix { float** dst; size_t off; };
+  std::vector<Fix> fix;
+  DevWeights& D = e->w;
+  auto put = [&](float** dst, const float* src, size_t n) { fix.push_back({dst, hp.add(src, n)}); };
+  const float* must[] = {w->head_dw_w, w->head_dw_b, w->head_pw_w, w->head_pw_b, w->tail_alpha, w->tail_w, w->tail_b};
+  for (const float* p : must) if (!p) return fail(e, SNACB_EINVAL, "snacb_load_weights: null tensor");
+  for (int l = 0; l < 3; ++l) {
+    if (!w->codebook[l] || !w->outproj_w[l] || !w->outproj_b[l]) return fail(e, SNACB_EINVAL, "snacb_load_weights: null quantizer tensor");
+    put(const_cast<float**>(&D.q.codebook[l]), w->codebook[l], (size_t)SNACB_CODEBOOK_SIZE * 8);
+    put(const_cast<float**>(&D.q.w[l]), w->outproj_w[l], (size_t)kLatent * 8);
+    put(const_cast<float**>(&D.q.b[l]), w->outproj_b[l], kLatent);
+  }
+  fix.push_back({&D.head_dw_w, add_transposed(hp, w->head_dw_w, kLatent, 7)});
+  put(&D.head_dw_b, w->head_dw_b, kLatent);
+  put(&D.head_pw_w, w->head_pw_w, (size_t)kDecDim * kLatent);
+  put(&D.head_pw_b, w->head_pw_b, kDecDim);
+  int cin = kDecDim;
+  for (int b = 0; b < 4; ++b) {
+    const snacb_block_weights& s = w->block[b];
+    const int cout = cin / 2, st = kRates[b];
+    if (!s.alpha || !s.convt_w || !s.convt_b || !s.noise_w) return fail(e, SNACB_EINVAL, "snacb_load_weights: null block tensor");
+    put(&D.blk[b].alpha, s.alpha, cin);
+    fix.push_back({&D.blk[b].inv, add_inv(hp, s.alpha, cin)});
+    fix.push_back({&D.blk[b].ct_w, add_convt(hp, s.convt_w, cin, cout, st)});
+    put(&D.blk[b].ct_b, s.convt_b, cout);
+    put(&D.blk[b].noise_w, s.noise_w, (size_t)cout * cout);
+    for (int r = 0; r < 3; ++r) {
+      const snacb_ru_weights& u = s.ru[r];
+      RuDev& R = D.blk[b].ru[r];
+      if (!u.alpha1 || !u.dw_w || !u.dw_b || !u.alpha2 || !u.pw_w || !u.pw_b) return fail(e, SNACB_EINVAL, "snacb_load_weights: null RU tensor");
+      put(&R.a1, u.alpha1, cout);
+      fix.push_back({&R.i1, add_inv(hp, u.alpha1, cout)});
+      fix.push_back({&R.dw_w, add_transposed(hp, u.dw_w, cout, 7)});
+      put(&R.dw_b, u.dw_b, cout);
+      put(&R.a2, u.alpha2, cout);
+      fix.push_back({&R.i2, add_inv(hp, u.alpha2, cout)});
+      put(&R.pw_w, u.pw_w, (size_t)cout * cout);
+      put(&R.pw_b, u.pw_b, cout);
+    }
+    cin = cout;
+  }
+  put(&D.tail_alpha, w->tail_alpha, 64);
+  fix.push_back({&D.tail_inv, add_inv(hp, w->tail_alpha, 64)});
+  fix.push_back({&D.tail_w, add_transposed(hp, w->tail_w, 64, 7)});
+  put(&D.tail_b, w->tail_b, 1);
+
+  const size_t bytes = hp.data.size() * sizeof(float);
+  CU(e, cudaDeviceSynchronize());
+  if (e->warena) { CU(e, cudaFree(e->warena)); e->warena = nullptr; }
+  CU(e, cudaMalloc(&e->warena, bytes));
+  e->warena_bytes = bytes;
+  CU(e, cudaMemcpy(e->warena, hp.data.data(), bytes, cudaMemcpyHostToDevice));
+  for (const Fix& f : fix) *f.dst = reinterpret_cast<float*>(e->warena) + f.off;
+  e->loaded = true;
+  return SNACB_OK;
+}
+
+static int deinterleave_common(snacb_engine* e, const int32_t* d_tokens, int32_t tokens_stride, const int32_t* h_ntok,
+                               int32_t ntok_uniform, int32_t n_win, int32_t max_frames, bool raw, int32_t* d_c0,
+                               int32_t* d_c1, int32_t* d_c2, int32_t* d_status, void* stream) {
+  if (!e) return SNACB_EINVAL;
+  if (n_win < 0 || max_frames < 1 || !d_tokens || !d_c0 || !d_c1 || !d_c2 || !d_status)
+    return fail(e, SNACB_EINVAL, "snacb_deinterleave: bad argument");
+  if (n_win == 0) return SNACB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(e, cudaSetDevice(e->device));
+  const int32_t* d_ntok = nullptr;
+  if (h_ntok) {
+    for (int i = 0; i < n_win; ++i)
+      if (h_ntok[i] < 0 || h_ntok[i] > tokens_stride) return fail(e, SNACB_EINVAL, "snacb_deinterleave: ntok[%d] out of range", i);
+    const size_t need = pad256((size_t)n_win * 4);
+    if (need > e->dstage_bytes) {
+      CU(e, cudaDeviceSynchronize());
+      if (e->dstage) CU(e, cudaFree(e->dstage));
+      e->dstage_bytes = need * 2;
+      CU(e, cudaMalloc((void**)&e->dstage, e->dstage_bytes));
+    }
+    CU(e, cudaMemcpyAsync(e->dstage, h_ntok, (size_t)n_win * 4, cudaMemcpyHostToDevice, st));
+    d_ntok = reinterpret_cast<const int32_t*>(e->dstage);
+  } else if (ntok_uniform < 0 || ntok_uniform > tokens_stride) {
+    return fail(e, SNACB_EINVAL, "snacb_deinterleave: ntok_uniform out of range");
+  }
+  launch_deinterleave(d_tokens, tokens_stride, d_ntok, ntok_uniform, n_win, max_frames, raw, d_c0, d_c1, d_c2,
+                      d_status, st, &e->launches);
+  return check_launch(e, "deinterleave");
+}
+
+int snacb_deinterleave(snacb_engine* e, const int32_t* d_tokens, int32_t tokens_stride, const int32_t* h_ntok,
+                       int32_t ntok_uniform, int32_t n_win, int32_t max_frames, int32_t* d_c0, int32_t* d_c1,
+                       int32_t* d_c2, int32_t* d_status, void* stream) {
+  return deinterleave_common(e, d_tokens, tokens_stride, h_ntok, ntok_uniform, n_win, max_frames, false, d_c0, d_c1,
+                             d_c2, d_status, stream);
+}
+
+int snacb_deinterleave_raw(snacb_engine* e, const int32_t* d_raw, int32_t tokens_stride, const int32_t* h_ntok,
+                           int32_t ntok_uniform, int32_t n_win, int32_t max_frames, int32_t* d_c0, int32_t* d_c1,
+                           int32_t* d_c2, int32_t* d_status, void* stream) {
+  return deinterleave_common(e, d_raw, tokens_stride, h_ntok, ntok_uniform, n_win, max_frames, true, d_c0, d_c1, d_c2,
+                             d_status, stream);
+}
+
+int snacb_decode_windows(snacb_engine* e, const int32_t* d_tokens, int32_t tokens_stride, const int32_t* h_ntok,
+                         int32_t ntok_uniform, int32_t n_win, int32_t noise_mode, const float* d_noise,
+                         int64_t noise_stride, uint64_t seed, const uint64_t* h_keys, int16_t* d_pcm,
+                         int32_t* d_status, void* stream) {
+  if (!e) return SNACB_EINVAL;
+  if (!e->loaded) return fail(e, SNACB_ESTATE, "snacb_decode_windows: weights not loaded");
+  if (n_win < 0 || !d_tokens || !d_pcm || !d_status) return fail(e, SNACB_EINVAL, "snacb_decode_windows: bad argument");
+  if (noise_mode < 0 || noise_mode > 2 || (noise_mode == SNACB_NOISE_TENSOR && !d_noise))
+    return fail(e, SNACB_EINVAL, "snacb_decode_windows: bad noise arguments");
+  if (n_win == 0) return SNACB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(e, cudaSetDevice(e->device));
+
+  // frame counts per window (host metadata)
+  int maxF = 1;
+  std::map<int, std::vector<int>> groups;  // F -> windows
+  if (h_ntok) {
+    for (int i = 0; i < n_win; ++i) {
+      if (h_ntok[i] < 0 || h_ntok[i] > tokens_stride) return fail(e, SNACB_EINVAL, "ntok[%d] out of range", i);
+      const int F = h_ntok[i] / 7;
+      maxF = std::max(maxF, F);
+      if (F >= 2) groups[F].push_back(i);
+    }
+  } else {
+    if (ntok_uniform < 0 || ntok_uniform > tokens_stride) return fail(e, SNACB_EINVAL, "ntok_uniform out of range");
+    maxF = std::max(1, ntok_uniform / 7);
+  }
+  if (noise_mode == SNACB_NOISE_TENSOR && noise_stride < (int64_t)kNoisePerFrame * maxF)
+    return fail(e, SNACB_EINVAL, "noise_stride %lld < 3360*%d", (long long)noise_stride, maxF);
+
+  // fixed part of the workspace: codes, ntok, keys, item tables
+  const size_t codes_b = pad256((size_t)n_win * maxF * 4) + pad256((size_t)n_win * maxF * 8) + pad256((size_t)n_win * maxF * 16);
+  const size_t fixed = codes_b + 3 * pad256((size_t)n_win * 16) + 4096;
+  // activation part: sized for the largest group plan
+  size_t act = 0;
+  std::vector<int> Fs;
+  if (h_ntok) for (auto& kv : groups) Fs.push_back(kv.first); else if (maxF >= 2) Fs.push_back(maxF);
+  const Rng slice{2048, 4096};
+  for (int F : Fs) {
+    Plan P = make_plan(4 * F, e->cfg.trim ? slice : Rng{0, 2048 * F}, true);
+    const size_t per_item = pad256((size_t)P.z.n() * kLatent * 4) + pad256((size_t)P.h.n() * kLatent * 4) + 3 * pad256(P.max_stage_floats * 4) + 1024;
+    const int cnt = h_ntok ? (int)groups[F].size() : n_win;
+    const int chunk = std::min(cnt, e->cfg.chunk_items > 0 ? e->cfg.chunk_items : 32);
+    act = std::max(act, std::min(kActBudget, per_item * chunk));
+    act = std::max(act, per_item);
+  }
+  int rc = ensure_ws(e, fixed + act, st);
+  if (rc) return rc;
+  Bump bp(e->ws);
+  int32_t* c0 = bp.take<int32_t>((size_t)n_win * maxF);
+  int32_t* c1 = bp.take<int32_t>((size_t)n_win * maxF * 2);
+  int32_t* c2 = bp.take<int32_t>((size_t)n_win * maxF * 4);
+  int32_t* d_ntok = bp.take<int32_t>(n_win);
+  unsigned long long* d_keys = bp.take<unsigned long long>(n_win);
+  Item* d_items = bp.take<Item>(n_win);
+  char* ws_free = e->ws + pad256(bp.off);
+  const size_t ws_avail = e->ws_bytes - pad256(bp.off);
+
+  if (h_ntok) CU(e, cudaMemcpyAsync(d_ntok, h_ntok, (size_t)n_win * 4, cudaMemcpyHostToDevice, st));
+  const unsigned long long* keys = nullptr;
+  if (noise_mode == SNACB_NOISE_PHILOX && h_keys) {
+    CU(e, cudaMemcpyAsync(d_keys, h_keys, (size_t)n_win * 8, cudaMemcpyHostToDevice, st));
+    keys = d_keys;
+  }
+  launch_deinterleave(d_tokens, tokens_stride, h_ntok ? d_ntok : nullptr, ntok_uniform, n_win, maxF, false, c0, c1, c2,
+                      d_status, st, &e->launches);
+  CU(e, cudaMemsetAsync(d_pcm, 0, (size_t)n_win * 2048 * sizeof(int16_t), st));
+  NoiseCfg nz{noise_mode, d_noise, (long long)noise_stride, seed, keys};
+
+  if (!h_ntok) {
+    if (maxF >= 2 && ntok_uniform >= 14) {
+      Plan P = make_plan(4 * maxF, e->cfg.trim ? slice : Rng{0, 2048 * maxF}, true);
+      rc = run_group_f32(e, P, nullptr, n_win, 2048, slice, c0, c1, c2, maxF, nz, d_status, nullptr, d_pcm, ws_free, ws_avail, st);
+      if (rc) return rc;
+    }
+  } else {
+    size_t used = 0;
+    std::vector<Item> all;
+    std::vector<std::pair<int, std::pair<size_t, int>>> runs;  // F, (offset, count)
+    for (auto& kv : groups) {
+      runs.push_back({kv.first, {all.size(), (int)kv.second.size()}});
+      for (int i : kv.second) all.push_back(Item{i, 0, (int64_t)i * 2048});
+    }
+    (void)used;
+    if (!all.empty()) {
+      rc = upload_items(e, all, d_items, st);
+      if (rc) return rc;
+      for (auto& r : runs) {
+        Plan P = make_plan(4 * r.first, e->cfg.trim ? slice : Rng{0, 2048 * r.first}, true);
+        rc = run_group_f32(e, P, d_items + r.second.first, r.second.second, 2048, slice, c0, c1, c2, maxF, nz, d_status,
+                           nullptr, d_pcm, ws_free, ws_avail, st);
+        if (rc) return rc;
+      }
+    }
+  }
+  return check_launch(e, "decode_windows");
+}
+
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+int snacb_decode_windows_host(snacb_engine* e, const int32_t* h_tokens, int32_t tokens_stride, const int32_t* h_ntok,
+                              int32_t ntok_uniform, int32_t n_win, int32_t noise_mode, const float* h_noise,
+                              int64_t noise_stride, uint64_t seed, const uint64_t* h_keys, int16_t* h_pcm,
+                              int32_t* h_status, void* stream) {
+  if (!e) return SNACB_EINVAL;
+  if (n_win < 0 || !h_tokens || !h_pcm || !h_status) return fail(e, SNACB_EINVAL, "snacb_decode_windows_host: bad argument");
+  if (n_win == 0) return SNACB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(e, cudaSetDevice(e->device));
+  const size_t tok_b = pad256((size_t)n_win * tokens_stride * 4);
+  const size_t pcm_b = pad256((size_t)n_win * 4096);
+  const size_t st_b = pad256((size_t)n_win * 4);
+  const size_t nz_b = (noise_mode == SNACB_NOISE_TENSOR && h_noise) ? pad256((size_t)n_win * noise_stride * 4) : 0;
+  const size_t total = tok_b + pcm_b + st_b + nz_b;
+  if (total > e->pin_bytes) {
+    CU(e, cudaStreamSynchronize(st));
+    if (e->pin) CU(e, cudaFreeHost(e->pin));
+    e->pin_bytes = total + total / 2;
+    CU(e, cudaMallocHost((void**)&e->pin, e->pin_bytes));
+  }
+  // device staging lives in its own allocation (the workspace may be re-allocated by the decode)
+  static_assert(sizeof(int32_t) == 4, "");
+  if (total > e->dstage_bytes) {
+    CU(e, cudaDeviceSynchronize());
+    if (e->dstage) CU(e, cudaFree(e->dstage));
+    e->dstage_bytes = total + total / 2;
+    CU(e, cudaMalloc((void**)&e->dstage, e->dstage_bytes));
+  }
+  char* hp = e->pin; char* dp = e->dstage;
+  const bool tok_pinned = is_pinned(h_tokens), pcm_pinned = is_pinned(h_pcm);
+  int32_t* d_tok = reinterpret_cast<int32_t*>(dp);
+  int16_t* d_pcm = reinterpret_cast<int16_t*>(dp + tok_b);
+  int32_t* d_st = reinterpret_cast<int32_t*>(dp + tok_b + pcm_b);
+  float* d_nz = nz_b ? reinterpret_cast<float*>(dp + tok_b + pcm_b + st_b) : nullptr;
+  const void* src_tok = h_tokens;
+  if (!tok_pinned) { memcpy(hp, h_tokens, (size_t)n_win * tokens_stride * 4); src_tok = hp; }
+  CU(e, cudaMemcpyAsync(d_tok, src_tok, (size_t)n_win * tokens_stride * 4, cudaMemcpyHostToDevice, st));
+  if (nz_b) {
+    memcpy(hp + tok_b + pcm_b + st_b, h_noise, (size_t)n_win * noise_stride * 4);
+    CU(e, cudaMemcpyAsync(d_nz, hp + tok_b + pcm_b + st_b, (size_t)n_win * noise_stride * 4, cudaMemcpyHostToDevice, st));
+  }
+  // NOTE: snacb_decode_windows uses e->dstage for nothing (ntok goes to the workspace), so the staging is stable.
+  int rc = snacb_decode_windows(e, d_tok, tokens_stride, h_ntok, ntok_uniform, n_win, noise_mode, d_nz, noise_stride, seed,
+                                h_keys, d_pcm, d_st, stream);
+  if (rc) return rc;
+  void* dst_pcm = pcm_pinned ? (void*)h_pcm : (void*)(hp + tok_b);
+  CU(e, cudaMemcpyAsync(dst_pcm, d_pcm, (size_t)n_win * 4096, cudaMemcpyDeviceToHost, st));
+  CU(e, cudaMemcpyAsync(hp + tok_b + pcm_b, d_st, (size_t)n_win * 4, cudaMemcpyDeviceToHost, st));
+  CU(e, cudaStreamSynchronize(st));
+  if (!pcm_pinned) memcpy(h_pcm, hp + tok_b, (size_t)n_win * 4096);
+  memcpy(h_status, hp + tok_b + pcm_b, (size_t)n_win * 4);
+  return SNACB_OK;
+}
+
+int snacb_decode_codes(snacb_engine* e, const int32_t* d_c0, const int32_t* d_c1, const int32_t* d_c2, int32_t B,
+                       int32_t F, int32_t noise_mode, const float* d_noise, uint64_t seed, float* d_wav, int16_t* d_pcm,
+                       void* stream) {
+  if (!e) return SNACB_EINVAL;
+  if (!e->loaded) return fail(e, SNACB_ESTATE, "snacb_decode_codes: weights not loaded");
+  if (B < 0 || F < 1 || !d_c0 || !d_c1 || !d_c2 || (!d_wav && !d_pcm)) return fail(e, SNACB_EINVAL, "snacb_decode_codes: bad argument");
+  if (noise_mode < 0 || noise_mode > 2 || (noise_mode == SNACB_NOISE_TENSOR && !d_noise))
+    return fail(e, SNACB_EINVAL, "snacb_decode_codes: bad noise arguments");
+  if (B == 0) return SNACB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(e, cudaSetDevice(e->device));
+  NoiseCfg nz{noise_mode, d_noise, (long long)kNoisePerFrame * F, seed, nullptr};
+  const int kTileFrames = 8;
+  if (F <= 2 * kTileFrames) {
+    Plan P = make_plan(4 * F, Rng{0, 2048 * F}, true);
+    const size_t per_item = pad256((size_t)P.z.n() * kLatent * 4) + pad256((size_t)P.h.n() * kLatent * 4) + 3 * pad256(P.max_stage_floats * 4) + 1024;
+    const int chunk = std::min((int)B, e->cfg.chunk_items > 0 ? e->cfg.chunk_items : 32);
+    int rc = ensure_ws(e, std::max(per_item, std::min(kActBudget, per_item * chunk)) + 4096, st);
+    if (rc) return rc;
+    return run_group_f32(e, P, nullptr, B, 2048 * F, P.out, d_c0, d_c1, d_c2, F, nz, nullptr, d_wav, d_pcm, e->ws, e->ws_bytes, st);
+  }
+  // long sequence: uniform time tiles with halo recompute; rows outside [0, T) are explicit zeros.
+  const int tiles = (F + kTileFrames - 1) / kTileFrames;
+  std::vector<Item> items;
+  items.reserve((size_t)B * tiles);
+  for (int b = 0; b < B; ++b)
+    for (int k = 0; k < tiles; ++k)
+      items.push_back(Item{b, k * kTileFrames * 4, (int64_t)b * 2048 * F + (int64_t)k * kTileFrames * 2048});
+  Plan P = make_plan(4 * F, Rng{0, 2048 * kTileFrames}, false);
+  const size_t per_item = pad256((size_t)P.z.n() * kLatent * 4) + pad256((size_t)P.h.n() * kLatent * 4) + 3 * pad256(P.max_stage_floats * 4) + 1024;
+  const int chunk = std::min((int)items.size(), e->cfg.chunk_items > 0 ? e->cfg.chunk_items : 32);
+  const size_t tab = pad256(items.size() * sizeof(Item)) + 256;
+  int rc = ensure_ws(e, tab + std::max(per_item, std::min(kActBudget, per_item * chunk)) + 4096, st);
+  if (rc) return rc;
+  Item* d_items = reinterpret_cast<Item*>(e->ws);
+  rc = upload_items(e, items, d_items, st);
+  if (rc) return rc;
+  return run_group_f32(e, P, d_items, (int)items.size(), 2048 * kTileFrames, P.out, d_c0, d_c1, d_c2, F, nz, nullptr, d_wav,
+                       d_pcm, e->ws + tab, e->ws_bytes - tab, st);
+}
+
+int snacb_fill_noise(snacb_engine* e, uint64_t seed, const uint64_t* h_keys, int32_t n_win, int32_t F, float* d_noise,
+                     int64_t noise_stride, void* stream) {
+  if (!e) return SNACB_EINVAL;
+  if (n_win < 0 || F < 1 || !d_noise || noise_stride < (int64_t)kNoisePerFrame * F) return fail(e, SNACB_EINVAL, "snacb_fill_noise: bad argument");
+  if (n_win == 0) return SNACB_OK;
+  if (n_win > 65535) return fail(e, SNACB_EINVAL, "snacb_fill_noise: at most 65535 windows per call");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(e, cudaSetDevice(e->device));
+  const unsigned long long* keys = nullptr;
+  if (h_keys) {
+    int rc = ensure_ws(e, pad256((size_t)n_win * 8), st);
+    if (rc) return rc;
+    CU(e, cudaMemcpyAsync(e->ws, h_keys, (size_t)n_win * 8, cudaMemcpyHostToDevice, st));
+    keys = reinterpret_cast<const unsigned long long*>(e->ws);
+  }
+  launch_fill_noise(seed, keys, n_win, F, d_noise, (long long)noise_stride, st, &e->launches);
+  return check_launch(e, "fill_noise");
+}
+
+int snacb_set_tap(snacb_engine* e, int32_t stage, float* d_buf, size_t capacity_floats) {
+  if (!e) return SNACB_EINVAL;
+  e->tap_stage = stage; e->tap_buf = d_buf; e->tap_cap = capacity_floats;
+  e->tap_rows = e->tap_ch = e->tap_lo = e->tap_items = 0;
+  return SNACB_OK;
+}
+
+int snacb_get_tap_shape(const snacb_engine* e, int32_t* rows, int32_t* channels, int32_t* t_lo, int32_t* items) {
+  if (!e) return SNACB_EINVAL;
+  if (rows) *rows = e->tap_rows;
+  if (channels) *channels = e->tap_ch;
+  if (t_lo) *t_lo = e->tap_lo;
+  if (items) *items = e->tap_items;
+  return SNACB_OK;
+}
+
+int snacb_plan(int32_t frames, int32_t out_lo, int32_t out_hi, int32_t clip, int32_t* ranges) {
+  if (frames < 1 || out_hi <= out_lo || !ranges) return SNACB_EINVAL;
+  const Plan P = make_plan(4 * frames, Rng{out_lo, out_hi}, clip != 0);
+  int k = 0;
+  auto put = [&](Rng r) { ranges[k++] = r.lo; ranges[k++] = r.hi; };
+  put(P.z); put(P.h);
+  for (int b = 0; b < 4; ++b) {
+    put(P.b[b].in); put(P.b[b].q); put(P.b[b].ct);
+    put(P.b[b].r[0]); put(P.b[b].r[1]); put(P.b[b].r[2]);
+  }
+  return SNACB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,77 @@
+// Launcher declarations shared by engine.cu and the kernel translation units.
+#pragma once
+#include "snacb_common.cuh"
+
+namespace snacb {
+
+// Group-wide context handed to every launcher.
+struct GroupCtx {
+  const Item* items;  // device pointer already offset to the chunk's first item, or nullptr
+  int base;           // implicit-item base row (chunk start) when items == nullptr
+  int n_items;        // items in this chunk
+  int out_len;        // samples per item in the destination (implicit dst = row * out_len)
+  int T0;             // latent steps of the whole sequence
+  cudaStream_t stream;
+  int64_t* launches;  // launch counter
+};
+
+// ---- integer kernel ------------------------------------------------------------------------
+void launch_deinterleave(const int32_t* d_tokens, int tokens_stride, const int32_t* d_ntok,
+                         int ntok_uniform, int n_win, int max_frames, bool raw, int32_t* c0,
+                         int32_t* c1, int32_t* c2, int32_t* status, cudaStream_t st, int64_t* launches);
+
+// ---- fp32 CUDA-core layer kernels ------------------------------------------------------------
+struct QuantW {
+  const float* codebook[3];
+  const float* w[3];  // [768][8]
+  const float* b[3];  // [768]
+};
+void launch_from_codes(const GroupCtx& g, const QuantW& q, const int32_t* c0, const int32_t* c1,
+                       const int32_t* c2, int pitch0, Rng z, float* out);
+
+struct DwArgs {
+  const float* in; Rng in_r;
+  float* out; Rng out_r;
+  int C, dil, up;
+  const float* w7;  // [7][C]
+  const float* bias;
+  const float* a1; const float* i1;  // pre-Snake alpha, 1/(alpha+1e-9); nullptr = none
+  const float* a2; const float* i2;  // post-Snake
+};
+void launch_dwconv(const GroupCtx& g, const DwArgs& a);
+
+void launch_snake(const GroupCtx& g, const float* in, float* out, Rng r, int C, const float* alpha,
+                  const float* inv);
+
+enum { EPI_BIAS = 0, EPI_RESID = 1, EPI_NOISE = 2, EPI_CONVT = 3 };
+struct GemmArgs {
+  int epi;
+  const float* A; int lda; Rng a_r;   // operand rows (per item) and its K-major row pitch
+  const float* W; int ldw;            // [N][ldw]
+  const float* bias;                  // [N] (EPI_CONVT: [Cout])
+  int K, N;
+  Rng m_r;                            // rows iterated per item (EPI_CONVT: positions q)
+  int s, p, Cout;                     // EPI_CONVT only
+  float* out; Rng o_r; int ldo;
+  const float* R; Rng r_r; int ldr;   // EPI_RESID residual / EPI_NOISE carrier x
+  NoiseSrc noise;
+  int up;                             // time scale of the OUTPUT rows
+};
+void launch_gemm_f32(const GroupCtx& g, const GemmArgs& a);
+
+struct TailArgs {
+  const float* x; Rng x_r;  // [item][rows][64]
+  Rng out_r;
+  const float* alpha; const float* inv;
+  const float* w7;  // [7][64]
+  const float* bias;  // [1]
+  const int32_t* status;  // per code_row; nullptr or skip rows whose status != 0
+  float* wav;   // nullable
+  int16_t* pcm; // nullable
+};
+void launch_tail(const GroupCtx& g, const TailArgs& a);
+
+void launch_fill_noise(uint64_t seed, const unsigned long long* d_keys, int n_win, int F, float* d_noise,
+                       long long stride, cudaStream_t st, int64_t* launches);
+
+}  // namespace snacb

@@ -1,0 +1,256 @@
+"""Python handle over the C-ABI engine: one ``SnacEngine`` per GPU.
+
+PyTorch is plumbing here (device tensors, streams); every number is produced by
+``libsnacb.so``.  Replaces the module-global ``model`` + ``model.decode`` of
+``/root/reference/Morpheus_Client/tts_engine/speechpipe.py:43-49,118``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from .weights import FoldedWeights
+
+NoiseArg = Union[str, torch.Tensor, np.ndarray, None]
+SAMPLES_PER_FRAME = 2048
+SLICE_SAMPLES = 2048
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class SnacEngine:
+    """Owns packed weights + workspace on one CUDA device; not re-entrant."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device: int = 0, precision: str = "fp16",
+                 chunk_items: int = 0, trim: bool = True):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        if not torch.cuda.is_available():
+            raise _lib.SnacbError("no CUDA device: the SNAC decode path has no CPU fallback")
+        self.device = int(device)
+        self.torch_device = torch.device("cuda", self.device)
+        self.precision = precision
+        prec = {"fp32": _lib.PREC_FP32, "fp16": _lib.PREC_FP16}[precision]
+        cfg = _lib.Config(abi_version=_lib.ABI_VERSION, device=self.device, precision=prec,
+                          chunk_items=int(chunk_items), trim=1 if trim else 0)
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            torch.zeros(1, device=self.torch_device)  # make sure the primary context exists
+            rc = self._lib.snacb_create(C.byref(self._h), C.byref(cfg))
+        if rc != _lib.OK:
+            msg = self._lib.snacb_last_error(None)
+            self._h = C.c_void_p()
+            raise _lib.SnacbError(f"snacb_create failed ({rc}): {msg.decode() if msg else ''}")
+        self._pin: Dict[str, torch.Tensor] = {}
+        self.load_state_dict(state_dict)
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.snacb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str) -> None:
+        _lib.check(self._lib, self._h, rc, what)
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        fw = sd if isinstance(sd, FoldedWeights) else FoldedWeights(sd)
+        t = fw.tensors
+        f32p = C.POINTER(C.c_float)
+
+        def p(name):
+            return C.cast(t[name].data_ptr(), f32p)
+
+        w = _lib.Weights()
+        for i in range(3):
+            w.codebook[i], w.outproj_w[i], w.outproj_b[i] = p(f"codebook{i}"), p(f"outproj_w{i}"), p(f"outproj_b{i}")
+        w.head_dw_w, w.head_dw_b, w.head_pw_w, w.head_pw_b = p("head_dw_w"), p("head_dw_b"), p("head_pw_w"), p("head_pw_b")
+        for b in range(4):
+            blk = w.block[b]
+            blk.alpha, blk.convt_w, blk.convt_b, blk.noise_w = p(f"b{b}_alpha"), p(f"b{b}_convt_w"), p(f"b{b}_convt_b"), p(f"b{b}_noise_w")
+            for r in range(3):
+                ru = blk.ru[r]
+                for fld in ("alpha1", "dw_w", "dw_b", "alpha2", "pw_w", "pw_b"):
+                    setattr(ru, fld, p(f"b{b}_r{r}_{fld}"))
+        w.tail_alpha, w.tail_w, w.tail_b = p("tail_alpha"), p("tail_w"), p("tail_b")
+        self._check(self._lib.snacb_load_weights(self._h, C.byref(w)), "snacb_load_weights")
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.torch_device).cuda_stream
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.snacb_launch_count(self._h))
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self._lib.snacb_workspace_bytes(self._h))
+
+    def _pinned(self, key: str, shape, dtype) -> torch.Tensor:
+        n = int(np.prod(shape))
+        buf = self._pin.get(key)
+        if buf is None or buf.numel() < n or buf.dtype != dtype:
+            buf = torch.empty(max(n, 1), dtype=dtype, pin_memory=True)
+            self._pin[key] = buf
+        return buf[:n].view(*shape)
+
+    @staticmethod
+    def _noise_mode(noise: NoiseArg) -> int:
+        if noise is None or (isinstance(noise, str) and noise == "off"):
+            return _lib.NOISE_OFF
+        if isinstance(noise, str):
+            if noise != "philox":
+                raise ValueError(f"unknown noise mode {noise!r}")
+            return _lib.NOISE_PHILOX
+        return _lib.NOISE_TENSOR
+
+    # ------------------------------------------------------------------ NS-1
+    def deinterleave(self, tokens: torch.Tensor, ntok: Optional[Sequence[int]] = None, raw: bool = False,
+                     max_frames: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+        """tokens: cuda int32 [n, stride] -> (c0 [n,F], c1 [n,2F], c2 [n,4F], status [n]) on device."""
+        assert tokens.is_cuda and tokens.dtype == torch.int32 and tokens.dim() == 2 and tokens.is_contiguous()
+        n, stride = tokens.shape
+        nt = None
+        if ntok is not None:
+            nt = np.ascontiguousarray(np.asarray(ntok, dtype=np.int32))
+            assert nt.shape == (n,)
+        mf = max_frames or max(1, (int(nt.max()) if nt is not None and n else stride) // 7)
+        c0 = torch.empty((n, mf), dtype=torch.int32, device=tokens.device)
+        c1 = torch.empty((n, 2 * mf), dtype=torch.int32, device=tokens.device)
+        c2 = torch.empty((n, 4 * mf), dtype=torch.int32, device=tokens.device)
+        status = torch.empty((n,), dtype=torch.int32, device=tokens.device)
+        fn = self._lib.snacb_deinterleave_raw if raw else self._lib.snacb_deinterleave
+        rc = fn(self._h, tokens.data_ptr(), stride, nt.ctypes.data if nt is not None else None, stride, n, mf,
+                c0.data_ptr(), c1.data_ptr(), c2.data_ptr(), status.data_ptr(), self._stream())
+        self._check(rc, "snacb_deinterleave")
+        return c0, c1, c2, status
+
+    # ------------------------------------------------------------------ streaming path
+    def decode_windows_device(self, tokens: torch.Tensor, ntok: Optional[Sequence[int]] = None,
+                              noise: NoiseArg = "philox", seed: int = 0, keys: Optional[Sequence[int]] = None,
+                              pcm: Optional[torch.Tensor] = None, status: Optional[torch.Tensor] = None
+                              ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Device-resident tick: tokens cuda int32 [n, stride] -> (pcm int16 [n,2048], status int32 [n])."""
+        assert tokens.is_cuda and tokens.dtype == torch.int32 and tokens.dim() == 2 and tokens.is_contiguous()
+        n, stride = tokens.shape
+        if pcm is None:
+            pcm = torch.empty((n, SLICE_SAMPLES), dtype=torch.int16, device=tokens.device)
+        if status is None:
+            status = torch.empty((n,), dtype=torch.int32, device=tokens.device)
+        nt = None
+        if ntok is not None:
+            nt = np.ascontiguousarray(np.asarray(ntok, dtype=np.int32))
+        mode = self._noise_mode(noise)
+        nz_ptr, nz_stride = None, 0
+        if mode == _lib.NOISE_TENSOR:
+            nz = noise if isinstance(noise, torch.Tensor) else torch.from_numpy(np.asarray(noise, dtype=np.float32))
+            nz = nz.to(device=tokens.device, dtype=torch.float32).contiguous()
+            assert nz.dim() == 2 and nz.shape[0] == n
+            self._keep = nz
+            nz_ptr, nz_stride = nz.data_ptr(), nz.shape[1]
+        kp = None
+        if keys is not None:
+            kp = np.ascontiguousarray(np.asarray(keys, dtype=np.uint64))
+        rc = self._lib.snacb_decode_windows(self._h, tokens.data_ptr(), stride, nt.ctypes.data if nt is not None else None,
+                                            stride, n, mode, nz_ptr, nz_stride, int(seed) & (2**64 - 1),
+                                            kp.ctypes.data if kp is not None else None, pcm.data_ptr(),
+                                            status.data_ptr(), self._stream())
+        self._check(rc, "snacb_decode_windows")
+        return pcm, status
+
+    def decode_windows(self, tokens, ntok: Optional[Sequence[int]] = None, noise: NoiseArg = "philox", seed: int = 0,
+                       keys: Optional[Sequence[int]] = None) -> Tuple[np.ndarray, np.ndarray]:
+        """Host tick (the call ``convert_to_audio[_batch]`` makes): tokens int32 [n, stride] host array
+        -> (pcm int16 [n,2048], status int32 [n]) numpy views of pinned buffers (valid until the next call)."""
+        tok = np.ascontiguousarray(np.asarray(tokens, dtype=np.int32))
+        assert tok.ndim == 2
+        n, stride = tok.shape
+        h_tok = self._pinned("tok", (n, stride), torch.int32)
+        h_tok.numpy()[...] = tok
+        h_pcm = self._pinned("pcm", (n, SLICE_SAMPLES), torch.int16)
+        h_st = self._pinned("status", (n,), torch.int32)
+        nt = None
+        if ntok is not None:
+            nt = np.ascontiguousarray(np.asarray(ntok, dtype=np.int32))
+        mode = self._noise_mode(noise)
+        nz_ptr, nz_stride = None, 0
+        if mode == _lib.NOISE_TENSOR:
+            nz = noise.detach().cpu().numpy() if isinstance(noise, torch.Tensor) else np.asarray(noise)
+            nz = np.ascontiguousarray(nz, dtype=np.float32)
+            assert nz.ndim == 2 and nz.shape[0] == n
+            nz_ptr, nz_stride = nz.ctypes.data, nz.shape[1]
+        kp = None
+        if keys is not None:
+            kp = np.ascontiguousarray(np.asarray(keys, dtype=np.uint64))
+        with torch.cuda.device(self.device):
+            rc = self._lib.snacb_decode_windows_host(self._h, h_tok.data_ptr(), stride,
+                                                     nt.ctypes.data if nt is not None else None, stride, n, mode,
+                                                     nz_ptr, nz_stride, int(seed) & (2**64 - 1),
+                                                     kp.ctypes.data if kp is not None else None,
+                                                     h_pcm.data_ptr(), h_st.data_ptr(), self._stream())
+        self._check(rc, "snacb_decode_windows_host")
+        return h_pcm.numpy(), h_st.numpy()
+
+    # ------------------------------------------------------------------ one-shot path
+    def decode_codes(self, codes: Sequence[torch.Tensor], noise: NoiseArg = "philox", seed: int = 0,
+                     want_pcm: bool = False):
+        """``model.decode(codes)``: 3 tensors [B,F],[B,2F],[B,4F] -> float32 [B,1,2048F] (and int16 if asked)."""
+        c = [x.to(device=self.torch_device, dtype=torch.int32).contiguous() for x in codes]
+        B, F = c[0].shape
+        if c[1].shape != (B, 2 * F) or c[2].shape != (B, 4 * F):
+            raise ValueError("code tensors must be [B,F],[B,2F],[B,4F]")
+        wav = torch.empty((B, 1, SAMPLES_PER_FRAME * F), dtype=torch.float32, device=self.torch_device)
+        pcm = torch.empty((B, SAMPLES_PER_FRAME * F), dtype=torch.int16, device=self.torch_device) if want_pcm else None
+        mode = self._noise_mode(noise)
+        nz_ptr = None
+        if mode == _lib.NOISE_TENSOR:
+            nz = noise if isinstance(noise, torch.Tensor) else torch.from_numpy(np.asarray(noise, dtype=np.float32))
+            nz = nz.to(device=self.torch_device, dtype=torch.float32).contiguous()
+            assert tuple(nz.shape) == (B, _lib.NOISE_PER_FRAME * F)
+            self._keep = nz
+            nz_ptr = nz.data_ptr()
+        with torch.cuda.device(self.device):
+            rc = self._lib.snacb_decode_codes(self._h, c[0].data_ptr(), c[1].data_ptr(), c[2].data_ptr(), B, F, mode,
+                                              nz_ptr, int(seed) & (2**64 - 1), wav.data_ptr(), _ptr(pcm), self._stream())
+        self._check(rc, "snacb_decode_codes")
+        self._keep_codes = c
+        return (wav, pcm) if want_pcm else wav
+
+    def fill_noise(self, seed: int, n_win: int, frames: int, keys: Optional[Sequence[int]] = None) -> torch.Tensor:
+        out = torch.empty((n_win, _lib.NOISE_PER_FRAME * frames), dtype=torch.float32, device=self.torch_device)
+        kp = np.ascontiguousarray(np.asarray(keys, dtype=np.uint64)) if keys is not None else None
+        with torch.cuda.device(self.device):
+            rc = self._lib.snacb_fill_noise(self._h, int(seed) & (2**64 - 1), kp.ctypes.data if kp is not None else None,
+                                            n_win, frames, out.data_ptr(), out.shape[1], self._stream())
+        self._check(rc, "snacb_fill_noise")
+        return out
+
+    # ------------------------------------------------------------------ bring-up taps
+    def set_tap(self, stage: int, capacity_floats: int = 0) -> Optional[torch.Tensor]:
+        if stage < 0:
+            self._lib.snacb_set_tap(self._h, -1, None, 0)
+            self._tap = None
+            return None
+        self._tap = torch.zeros(capacity_floats, dtype=torch.float32, device=self.torch_device)
+        self._check(self._lib.snacb_set_tap(self._h, stage, self._tap.data_ptr(), capacity_floats), "snacb_set_tap")
+        return self._tap
+
+    def get_tap(self) -> Tuple[torch.Tensor, int]:
+        r, ch, lo, it = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        self._lib.snacb_get_tap_shape(self._h, C.byref(r), C.byref(ch), C.byref(lo), C.byref(it))
+        n = r.value * ch.value * it.value
+        torch.cuda.synchronize(self.torch_device)
+        return self._tap[:n].view(it.value, r.value, ch.value).clone(), lo.value
