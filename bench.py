@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Headline benchmark: SNAC-24k audio-seconds/sec of the token->waveform hot path (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
+
+A *step* is one decode tick: every stream of this rank's partition contributes one 28-token
+(4-frame) sliding window, the tick is decoded in one engine call and emits 2048 samples (85.33 ms
+of 24 kHz audio) per stream.  Workload = BASELINE config 4's per-GPU figure: 1024 concurrent
+streams per GPU (weak scaling: every added GPU brings its own 1024-stream partition; no data-path
+collective, streams are independent).  ``value`` is measured with tokens already resident in HBM;
+``e2e`` goes through the host-buffer C-ABI call the Python ``convert_to_audio_batch`` makes (pinned
+host tokens -> H2D -> kernels -> D2H PCM + status inside the timed region).
+
+One JSON line on stdout (rank 0).  Only the ``cpu_baseline`` leg and ``--impl reference`` touch
+``oracle/``.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SAMPLES_PER_WINDOW = 2048
+SAMPLE_RATE = 24000.0
+AUDIO_S_PER_WINDOW = SAMPLES_PER_WINDOW / SAMPLE_RATE
+FLOP_PER_WINDOW_REFERENCE = 3.312e9   # what model.decode executes for a 4-frame window
+FLOP_PER_WINDOW_CONE = 1.363e9        # exact dependency cone of samples [2048,4096)
+METRIC = "snac24k_audio_seconds_per_second"
+UNIT = "audio-s/s"
+
+
+def synth_tokens(first_stream: int, n: int, frames: int) -> np.ndarray:
+    """SURVEY 8(d) token recipe: stream s -> PCG64(1234+s), ids U{1..4095}; [n, 7*frames] int32."""
+    out = np.empty((n, 7 * frames), dtype=np.int32)
+    for i in range(n):
+        rng = np.random.Generator(np.random.PCG64(1234 + first_stream + i))
+        out[i] = rng.integers(1, 4096, size=7 * frames, dtype=np.int64)
+    return out
+
+
+def measured_peaks() -> dict:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"tensor_tflops": float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))),
+                "tensor_tflops_burst": float(d.get("bf16_tflops", 1590.0)),
+                "hbm_gbs": float(d.get("hbm_gbs", 6650.0)), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tensor_tflops": 1400.0, "tensor_tflops_burst": 1590.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 8:
+                    continue
+                try:
+                    sm.append(float(p[1])); mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(names, p[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:  # noqa: BLE001
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_run(n_windows: int, frames: int, steps: int, warmup: int, budget_s: float | None = None):
+    """The reference's CPU algorithm (oracle port: verbatim speechpipe semantics + restated SNAC decode),
+    one B=1 ``convert_to_audio``-equivalent per window exactly like the reference serialises them,
+    torch intra-op threads = all host cores.  Returns (windows_per_s, seconds_per_step list, cores)."""
+    import torch
+
+    from oracle import snac_ref, speechpipe_ref as sp
+    from project_morpheus_b200 import weights
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.set_grad_enabled(False)
+    model = snac_ref.SNAC.from_state_dict(weights.random_state_dict(0, "w1")).eval()
+    model.set_noise("randn")  # reference behaviour: fresh torch.randn inside decode
+    tok = synth_tokens(0, n_windows, frames)
+
+    def decode(c0, c1, c2):
+        codes = [torch.from_numpy(c.astype(np.int64))[None] for c in (c0, c1, c2)]
+        return model.decode(codes)[0, 0].numpy()
+
+    def one_step():
+        t0 = time.perf_counter()
+        for row in tok:
+            out = sp.window_to_pcm(row.tolist(), decode)
+            assert out is not None and len(out) == 4096
+        return time.perf_counter() - t0
+
+    for _ in range(warmup):
+        one_step()
+    times, spent = [], 0.0
+    for _ in range(steps):
+        dt = one_step()
+        times.append(dt); spent += dt
+        if budget_s is not None and spent >= budget_s and len(times) >= 2:
+            break
+    wps = n_windows * len(times) / sum(times)
+    return wps, times, cores
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.ref_windows
+    wps, times, cores = cpu_reference_run(n, args.frames, args.steps, args.warmup)
+    value = wps * AUDIO_S_PER_WINDOW
+    sample = f"{n} of the {args.streams} windows of one tick per step, B=1 decode per window (the reference has no batching)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "streams_per_gpu": args.streams, "frames_per_window": args.frames,
+                   "tokens_per_window": 7 * args.frames, "weights": "random-init seed 0 variant w1"},
+        "windows_per_s": wps,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args) -> str:
+    return (f"cfg4-per-gpu: {args.streams} concurrent streams per GPU, one {args.frames}-frame "
+            f"({7 * args.frames}-token) sliding window per stream per tick, emits samples [2048,4096) as int16")
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from project_morpheus_b200 import _lib, weights
+    from project_morpheus_b200.engine import SnacEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    S, F, K, W = args.streams, args.frames, args.steps, max(3, args.warmup)
+    eng = SnacEngine(weights.random_state_dict(0, "w1"), device=local, precision=args.precision, trim=not args.no_trim,
+                     chunk_items=args.chunk)
+    tok_host = synth_tokens(rank * S, S, F)                      # this rank's stream partition
+    keys = np.arange(rank * S, rank * S + S, dtype=np.uint64)    # Philox stream keys
+    tok_dev = torch.from_numpy(tok_host).to(dev)
+    pcm_dev = torch.empty((S, 2048), dtype=torch.int16, device=dev)
+    st_dev = torch.empty((S,), dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def tick_device(step):
+        eng.decode_windows_device(tok_dev, noise="philox", seed=step, keys=keys, pcm=pcm_dev, status=st_dev)
+
+    def tick_host(step):
+        return eng.decode_windows(tok_host, noise="philox", seed=step, keys=keys)
+
+    for i in range(W):
+        tick_device(i)
+        tick_host(i)
+    torch.cuda.synchronize(dev)
+    assert int((st_dev != _lib.WIN_OK).sum()) == 0
+
+    # ---- timed region 1: device-resident inputs (value)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    launches0 = eng.launch_count
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(K):
+        flush.zero_()                                  # untimed L2 flush between steps
+        evs[i][0].record()
+        tick_device(100 + i)
+        evs[i][1].record()
+    barrier()
+    wall_dev = time.perf_counter() - wall0
+    launches = eng.launch_count - launches0
+    dev_ms = [a.elapsed_time(b) for a, b in evs]
+
+    # ---- timed region 2: host buffers through the C-ABI (e2e)
+    evs2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    e2e_wall = []
+    for i in range(K):
+        flush.zero_()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        evs2[i][0].record()
+        pcm, st = tick_host(200 + i)
+        evs2[i][1].record()
+        evs2[i][1].synchronize()
+        e2e_wall.append(time.perf_counter() - t0)
+        checksum = int(pcm[:, ::257].astype(np.int64).sum())  # touch the result on the host
+    barrier()
+    clocks = sampler.stop() if rank == 0 else {}
+    e2e_ms = [max(a.elapsed_time(b), 1e3 * w) for (a, b), w in zip(evs2, e2e_wall)]
+
+    t_dev = torch.tensor([sum(dev_ms), sum(e2e_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    tot_dev_ms, tot_e2e_ms = float(t_dev[0]), float(t_dev[1])
+
+    # ---- per-kernel-class device time (CUDA events around each launch), same tick, right after
+    stats, extra = {}, {}
+    if rank == 0:
+        eng.profile(True)
+        for i in range(2):
+            tick_device(300 + i)
+        torch.cuda.synchronize(dev)
+        stats = eng.profile_read()
+        eng.profile(False)
+        # BASELINE config 2 (64 streams per tick) and single-window latency through the host API
+        for name, n in (("cfg2_64_streams", 64), ("single_window", 1)):
+            t = tok_host[:n]
+            k = keys[:n]
+            for i in range(5):
+                eng.decode_windows(t, noise="philox", seed=i, keys=k)
+            lat = []
+            for i in range(args.latency_reps):
+                t0 = time.perf_counter()
+                eng.decode_windows(t, noise="philox", seed=i, keys=k)
+                lat.append(time.perf_counter() - t0)
+            p50 = statistics.median(lat)
+            extra[name] = {"p50_ms": 1e3 * p50, "p95_ms": 1e3 * sorted(lat)[int(0.95 * (len(lat) - 1))],
+                           "audio_s_per_s": n * AUDIO_S_PER_WINDOW / p50, "reps": len(lat)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    windows_total = world * S * K
+    value = windows_total * AUDIO_S_PER_WINDOW / (tot_dev_ms * 1e-3)
+    e2e_value = windows_total * AUDIO_S_PER_WINDOW / (tot_e2e_ms * 1e-3)
+    wps = windows_total / (tot_dev_ms * 1e-3)
+
+    # dominant kernel class and its roofline
+    roof = None
+    if stats:
+        tot_ms = sum(v["ms"] for v in stats.values()) or 1e-9
+        name, top = max(stats.items(), key=lambda kv: kv[1]["ms"])
+        tensor_like = name.startswith("gemm") or name.startswith("block")
+        if tensor_like:
+            ach = top["flops"] / (top["ms"] * 1e-3) / 1e12
+            peak = peaks["tensor_tflops"]
+            roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak}
+        else:
+            ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9
+            peak = peaks["hbm_gbs"]
+            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}
+        roof.update({
+            "traffic": None, "kernel": name, "launches_per_step": top["launches"] / 2,
+            "avg_launch_ms": top["ms"] / max(1, top["launches"]), "share_of_step": top["ms"] / tot_ms,
+            "peak_source": peaks["source"] + (", bf16 dense sustained" if tensor_like else ", copy"),
+            "flops_counted": "executed (2*MAC of the launches, dependency-cone trimmed)",
+            "classes": {k: {"ms_per_step": v["ms"] / 2, "launches_per_step": v["launches"] / 2,
+                            "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else 0.0,
+                            "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else 0.0}
+                        for k, v in stats.items() if v["launches"]},
+        })
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cw, ctimes, cores = cpu_reference_run(args.ref_windows, F, steps=50, warmup=1, budget_s=args.cpu_budget)
+        cpu = {"value": cw * AUDIO_S_PER_WINDOW, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{args.ref_windows} windows per pass x {len(ctimes)} passes of the same tick, B=1 decode per "
+                         f"window on torch CPU threads (reference semantics), {sum(ctimes):.1f} s",
+               "windows_per_s": cw}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": tot_dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 operands, f32 accumulate" if args.precision == "fp16" else "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "streams_per_gpu": S, "frames_per_window": F,
+                   "tokens_per_window": 7 * F, "weights": "random-init seed 0 variant w1", "noise": "in-kernel philox",
+                   "precision": args.precision, "trim": not args.no_trim, "partition": f"stream s -> rank s // {S}",
+                   "l2": "256 MiB memset between steps (untimed); per-tick activations exceed L2"},
+        "windows_per_s": wps, "realtime_factor_per_gpu": value / world,
+        "tflops_reference_equivalent": wps * FLOP_PER_WINDOW_REFERENCE / 1e12,
+        "tflops_cone": wps * FLOP_PER_WINDOW_CONE / 1e12,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tok_host.nbytes),
+                "d2h_bytes_per_step": int(S * 2048 * 2 + S * 4), "ms_per_step": tot_e2e_ms / K,
+                "api": "snacb_decode_windows_host via SnacEngine.decode_windows (pinned host tokens -> PCM on host)"},
+        "gpu_launches": int(launches), "wall_s_device_region": wall_dev, "clocks": clocks,
+        "roofline": roof, "cpu_baseline": cpu, "latency": extra, "checksum": checksum,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--streams", type=int, default=1024, help="concurrent streams (= windows per tick) per GPU")
+    ap.add_argument("--frames", type=int, default=4)
+    ap.add_argument("--precision", choices=["fp16", "fp32"], default="fp16")
+    ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--no-trim", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline leg")
+    ap.add_argument("--ref-windows", type=int, default=32, help="windows per step of the CPU reference sample")
+    ap.add_argument("--latency-reps", type=int, default=200)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -186,6 +186,23 @@ int snacb_decode_codes(snacb_engine* e, const int32_t* d_c0, const int32_t* d_c1
 int snacb_fill_noise(snacb_engine* e, uint64_t seed, const uint64_t* h_keys, int32_t n_win,
                      int32_t F, float* d_noise, int64_t noise_stride, void* stream);
 
+/* ---- measurement ---------------------------------------------------------------------------- */
+
+/* Per-kernel-class device timing (CUDA events on the launching stream around every launch of the
+ * class) for bench.py's roofline object.  Off by default; when on, every decode call records two
+ * events per launch.  snacb_profile_read() synchronises the recorded events, ACCUMULATES them into
+ * per-class totals, writes up to `cap` rows and returns the number of classes (negative on error);
+ * snacb_profile_enable(e, 1) clears the totals. */
+typedef struct snacb_kernel_stat {
+  char name[32];      /* kernel class, e.g. "gemm_1x1", "gemm_convt", "dwconv", "tail" */
+  int64_t launches;
+  double ms;          /* summed device time of the launches                                  */
+  double flops;       /* executed floating-point operations (2*MAC for GEMM-shaped kernels)  */
+  double bytes;       /* algorithmic global-memory bytes read + written by the launches      */
+} snacb_kernel_stat;
+int snacb_profile_enable(snacb_engine* e, int32_t on);
+int snacb_profile_read(snacb_engine* e, snacb_kernel_stat* out, int32_t cap);
+
 /* ---- bring-up / parity taps ----------------------------------------------------------------- */
 
 /* Layer-wise parity: after the next decode, d_buf receives the fp32 activation of `stage`

@@ -55,6 +55,11 @@ class Weights(C.Structure):
     ]
 
 
+class KernelStat(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("ms", C.c_double), ("flops", C.c_double),
+                ("bytes", C.c_double)]
+
+
 # name -> (restype, argtypes); every symbol include/snacb.h declares
 _vp, _i32, _i64, _u64, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_size_t
 SIGNATURES = {
@@ -70,6 +75,8 @@ SIGNATURES = {
     "snacb_decode_windows_host": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _i64, _u64, _vp, _vp, _vp, _vp]),
     "snacb_decode_codes": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _u64, _vp, _vp, _vp]),
     "snacb_fill_noise": (_i32, [_vp, _u64, _vp, _i32, _i32, _vp, _i64, _vp]),
+    "snacb_profile_enable": (_i32, [_vp, _i32]),
+    "snacb_profile_read": (_i32, [_vp, C.POINTER(KernelStat), _i32]),
     "snacb_set_tap": (_i32, [_vp, _i32, _vp, _sz]),
     "snacb_plan": (_i32, [_i32, _i32, _i32, _i32, C.POINTER(_i32)]),
     "snacb_get_tap_shape": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),

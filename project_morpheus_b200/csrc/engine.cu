@@ -30,6 +30,23 @@ struct DevWeights {
   float *tail_alpha, *tail_inv, *tail_w /*[7][64]*/, *tail_b;
 };
 
+enum KClass { KC_DEINT = 0, KC_CODES, KC_DW, KC_SNAKE, KC_GEMM1, KC_CONVT, KC_TAIL, KC_COUNT };
+const char* const kClassName[KC_COUNT] = {"deinterleave", "from_codes", "dwconv_snake", "snake", "gemm_1x1",
+                                          "gemm_convt", "tail_pack"};
+
+struct Prof {
+  bool on = false;
+  struct Rec { int cls; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  double ms[KC_COUNT] = {}, flops[KC_COUNT] = {}, bytes[KC_COUNT] = {};
+  int64_t launches[KC_COUNT] = {};
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+};
+
 }  // namespace
 
 struct snacb_engine {
@@ -51,6 +68,7 @@ struct snacb_engine {
   size_t pin_items_cap = 0;
   cudaEvent_t items_ev = nullptr;
   int64_t launches = 0;
+  Prof prof;
   // tap
   int tap_stage = -1;
   float* tap_buf = nullptr;
@@ -82,6 +100,23 @@ int check_launch(snacb_engine* e, const char* what) {
   if (c != cudaSuccess) return fail(e, SNACB_ECUDA, "%s: launch failed: %s", what, cudaGetErrorString(c));
   return SNACB_OK;
 }
+
+// Times one launch with a pair of events on the launching stream when profiling is on.
+struct ProfScope {
+  Prof& p; cudaStream_t st; cudaEvent_t a = nullptr; int cls;
+  ProfScope(snacb_engine* e, int cls_, double flops, double bytes, cudaStream_t st_) : p(e->prof), st(st_), cls(cls_) {
+    if (!p.on) return;
+    p.flops[cls] += flops; p.bytes[cls] += bytes; p.launches[cls] += 1;
+    a = p.get();
+    cudaEventRecord(a, st);
+  }
+  ~ProfScope() {
+    if (!a) return;
+    cudaEvent_t b = p.get();
+    cudaEventRecord(b, st);
+    p.recs.push_back({cls, a, b});
+  }
+};
 
 int ensure_ws(snacb_engine* e, size_t bytes, cudaStream_t st) {
   if (bytes <= e->ws_bytes) return SNACB_OK;
@@ -188,11 +223,26 @@ int run_group_f32(snacb_engine* e, const Plan& P, const Item* d_items, int n_tot
     float* A = bp.take<float>(S * n);
     GroupCtx g{d_items ? d_items + start : nullptr, start, n, out_len, P.T0, st, &e->launches};
 
-    launch_from_codes(g, W.q, c0, c1, c2, pitch0, P.z, Z);
+    auto gemm = [&](const GemmArgs& a) {
+      const double M = (double)n * a.m_r.n(), segs = a.epi == EPI_CONVT ? 2.0 : 1.0;
+      const double flops = 2.0 * M * a.N * a.K * segs;
+      const double by = 4.0 * ((double)n * a.a_r.n() * a.K + (double)a.N * a.K * segs + M * a.N * (a.R ? 2.0 : 1.0));
+      ProfScope ps(e, a.epi == EPI_CONVT ? KC_CONVT : KC_GEMM1, flops, by, st);
+      launch_gemm_f32(g, a);
+    };
+    auto dwconv = [&](const DwArgs& d) {
+      const double el = (double)n * d.out_r.n() * d.C;
+      ProfScope ps(e, KC_DW, el * (14.0 + (d.a1 ? 28.0 : 0.0) + (d.a2 ? 4.0 : 0.0)), 4.0 * ((double)n * d.in_r.n() * d.C + el), st);
+      launch_dwconv(g, d);
+    };
+    {
+      ProfScope ps(e, KC_CODES, 2.0 * 24 * kLatent * n * P.z.n(), 4.0 * kLatent * n * P.z.n(), st);
+      launch_from_codes(g, W.q, c0, c1, c2, pitch0, P.z, Z);
+    }
     tap(e, 0, Z, P.z, kLatent, n, first, st);
     {
       DwArgs d{Z, P.z, H0, P.h, kLatent, 1, 1, W.head_dw_w, W.head_dw_b, nullptr, nullptr, nullptr, nullptr};
-      launch_dwconv(g, d);
+      dwconv(d);
       tap(e, 1, H0, P.h, kLatent, n, first, st);
     }
     {
@@ -200,21 +250,25 @@ int run_group_f32(snacb_engine* e, const Plan& P, const Item* d_items, int n_tot
       a.epi = EPI_BIAS; a.A = H0; a.lda = kLatent; a.a_r = P.h; a.W = W.head_pw_w; a.ldw = kLatent;
       a.bias = W.head_pw_b; a.K = kLatent; a.N = kDecDim; a.m_r = P.h; a.out = X; a.o_r = P.h; a.ldo = kDecDim;
       a.up = 1;
-      launch_gemm_f32(g, a);
+      gemm(a);
       tap(e, 2, X, P.h, kDecDim, n, first, st);
     }
     for (int b = 0; b < 4; ++b) {
       const BlockPlan& B = P.b[b];
       const BlockDev& Wb = W.blk[b];
       const int sid = 3 + 9 * b;
-      launch_snake(g, X, A, B.in, B.Cin, Wb.alpha, Wb.inv);
+      {
+        const double el = (double)n * B.in.n() * B.Cin;
+        ProfScope ps(e, KC_SNAKE, 4.0 * el, 8.0 * el, st);
+        launch_snake(g, X, A, B.in, B.Cin, Wb.alpha, Wb.inv);
+      }
       tap(e, sid + 0, A, B.in, B.Cin, n, first, st);
       {
         GemmArgs a{};
         a.epi = EPI_CONVT; a.A = A; a.lda = B.Cin; a.a_r = B.in; a.W = Wb.ct_w; a.ldw = 2 * B.Cin;
         a.bias = Wb.ct_b; a.K = B.Cin; a.N = B.s * B.Cout; a.m_r = B.q; a.s = B.s; a.p = B.p; a.Cout = B.Cout;
         a.out = Y; a.o_r = B.ct; a.ldo = B.Cout; a.up = B.up_out;
-        launch_gemm_f32(g, a);
+        gemm(a);
         tap(e, sid + 1, Y, B.ct, B.Cout, n, first, st);
       }
       if (nz.mode != SNACB_NOISE_OFF) {
@@ -223,7 +277,7 @@ int run_group_f32(snacb_engine* e, const Plan& P, const Item* d_items, int n_tot
         a.K = B.Cout; a.N = B.Cout; a.m_r = B.ct; a.out = X; a.o_r = B.ct; a.ldo = B.Cout;
         a.R = Y; a.r_r = B.ct; a.ldr = B.Cout; a.up = B.up_out;
         a.noise = NoiseSrc{nz.mode, nz.tensor, nz.stride, noise_off[b], (unsigned long long)nz.seed, nz.d_keys, b};
-        launch_gemm_f32(g, a);
+        gemm(a);
       } else {
         std::swap(X, Y);  // x + 0 * h == x
       }
@@ -232,20 +286,24 @@ int run_group_f32(snacb_engine* e, const Plan& P, const Item* d_items, int n_tot
       for (int r = 0; r < 3; ++r) {
         const RuDev& R = Wb.ru[r];
         DwArgs d{X, cur, A, B.r[r], B.Cout, kDil[r], B.up_out, R.dw_w, R.dw_b, R.a1, R.i1, R.a2, R.i2};
-        launch_dwconv(g, d);
+        dwconv(d);
         tap(e, sid + 3 + 2 * r, A, B.r[r], B.Cout, n, first, st);
         GemmArgs a{};
         a.epi = EPI_RESID; a.A = A; a.lda = B.Cout; a.a_r = B.r[r]; a.W = R.pw_w; a.ldw = B.Cout; a.bias = R.pw_b;
         a.K = B.Cout; a.N = B.Cout; a.m_r = B.r[r]; a.out = Y; a.o_r = B.r[r]; a.ldo = B.Cout;
         a.R = X; a.r_r = cur; a.ldr = B.Cout; a.up = B.up_out;
-        launch_gemm_f32(g, a);
+        gemm(a);
         tap(e, sid + 4 + 2 * r, Y, B.r[r], B.Cout, n, first, st);
         std::swap(X, Y);
         cur = B.r[r];
       }
     }
     TailArgs t{X, P.b[3].r[2], tail_out, W.tail_alpha, W.tail_inv, W.tail_w, W.tail_b, d_status, wav, pcm};
-    launch_tail(g, t);
+    {
+      const double smp = (double)n * tail_out.n();
+      ProfScope ps(e, KC_TAIL, smp * (2.0 * 448 + 4.0 * 64), 4.0 * (double)n * P.b[3].r[2].n() * 64 + smp * 2.0, st);
+      launch_tail(g, t);
+    }
     int rc = check_launch(e, "layer pipeline");
     if (rc) return rc;
   }
@@ -308,6 +366,8 @@ void snacb_destroy(snacb_engine* e) {
   if (e->pin) cudaFreeHost(e->pin);
   if (e->pin_items) cudaFreeHost(e->pin_items);
   if (e->items_ev) cudaEventDestroy(e->items_ev);
+  for (auto& r : e->prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto ev : e->prof.pool) cudaEventDestroy(ev);
   delete e;
 }
 
@@ -403,8 +463,11 @@ static int deinterleave_common(snacb_engine* e, const int32_t* d_tokens, int32_t
   } else if (ntok_uniform < 0 || ntok_uniform > tokens_stride) {
     return fail(e, SNACB_EINVAL, "snacb_deinterleave: ntok_uniform out of range");
   }
-  launch_deinterleave(d_tokens, tokens_stride, d_ntok, ntok_uniform, n_win, max_frames, raw, d_c0, d_c1, d_c2,
-                      d_status, st, &e->launches);
+  {
+    ProfScope ps(e, KC_DEINT, 0.0, 8.0 * (double)n_win * 7 * max_frames, st);
+    launch_deinterleave(d_tokens, tokens_stride, d_ntok, ntok_uniform, n_win, max_frames, raw, d_c0, d_c1, d_c2,
+                        d_status, st, &e->launches);
+  }
   return check_launch(e, "deinterleave");
 }
 
@@ -486,8 +549,11 @@ int snacb_decode_windows(snacb_engine* e, const int32_t* d_tokens, int32_t token
     CU(e, cudaMemcpyAsync(d_keys, h_keys, (size_t)n_win * 8, cudaMemcpyHostToDevice, st));
     keys = d_keys;
   }
-  launch_deinterleave(d_tokens, tokens_stride, h_ntok ? d_ntok : nullptr, ntok_uniform, n_win, maxF, false, c0, c1, c2,
-                      d_status, st, &e->launches);
+  {
+    ProfScope ps(e, KC_DEINT, 0.0, 8.0 * (double)n_win * 7 * maxF, st);
+    launch_deinterleave(d_tokens, tokens_stride, h_ntok ? d_ntok : nullptr, ntok_uniform, n_win, maxF, false, c0, c1, c2,
+                        d_status, st, &e->launches);
+  }
   CU(e, cudaMemsetAsync(d_pcm, 0, (size_t)n_win * 2048 * sizeof(int16_t), st));
   NoiseCfg nz{noise_mode, d_noise, (long long)noise_stride, seed, keys};
 
@@ -638,6 +704,37 @@ int snacb_fill_noise(snacb_engine* e, uint64_t seed, const uint64_t* h_keys, int
   }
   launch_fill_noise(seed, keys, n_win, F, d_noise, (long long)noise_stride, st, &e->launches);
   return check_launch(e, "fill_noise");
+}
+
+int snacb_profile_enable(snacb_engine* e, int32_t on) {
+  if (!e) return SNACB_EINVAL;
+  Prof& p = e->prof;
+  cudaSetDevice(e->device);
+  for (auto& r : p.recs) { cudaEventSynchronize(r.b); p.pool.push_back(r.a); p.pool.push_back(r.b); }
+  p.recs.clear();
+  for (int c = 0; c < KC_COUNT; ++c) { p.ms[c] = p.flops[c] = p.bytes[c] = 0.0; p.launches[c] = 0; }
+  p.on = on != 0;
+  return SNACB_OK;
+}
+
+int snacb_profile_read(snacb_engine* e, snacb_kernel_stat* out, int32_t cap) {
+  if (!e || (cap > 0 && !out)) return SNACB_EINVAL;
+  Prof& p = e->prof;
+  CU(e, cudaSetDevice(e->device));
+  for (auto& r : p.recs) {
+    CU(e, cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    CU(e, cudaEventElapsedTime(&ms, r.a, r.b));
+    p.ms[r.cls] += ms;
+    p.pool.push_back(r.a); p.pool.push_back(r.b);
+  }
+  p.recs.clear();
+  for (int c = 0; c < KC_COUNT && c < cap; ++c) {
+    memset(&out[c], 0, sizeof out[c]);
+    snprintf(out[c].name, sizeof out[c].name, "%s", kClassName[c]);
+    out[c].launches = p.launches[c]; out[c].ms = p.ms[c]; out[c].flops = p.flops[c]; out[c].bytes = p.bytes[c];
+  }
+  return KC_COUNT;
 }
 
 int snacb_set_tap(snacb_engine* e, int32_t stage, float* d_buf, size_t capacity_floats) {

@@ -238,6 +238,20 @@ class SnacEngine:
         self._check(rc, "snacb_fill_noise")
         return out
 
+    # ------------------------------------------------------------------ measurement
+    def profile(self, on: bool) -> None:
+        self._check(self._lib.snacb_profile_enable(self._h, 1 if on else 0), "snacb_profile_enable")
+
+    def profile_read(self) -> Dict[str, Dict[str, float]]:
+        """Per-kernel-class totals since ``profile(True)``: launches, device ms, executed flops, bytes."""
+        rows = (_lib.KernelStat * 16)()
+        n = self._lib.snacb_profile_read(self._h, rows, 16)
+        if n < 0:
+            self._check(n, "snacb_profile_read")
+        return {rows[i].name.decode(): {"launches": int(rows[i].launches), "ms": float(rows[i].ms),
+                                        "flops": float(rows[i].flops), "bytes": float(rows[i].bytes)}
+                for i in range(min(n, 16))}
+
     # ------------------------------------------------------------------ bring-up taps
     def set_tap(self, stage: int, capacity_floats: int = 0) -> Optional[torch.Tensor]:
         if stage < 0:

@@ -69,8 +69,14 @@ class SNAC:
         return cls(source)
 
     @classmethod
-    def from_state_dict(cls, state_dict: Dict[str, torch.Tensor]) -> "SNAC":
-        return cls("<state_dict>", state_dict)
+    def from_state_dict(cls, state_dict: Dict[str, torch.Tensor], precision: Optional[str] = None,
+                        noise: Optional[str] = None) -> "SNAC":
+        m = cls("<state_dict>", state_dict)
+        if precision is not None:
+            m.precision = precision
+        if noise is not None:
+            m.noise = noise
+        return m
 
     def eval(self) -> "SNAC":
         self.training = False

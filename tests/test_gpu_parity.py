@@ -1,0 +1,313 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  B200 only."""
+import asyncio
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import (TOL_FP32_MAX_ABS, TOL_MAX_ABS, TOL_SNR_DB, load_golden, oracle_decode_windows, pcm_trunc, snr_db,
+                     windows_tokens)
+from oracle import snac_ref, speechpipe_ref as sp
+from project_morpheus_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+PRECISIONS = ["fp32", "fp16"]
+
+
+@pytest.fixture(scope="module")
+def engines(state_dict_w1, ensure_lib):
+    from project_morpheus_b200.engine import SnacEngine
+    made = {}
+
+    def get(precision="fp32", trim=True):
+        key = (precision, trim)
+        if key not in made:
+            made[key] = SnacEngine(state_dict_w1, device=0, precision=precision, trim=trim)
+        return made[key]
+
+    yield get
+    for e in made.values():
+        e.close()
+
+
+# ------------------------------------------------------------------------------------ NS-1
+def test_deinterleave_bit_exact_vs_golden(engines):
+    eng = engines("fp32")
+    gold = load_golden()["g1_deinterleave"]
+    rows = [r for r in gold]
+    stride = max(len(r["tokens"]) for r in rows)
+    tok = np.zeros((len(rows), stride), dtype=np.int32)
+    for i, r in enumerate(rows):
+        tok[i, : len(r["tokens"])] = r["tokens"]
+    ntok = [len(r["tokens"]) for r in rows]
+    c0, c1, c2, st = eng.deinterleave(torch.from_numpy(tok).cuda(), ntok=ntok)
+    c0, c1, c2, st = c0.cpu().numpy(), c1.cpu().numpy(), c2.cpu().numpy(), st.cpu().numpy()
+    for i, r in enumerate(rows):
+        F = len(r["tokens"]) // 7
+        if r["verdict"] == "none":
+            assert st[i] == _lib.WIN_REJECTED
+            continue
+        want = r["codes"]
+        assert c0[i, :F].tolist() == want[0] and c1[i, : 2 * F].tolist() == want[1] and c2[i, : 4 * F].tolist() == want[2]
+        has4096 = any(4096 in w for w in want)
+        assert st[i] == (_lib.WIN_CODE4096 if has4096 else _lib.WIN_EMPTY if F == 1 else _lib.WIN_OK)
+
+
+def test_deinterleave_random_and_raw_mode(engines):
+    eng = engines("fp32")
+    rng = np.random.default_rng(0)
+    n, F = 513, 7
+    tok = rng.integers(-3, 4100, size=(n, 7 * F)).astype(np.int32)
+    tok[::3] = rng.integers(0, 4096, size=tok[::3].shape)
+    ntok = rng.integers(0, 7 * F + 1, size=n).astype(np.int32)
+    c0, c1, c2, st = [x.cpu().numpy() for x in eng.deinterleave(torch.from_numpy(tok).cuda(), ntok=ntok.tolist(), max_frames=F)]
+    for i in range(n):
+        lv = sp.split_levels(tok[i, : ntok[i]].tolist())
+        if lv is None or not lv[3]:
+            assert st[i] == _lib.WIN_REJECTED
+            continue
+        f = ntok[i] // 7
+        assert np.array_equal(c0[i, :f], lv[0]) and np.array_equal(c1[i, : 2 * f], lv[1]) and np.array_equal(c2[i, : 4 * f], lv[2])
+        assert not c0[i, f:].any() and not c2[i, 4 * f:].any()
+    # raw mode: N of <custom_token_N> for aligned windows
+    ids = rng.integers(0, 4096, size=(64, 28)).astype(np.int32)
+    raw = ids + 10 + 4096 * (np.arange(28) % 7)[None, :].astype(np.int32)
+    a = [x.cpu().numpy() for x in eng.deinterleave(torch.from_numpy(ids).cuda())]
+    b = [x.cpu().numpy() for x in eng.deinterleave(torch.from_numpy(raw.astype(np.int32)).cuda(), raw=True)]
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+# ------------------------------------------------------------------------------------ layer-wise (fp32 recipe)
+def _oracle_taps(model, codes, noise):
+    """Activations of the oracle at the engine's tap points, channels-last [B, T, C]."""
+    taps = {}
+    model.set_noise(noise)
+    z = model.quantizer.from_codes(codes)
+    taps[0] = z
+    x = model.decoder.model[0](z); taps[1] = x
+    x = model.decoder.model[1](x); taps[2] = x
+    for b in range(4):
+        blk = model.decoder.model[2 + b].block
+        sid = 3 + 9 * b
+        x = blk[0](x); taps[sid] = x
+        x = blk[1](x); taps[sid + 1] = x
+        x = blk[2](x); taps[sid + 2] = x
+        for r in range(3):
+            ru = blk[3 + r].block
+            a = ru[2](ru[1](ru[0](x))); taps[sid + 3 + 2 * r] = a
+            x = x + ru[3](a); taps[sid + 4 + 2 * r] = x
+    model.set_noise("off")
+    return {k: v.transpose(1, 2).contiguous().numpy() for k, v in taps.items()}
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_layerwise_taps(engines, oracle_w1, precision):
+    eng = engines(precision, trim=False)
+    n, F = 3, 4
+    tok = windows_tokens(n, F, base_stream=100)
+    noise = snac_ref.make_noise(n, F, seed=5)
+    lv = [sp.split_levels(row.tolist()) for row in tok]
+    codes = [torch.from_numpy(np.stack([l[k] for l in lv]).astype(np.int64)) for k in range(3)]
+    want = _oracle_taps(oracle_w1, codes, noise)
+    tol = 3e-5 if precision == "fp32" else 2e-2
+    worst = {}
+    for stage in sorted(want):
+        eng.set_tap(stage, 3 * 8192 * 1024)
+        eng.decode_windows_device(torch.from_numpy(tok).cuda(), noise=snac_ref.pack_noise(noise))
+        got, lo = eng.get_tap()
+        got = got.cpu().numpy()
+        ref = want[stage][:, lo: lo + got.shape[1], :]
+        assert got.shape == ref.shape, (stage, got.shape, ref.shape)
+        scale = max(1.0, float(np.abs(ref).max()))
+        worst[stage] = float(np.abs(got - ref).max()) / scale
+    eng.set_tap(-1)
+    bad = {s: e for s, e in worst.items() if not e <= tol}
+    assert not bad, f"layer-wise mismatch (stage: rel max-abs) {bad}; all: {worst}"
+
+
+# ------------------------------------------------------------------------------------ end to end
+def _check_wave(ref, got, max_abs, snr):
+    err = float(np.abs(ref - got).max())
+    s = snr_db(ref, got)
+    assert err <= max_abs and s >= snr, f"max-abs {err:.3e} (<= {max_abs}), SNR {s:.1f} dB (>= {snr})"
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("frames", [2, 4, 7])
+def test_decode_codes_matches_oracle(engines, oracle_w1, precision, frames):
+    eng = engines(precision)
+    n = 5
+    tok = windows_tokens(n, frames, base_stream=10 * frames)
+    noise = snac_ref.make_noise(n, frames, seed=99)
+    ref = oracle_decode_windows(oracle_w1, tok, noise)
+    lv = [sp.split_levels(row.tolist()) for row in tok]
+    codes = [torch.from_numpy(np.stack([l[k] for l in lv])) for k in range(3)]
+    wav, pcm = eng.decode_codes(codes, noise=snac_ref.pack_noise(noise), want_pcm=True)
+    got = wav[:, 0].cpu().numpy()
+    if precision == "fp32":
+        _check_wave(ref, got, TOL_FP32_MAX_ABS, 90.0)
+    else:
+        _check_wave(ref, got, TOL_MAX_ABS, TOL_SNR_DB)
+    assert np.array_equal(pcm.cpu().numpy(), pcm_trunc(got))  # NS-4: trunc(x*32767), no clip, no rounding
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("trim", [True, False])
+@pytest.mark.parametrize("frames", [4, 7])
+def test_windows_pcm_matches_oracle(engines, oracle_w1, precision, trim, frames):
+    eng = engines(precision, trim)
+    n = 9
+    tok = windows_tokens(n, frames, base_stream=500)
+    noise = snac_ref.make_noise(n, frames, seed=7)
+    ref = oracle_decode_windows(oracle_w1, tok, noise)[:, 2048:4096]
+    pcm, st = eng.decode_windows(tok, noise=snac_ref.pack_noise(noise))
+    assert (st == _lib.WIN_OK).all()
+    want = pcm_trunc(ref).astype(np.int32)
+    diff = np.abs(pcm.astype(np.int32) - want)
+    if precision == "fp32":
+        assert diff.max() <= 1, f"fp32 recipe: {diff.max()} LSB"  # truncation flips only
+    else:
+        got = pcm.astype(np.float32) / 32767.0
+        # int16 grid adds up to 1 LSB = 3.05e-5 of quantisation on both sides
+        _check_wave(want.astype(np.float32) / 32767.0, got, TOL_MAX_ABS, TOL_SNR_DB - 0.5)
+
+
+def test_trim_equals_untrimmed_fp32(engines):
+    """The dependency-cone trim is exact: same bits as computing the whole window."""
+    a, b = engines("fp32", True), engines("fp32", False)
+    tok = windows_tokens(6, 4, base_stream=900)
+    p1, _ = a.decode_windows(tok, noise="off"); p1 = p1.copy()
+    p2, _ = b.decode_windows(tok, noise="off")
+    assert np.array_equal(p1, p2)
+
+
+def test_ragged_tick_statuses_and_isolation(engines, oracle_w1):
+    """Mixed window lengths + poisoned windows in one call: a bad window never poisons the batch."""
+    eng = engines("fp32")
+    good4, good7 = windows_tokens(2, 4, 30), windows_tokens(2, 7, 40)
+    wins = [good4[0].tolist(), [5] * 6, good7[0].tolist(), [-1] + [5] * 27, [4096] + [5] * 27, list(range(1, 8)),
+            good4[1].tolist(), good7[1].tolist()[:-3], [4097] * 28, []]
+    stride = max(len(w) for w in wins)
+    tok = np.zeros((len(wins), stride), dtype=np.int32)
+    for i, w in enumerate(wins):
+        tok[i, : len(w)] = w
+    pcm, st = eng.decode_windows(tok, ntok=[len(w) for w in wins], noise="off")
+    R, O, T, E = _lib.WIN_REJECTED, _lib.WIN_OK, _lib.WIN_CODE4096, _lib.WIN_EMPTY
+    assert st.tolist() == [O, R, O, R, T, E, O, O, R, R]
+    assert not pcm[[1, 3, 4, 5, 8, 9]].any()
+    for i in (0, 2, 6, 7):
+        w = np.asarray(wins[i][: (len(wins[i]) // 7) * 7], dtype=np.int32)[None]
+        ref = oracle_decode_windows(oracle_w1, w, "off")[:, 2048:4096]
+        assert np.abs(pcm[i].astype(np.int32) - pcm_trunc(ref)[0].astype(np.int32)).max() <= 1
+
+
+def test_philox_noise_replays_through_oracle(engines, oracle_w1):
+    """Mode C: in-kernel Philox noise, dumped and replayed through the oracle."""
+    eng = engines("fp32")
+    n, F = 4, 4
+    tok = windows_tokens(n, F, 70)
+    keys = [11, 12, 13, 2**40 + 5]
+    pcm, _ = eng.decode_windows(tok, noise="philox", seed=1234, keys=keys); pcm = pcm.copy()
+    pcm2, _ = eng.decode_windows(tok, noise="philox", seed=1234, keys=keys)
+    assert np.array_equal(pcm, pcm2)  # byte-identical replay under a fixed seed
+    pcm3, _ = eng.decode_windows(tok, noise="philox", seed=1235, keys=keys)
+    assert not np.array_equal(pcm, pcm3)
+    dump = eng.fill_noise(1234, n, F, keys=keys).cpu()
+    assert abs(float(dump.mean())) < 0.02 and abs(float(dump.std()) - 1.0) < 0.02
+    lens = snac_ref.noise_lengths(F)
+    parts, off = [], 0
+    for L in lens:
+        parts.append(dump[:, off: off + L].reshape(n, 1, L).clone()); off += L
+    ref = oracle_decode_windows(oracle_w1, tok, parts)[:, 2048:4096]
+    assert np.abs(pcm.astype(np.int32) - pcm_trunc(ref).astype(np.int32)).max() <= 1
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_long_read_tiled_matches_oracle(engines, oracle_w1, precision):
+    """Time-tiled one-shot decode (halo recompute) of a sequence longer than two tiles."""
+    eng = engines(precision)
+    F = 21
+    tok = windows_tokens(2, F, 300)
+    noise = snac_ref.make_noise(2, F, seed=3)
+    ref = oracle_decode_windows(oracle_w1, tok, noise)
+    lv = [sp.split_levels(row.tolist()) for row in tok]
+    codes = [torch.from_numpy(np.stack([l[k] for l in lv])) for k in range(3)]
+    got = eng.decode_codes(codes, noise=snac_ref.pack_noise(noise))[:, 0].cpu().numpy()
+    if precision == "fp32":
+        _check_wave(ref, got, TOL_FP32_MAX_ABS, 90.0)
+    else:
+        _check_wave(ref, got, TOL_MAX_ABS, TOL_SNR_DB)
+
+
+def test_full_size_properties(engines):
+    """BASELINE config sizes (1024 windows): size-independent properties instead of an oracle run -
+    batch independence (a window's PCM does not depend on its batch or position) and determinism."""
+    eng = engines("fp16")
+    tok = windows_tokens(1024, 4, 2000)
+    pcm, st = eng.decode_windows(tok, noise="philox", seed=5, keys=list(range(1024)))
+    pcm = pcm.copy()
+    assert (st == _lib.WIN_OK).all() and pcm.any(axis=1).all()
+    idx = [0, 1, 511, 777, 1023]
+    sub, _ = eng.decode_windows(tok[idx], noise="philox", seed=5, keys=idx)
+    assert np.array_equal(sub, pcm[idx])
+    perm = np.random.default_rng(0).permutation(1024)
+    again, _ = eng.decode_windows(tok[perm], noise="philox", seed=5, keys=perm.tolist())
+    assert np.array_equal(again, pcm[perm])
+
+
+# ------------------------------------------------------------------------------------ the Python boundary
+def test_speechpipe_module_matches_oracle_stream(oracle_w1, state_dict_w1, monkeypatch):
+    monkeypatch.setenv("SNACB_NOISE", "off")
+    monkeypatch.setenv("SNACB_PRECISION", "fp32")
+    monkeypatch.setenv("SNACB_RANDOM_INIT", "0:w1")  # no checkpoint on the box: seeded weights == state_dict_w1
+    monkeypatch.delenv("ORPHEUS_SNAC_PATH", raising=False)
+    import importlib
+    import sys
+    sys.modules.pop("project_morpheus_b200.speechpipe", None)
+    speechpipe = importlib.import_module("project_morpheus_b200.speechpipe")
+    assert speechpipe.snac_device == "cuda" and speechpipe.noise_mode == "off"
+    strings = sp.synth_token_strings(0, 14)
+
+    async def go():
+        async def gen():
+            for s in strings:
+                yield s
+        return [c async for c in speechpipe.tokens_decoder(gen())]
+
+    got = asyncio.run(go())
+
+    def decode(c0, c1, c2):
+        codes = [torch.from_numpy(c.astype(np.int64))[None] for c in (c0, c1, c2)]
+        return oracle_w1.decode(codes)[0, 0].numpy()
+
+    oracle_w1.set_noise("off")
+    want = list(sp.decode_stream(strings, lambda w: sp.window_to_pcm(w, decode)))
+    assert [len(c) for c in got] == [len(c) for c in want] == load_golden()["g4_config1"]["sizes"]
+    for a, b in zip(got, want):
+        if a:
+            d = np.abs(np.frombuffer(a, "<i2").astype(np.int32) - np.frombuffer(b, "<i2").astype(np.int32))
+            assert d.max() <= 1
+    # conventions: None / b'' / IndexError
+    assert speechpipe.convert_to_audio([5] * 6, 0) is None
+    assert speechpipe.convert_to_audio([5] * 7, 0) == b""
+    assert speechpipe.convert_to_audio([-1] + [5] * 27, 0) is None
+    with pytest.raises(IndexError):
+        speechpipe.convert_to_audio([4096] + [5] * 27, 0)
+    outs = speechpipe.convert_to_audio_batch([[5] * 28, [4096] + [5] * 27, [5] * 7, [5] * 3, strings and [9] * 49])
+    assert [None if o is None else len(o) for o in outs] == [4096, None, 0, None, 4096]
+
+
+def test_snac_shim_runs_decode_like_reference(oracle_w1, state_dict_w1):
+    from project_morpheus_b200 import snac as snac_mod
+    m = snac_mod.SNAC.from_state_dict(state_dict_w1, precision="fp32", noise="off").eval().to("cuda")
+    codes = [torch.randint(0, 4096, (2, 4 * k), generator=torch.Generator().manual_seed(1)) for k in (1, 2, 4)]
+    y = m.decode([c.cuda().to(torch.int32) for c in codes])
+    oracle_w1.set_noise("off")
+    ref = oracle_w1.decode(codes)
+    assert y.shape == ref.shape and y.is_cuda and y.dtype == torch.float32
+    assert float((y.cpu() - ref).abs().max()) <= TOL_FP32_MAX_ABS
+    with pytest.raises(IndexError):
+        m.decode([torch.full((1, k), 4096, dtype=torch.int32, device="cuda") for k in (1, 2, 4)])
