@@ -18,14 +18,17 @@ thread_local std::string g_create_error;
 
 struct RuDev {
   float *a1, *i1, *dw_w, *dw_b, *a2, *i2, *pw_w, *pw_b;
+  __half* pw16;
 };
 struct BlockDev {
   float *alpha, *inv, *ct_w /*[s*Cout][2*Cin]*/, *ct_b, *noise_w;
+  __half *ct16, *noise16;
   RuDev ru[3];
 };
 struct DevWeights {
   QuantW q;
   float *head_dw_w /*[7][768]*/, *head_dw_b, *head_pw_w, *head_pw_b;
+  __half* head_pw16;
   BlockDev blk[4];
   float *tail_alpha, *tail_inv, *tail_w /*[7][64]*/, *tail_b;
 };
@@ -57,6 +60,7 @@ struct snacb_engine {
   DevWeights w{};
   void* warena = nullptr;
   size_t warena_bytes = 0;
+  __half* harena = nullptr;  // fp16 copies of the GEMM-shaped weights (tensor-core recipe)
   char* ws = nullptr;
   size_t ws_bytes = 0;
   // pinned + device staging for the host-buffer API and the item tables
@@ -310,6 +314,155 @@ int run_group_f32(snacb_engine* e, const Plan& P, const Item* d_items, int n_tot
   return SNACB_OK;
 }
 
+// Tensor-core recipe: fp16 operands through TMA + tcgen05, fp32 residual stream, fused epilogues.
+// Buffers per chunk: Z (latent, fp32), X/Y (fp32 residual stream ping-pong), P/Q (fp16 GEMM operands).
+int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_total, int out_len, Rng tail_out,
+                 const int32_t* c0, const int32_t* c1, const int32_t* c2, int pitch0, const NoiseCfg& nz,
+                 const int32_t* d_status, float* wav, int16_t* pcm, char* ws_free, size_t ws_avail, int chunk,
+                 cudaStream_t st) {
+  const DevWeights& W = e->w;
+  const size_t Zf = (size_t)P.z.n() * kLatent, S = P.max_stage_floats;
+  const int F = P.T0 / 4;
+  const int noise_off[4] = {0, 32 * F, 288 * F, 1312 * F};
+  cudaError_t ce = cudaSuccess;
+
+  for (int start = 0; start < n_total; start += chunk) {
+    const int n = std::min(chunk, n_total - start);
+    const bool first = start == 0;
+    Bump bp(ws_free);
+    float* Z = bp.take<float>(Zf * n);
+    float* X = bp.take<float>(S * n);
+    float* Y = bp.take<float>(S * n);
+    __half* P16 = bp.take<__half>(S * n);
+    __half* Q16 = bp.take<__half>(S * n);
+    if (bp.off > ws_avail) return fail(e, SNACB_ENOMEM, "workspace overflow in tensor-core pipeline");
+    GroupCtx g{d_items ? d_items + start : nullptr, start, n, out_len, P.T0, st, &e->launches};
+
+    auto gemm = [&](const TcGemmArgs& a) {
+      if (ce != cudaSuccess) return;
+      const double M = (double)n * a.a_rows, segs = a.epi == EPI_CONVT ? 2.0 : 1.0;
+      const double flops = 2.0 * M * a.N * a.K * segs;
+      const double by = 2.0 * (M * a.K * segs + (double)a.N * a.K * segs) +
+                        (double)n * a.o_r.n() * a.ldo * ((a.out32 ? 4.0 : 0.0) + (a.out16 ? 2.0 : 0.0) + (a.R ? 4.0 : 0.0));
+      ProfScope ps(e, a.epi == EPI_CONVT ? KC_CONVT : KC_GEMM1, flops, by, st);
+      ce = launch_gemm_tc(g, a);
+    };
+    {
+      ProfScope ps(e, KC_CODES, 2.0 * 24 * kLatent * n * P.z.n(), 4.0 * kLatent * n * P.z.n(), st);
+      launch_from_codes(g, W.q, c0, c1, c2, pitch0, P.z, Z);
+    }
+    tap(e, 0, Z, P.z, kLatent, n, first, st);
+    {  // decoder.model.0: depthwise k7 -> fp16 operand of the 1x1
+      DwArgs d{Z, P.z, nullptr, P.h, kLatent, 1, 1, W.head_dw_w, W.head_dw_b, nullptr, nullptr, nullptr, nullptr};
+      const double el = (double)n * P.h.n() * kLatent;
+      ProfScope ps(e, KC_DW, el * 14.0, 4.0 * (double)n * P.z.n() * kLatent + 2.0 * el, st);
+      launch_dwconv_half(g, d, P16);
+    }
+    __half* Ain = Q16;    // block input operand (Snake'd, fp16)
+    __half* Aother = P16;
+    {  // decoder.model.1: 1x1 768->1024 + bias, then block 0's Snake, written as fp16
+      TcGemmArgs a{};
+      a.epi = EPI_BIAS; a.A = P16; a.K = kLatent; a.a_rows = P.h.n(); a.a_lo = P.h.lo; a.W = W.head_pw16; a.N = kDecDim;
+      a.bias = W.head_pw_b; a.out16 = Ain; a.o_r = P.h; a.ldo = kDecDim; a.sn_alpha = W.blk[0].alpha; a.sn_inv = W.blk[0].inv;
+      a.up = 1;
+      if (e->tap_stage == 2) a.out32 = X;
+      gemm(a);
+      tap(e, 2, X, P.h, kDecDim, n, first, st);
+    }
+    for (int b = 0; b < 4 && ce == cudaSuccess; ++b) {
+      const BlockPlan& B = P.b[b];
+      const BlockDev& Wb = W.blk[b];
+      const int sid = 3 + 9 * b;
+      const bool noisy = nz.mode != SNACB_NOISE_OFF;
+      __half* Y16 = Aother;  // transposed-conv output as the noise GEMM operand
+      {
+        TcGemmArgs a{};
+        a.epi = EPI_CONVT; a.A = Ain; a.K = B.Cin; a.a_rows = B.in.n(); a.a_lo = B.in.lo; a.W = Wb.ct16; a.N = B.s * B.Cout;
+        a.bias = Wb.ct_b; a.s = B.s; a.p = B.p; a.Cout = B.Cout; a.o_r = B.ct; a.ldo = B.Cout; a.up = B.up_out;
+        a.out32 = noisy ? Y : X; a.out16 = noisy ? Y16 : nullptr;
+        gemm(a);
+        tap(e, sid + 1, noisy ? Y : X, B.ct, B.Cout, n, first, st);
+      }
+      if (noisy) {
+        TcGemmArgs a{};
+        a.epi = EPI_NOISE; a.A = Y16; a.K = B.Cout; a.a_rows = B.ct.n(); a.a_lo = B.ct.lo; a.W = Wb.noise16; a.N = B.Cout;
+        a.out32 = X; a.o_r = B.ct; a.ldo = B.Cout; a.R = Y; a.r_r = B.ct; a.ldr = B.Cout; a.up = B.up_out;
+        a.noise = NoiseSrc{nz.mode, nz.tensor, nz.stride, noise_off[b], (unsigned long long)nz.seed, nz.d_keys, b};
+        gemm(a);
+      }
+      tap(e, sid + 2, X, B.ct, B.Cout, n, first, st);
+      // X holds the residual stream; Ain (dead after the transposed conv) becomes the dw output operand
+      __half* D16 = Ain;
+      __half* Anext = Aother;
+      Rng cur = B.ct;
+      for (int r = 0; r < 3 && ce == cudaSuccess; ++r) {
+        const RuDev& R = Wb.ru[r];
+        {
+          DwTcArgs d{X, cur, D16, B.r[r], B.Cout, kDil[r], B.up_out, R.dw_w, R.dw_b, R.a1, R.i1, R.a2, R.i2};
+          const double el = (double)n * B.r[r].n() * B.Cout;
+          ProfScope ps(e, KC_DW, el * 24.0, (double)n * cur.n() * B.Cout * 4.0 + el * 2.0, st);
+          launch_dw_tc(g, d);
+        }
+        const bool last = (r == 2) && (b < 3);  // the block output only feeds the next block's Snake + ConvT
+        TcGemmArgs a{};
+        a.epi = EPI_RESID; a.A = D16; a.K = B.Cout; a.a_rows = B.r[r].n(); a.a_lo = B.r[r].lo; a.W = R.pw16; a.N = B.Cout;
+        a.bias = R.pw_b; a.o_r = B.r[r]; a.ldo = B.Cout; a.R = X; a.r_r = cur; a.ldr = B.Cout; a.up = B.up_out;
+        const bool want32 = !last || e->tap_stage == sid + 4 + 2 * r;
+        a.out32 = want32 ? Y : nullptr;
+        if (last) { a.out16 = Anext; a.sn_alpha = W.blk[b + 1].alpha; a.sn_inv = W.blk[b + 1].inv; }
+        gemm(a);
+        tap(e, sid + 4 + 2 * r, Y, B.r[r], B.Cout, n, first, st);
+        std::swap(X, Y);
+        cur = B.r[r];
+      }
+      Ain = Anext;
+      Aother = D16;
+    }
+    if (ce != cudaSuccess) return fail(e, SNACB_ECUDA, "tensor-core GEMM launch failed: %s", cudaGetErrorString(ce));
+    {
+      const double smp = (double)n * tail_out.n();
+      ProfScope ps(e, KC_TAIL, smp * (2.0 * 448 + 4.0 * 64), 4.0 * (double)n * P.b[3].r[2].n() * 64 + smp * 2.0, st);
+      TailArgs t{X, P.b[3].r[2], tail_out, W.tail_alpha, W.tail_inv, W.tail_w, W.tail_b, d_status, wav, pcm};
+      launch_tail(g, t);
+    }
+    int rc = check_launch(e, "tensor-core layer pipeline");
+    if (rc) return rc;
+  }
+  return SNACB_OK;
+}
+
+// ---- sizing shared by every entry point
+Plan plan_for(const snacb_engine* e, int T0, Rng out, bool clip) {
+  return make_plan(T0, out, clip, e->cfg.precision == SNACB_PREC_FP16);
+}
+size_t per_item_bytes(const snacb_engine* e, const Plan& P) {
+  const size_t Zb = pad256((size_t)P.z.n() * kLatent * 4), Sb = pad256(P.max_stage_floats * 4);
+  if (e->cfg.precision == SNACB_PREC_FP16) return Zb + 2 * Sb + 2 * pad256(P.max_stage_floats * 2) + 2048;
+  return Zb + pad256((size_t)P.h.n() * kLatent * 4) + 3 * Sb + 1024;
+}
+constexpr size_t kActBudget = size_t(6) << 30;  // activation workspace cap per engine
+int default_chunk(const snacb_engine* e) { return e->cfg.chunk_items > 0 ? e->cfg.chunk_items : 32; }
+size_t act_bytes(const snacb_engine* e, const Plan& P, int count) {
+  const size_t per = per_item_bytes(e, P);
+  const int chunk = std::max(1, std::min(count, default_chunk(e)));
+  return std::max(per, std::min(kActBudget, per * chunk)) + 4096;
+}
+
+int run_group(snacb_engine* e, const Plan& P, const Item* d_items, int n_total, int out_len, Rng tail_out,
+              const int32_t* c0, const int32_t* c1, const int32_t* c2, int pitch0, const NoiseCfg& nz,
+              const int32_t* d_status, float* wav, int16_t* pcm, char* ws_free, size_t ws_avail, cudaStream_t st) {
+  if (e->cfg.precision == SNACB_PREC_FP16) {
+    const size_t per = per_item_bytes(e, P);
+    int chunk = default_chunk(e);
+    if ((size_t)chunk * per > ws_avail) chunk = (int)(ws_avail / per);
+    if (chunk < 1) return fail(e, SNACB_ENOMEM, "workspace too small for one item");
+    return run_group_tc(e, P, d_items, n_total, out_len, tail_out, c0, c1, c2, pitch0, nz, d_status, wav, pcm, ws_free,
+                        ws_avail, chunk, st);
+  }
+  return run_group_f32(e, P, d_items, n_total, out_len, tail_out, c0, c1, c2, pitch0, nz, d_status, wav, pcm, ws_free,
+                       ws_avail, st);
+}
+
 int upload_items(snacb_engine* e, const std::vector<Item>& items, Item* d_dst, cudaStream_t st) {
   if (!e->items_ev) CU(e, cudaEventCreateWithFlags(&e->items_ev, cudaEventDisableTiming));
   else CU(e, cudaEventSynchronize(e->items_ev));
@@ -323,8 +476,6 @@ int upload_items(snacb_engine* e, const std::vector<Item>& items, Item* d_dst, c
   CU(e, cudaEventRecord(e->items_ev, st));
   return SNACB_OK;
 }
-
-constexpr size_t kActBudget = size_t(6) << 30;  // activation workspace cap per engine
 
 }  // namespace
 
@@ -361,6 +512,7 @@ void snacb_destroy(snacb_engine* e) {
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
   if (e->warena) cudaFree(e->warena);
+  if (e->harena) cudaFree(e->harena);
   if (e->ws) cudaFree(e->ws);
   if (e->dstage) cudaFree(e->dstage);
   if (e->pin) cudaFreeHost(e->pin);
@@ -434,6 +586,31 @@ int snacb_load_weights(snacb_engine* e, const snacb_weights* w) {
   e->warena_bytes = bytes;
   CU(e, cudaMemcpy(e->warena, hp.data.data(), bytes, cudaMemcpyHostToDevice));
   for (const Fix& f : fix) *f.dst = reinterpret_cast<float*>(e->warena) + f.off;
+
+  // fp16 operand copies for the tensor-core recipe
+  if (e->harena) { CU(e, cudaFree(e->harena)); e->harena = nullptr; }
+  if (e->cfg.precision == SNACB_PREC_FP16) {
+    struct H { __half** dst; const float* src; size_t n; size_t off; };
+    std::vector<H> hs;
+    size_t hoff = 0;
+    auto hput = [&](__half** dst, const float* src, size_t n) { hs.push_back({dst, src, n, hoff}); hoff += (n + 127) & ~size_t(127); };
+    hput(&D.head_pw16, D.head_pw_w, (size_t)kDecDim * kLatent);
+    int ci = kDecDim;
+    for (int b = 0; b < 4; ++b) {
+      const int co = ci / 2;
+      hput(&D.blk[b].ct16, D.blk[b].ct_w, (size_t)kRates[b] * co * 2 * ci);
+      hput(&D.blk[b].noise16, D.blk[b].noise_w, (size_t)co * co);
+      for (int r = 0; r < 3; ++r) hput(&D.blk[b].ru[r].pw16, D.blk[b].ru[r].pw_w, (size_t)co * co);
+      ci = co;
+    }
+    CU(e, cudaMalloc((void**)&e->harena, hoff * sizeof(__half)));
+    for (const H& h : hs) {
+      *h.dst = e->harena + h.off;
+      launch_to_half(h.src, *h.dst, h.n, 0);
+    }
+    CU(e, cudaGetLastError());
+    CU(e, cudaDeviceSynchronize());
+  }
   e->loaded = true;
   return SNACB_OK;
 }
@@ -524,12 +701,9 @@ int snacb_decode_windows(snacb_engine* e, const int32_t* d_tokens, int32_t token
   if (h_ntok) for (auto& kv : groups) Fs.push_back(kv.first); else if (maxF >= 2) Fs.push_back(maxF);
   const Rng slice{2048, 4096};
   for (int F : Fs) {
-    Plan P = make_plan(4 * F, e->cfg.trim ? slice : Rng{0, 2048 * F}, true);
-    const size_t per_item = pad256((size_t)P.z.n() * kLatent * 4) + pad256((size_t)P.h.n() * kLatent * 4) + 3 * pad256(P.max_stage_floats * 4) + 1024;
+    Plan P = plan_for(e, 4 * F, e->cfg.trim ? slice : Rng{0, 2048 * F}, true);
     const int cnt = h_ntok ? (int)groups[F].size() : n_win;
-    const int chunk = std::min(cnt, e->cfg.chunk_items > 0 ? e->cfg.chunk_items : 32);
-    act = std::max(act, std::min(kActBudget, per_item * chunk));
-    act = std::max(act, per_item);
+    act = std::max(act, act_bytes(e, P, cnt));
   }
   int rc = ensure_ws(e, fixed + act, st);
   if (rc) return rc;
@@ -559,8 +733,8 @@ int snacb_decode_windows(snacb_engine* e, const int32_t* d_tokens, int32_t token
 
   if (!h_ntok) {
     if (maxF >= 2 && ntok_uniform >= 14) {
-      Plan P = make_plan(4 * maxF, e->cfg.trim ? slice : Rng{0, 2048 * maxF}, true);
-      rc = run_group_f32(e, P, nullptr, n_win, 2048, slice, c0, c1, c2, maxF, nz, d_status, nullptr, d_pcm, ws_free, ws_avail, st);
+      Plan P = plan_for(e, 4 * maxF, e->cfg.trim ? slice : Rng{0, 2048 * maxF}, true);
+      rc = run_group(e, P, nullptr, n_win, 2048, slice, c0, c1, c2, maxF, nz, d_status, nullptr, d_pcm, ws_free, ws_avail, st);
       if (rc) return rc;
     }
   } else {
@@ -576,8 +750,8 @@ int snacb_decode_windows(snacb_engine* e, const int32_t* d_tokens, int32_t token
       rc = upload_items(e, all, d_items, st);
       if (rc) return rc;
       for (auto& r : runs) {
-        Plan P = make_plan(4 * r.first, e->cfg.trim ? slice : Rng{0, 2048 * r.first}, true);
-        rc = run_group_f32(e, P, d_items + r.second.first, r.second.second, 2048, slice, c0, c1, c2, maxF, nz, d_status,
+        Plan P = plan_for(e, 4 * r.first, e->cfg.trim ? slice : Rng{0, 2048 * r.first}, true);
+        rc = run_group(e, P, d_items + r.second.first, r.second.second, 2048, slice, c0, c1, c2, maxF, nz, d_status,
                            nullptr, d_pcm, ws_free, ws_avail, st);
         if (rc) return rc;
       }
@@ -660,12 +834,10 @@ int snacb_decode_codes(snacb_engine* e, const int32_t* d_c0, const int32_t* d_c1
   NoiseCfg nz{noise_mode, d_noise, (long long)kNoisePerFrame * F, seed, nullptr};
   const int kTileFrames = 8;
   if (F <= 2 * kTileFrames) {
-    Plan P = make_plan(4 * F, Rng{0, 2048 * F}, true);
-    const size_t per_item = pad256((size_t)P.z.n() * kLatent * 4) + pad256((size_t)P.h.n() * kLatent * 4) + 3 * pad256(P.max_stage_floats * 4) + 1024;
-    const int chunk = std::min((int)B, e->cfg.chunk_items > 0 ? e->cfg.chunk_items : 32);
-    int rc = ensure_ws(e, std::max(per_item, std::min(kActBudget, per_item * chunk)) + 4096, st);
+    Plan P = plan_for(e, 4 * F, Rng{0, 2048 * F}, true);
+    int rc = ensure_ws(e, act_bytes(e, P, B), st);
     if (rc) return rc;
-    return run_group_f32(e, P, nullptr, B, 2048 * F, P.out, d_c0, d_c1, d_c2, F, nz, nullptr, d_wav, d_pcm, e->ws, e->ws_bytes, st);
+    return run_group(e, P, nullptr, B, 2048 * F, P.out, d_c0, d_c1, d_c2, F, nz, nullptr, d_wav, d_pcm, e->ws, e->ws_bytes, st);
   }
   // long sequence: uniform time tiles with halo recompute; rows outside [0, T) are explicit zeros.
   const int tiles = (F + kTileFrames - 1) / kTileFrames;
@@ -674,16 +846,14 @@ int snacb_decode_codes(snacb_engine* e, const int32_t* d_c0, const int32_t* d_c1
   for (int b = 0; b < B; ++b)
     for (int k = 0; k < tiles; ++k)
       items.push_back(Item{b, k * kTileFrames * 4, (int64_t)b * 2048 * F + (int64_t)k * kTileFrames * 2048});
-  Plan P = make_plan(4 * F, Rng{0, 2048 * kTileFrames}, false);
-  const size_t per_item = pad256((size_t)P.z.n() * kLatent * 4) + pad256((size_t)P.h.n() * kLatent * 4) + 3 * pad256(P.max_stage_floats * 4) + 1024;
-  const int chunk = std::min((int)items.size(), e->cfg.chunk_items > 0 ? e->cfg.chunk_items : 32);
+  Plan P = plan_for(e, 4 * F, Rng{0, 2048 * kTileFrames}, false);
   const size_t tab = pad256(items.size() * sizeof(Item)) + 256;
-  int rc = ensure_ws(e, tab + std::max(per_item, std::min(kActBudget, per_item * chunk)) + 4096, st);
+  int rc = ensure_ws(e, tab + act_bytes(e, P, (int)items.size()), st);
   if (rc) return rc;
   Item* d_items = reinterpret_cast<Item*>(e->ws);
   rc = upload_items(e, items, d_items, st);
   if (rc) return rc;
-  return run_group_f32(e, P, d_items, (int)items.size(), 2048 * kTileFrames, P.out, d_c0, d_c1, d_c2, F, nz, nullptr, d_wav,
+  return run_group(e, P, d_items, (int)items.size(), 2048 * kTileFrames, P.out, d_c0, d_c1, d_c2, F, nz, nullptr, d_wav,
                        d_pcm, e->ws + tab, e->ws_bytes - tab, st);
 }
 

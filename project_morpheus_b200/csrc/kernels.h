@@ -1,5 +1,7 @@
 // Launcher declarations shared by engine.cu and the kernel translation units.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "snacb_common.cuh"
 
 namespace snacb {
@@ -58,6 +60,35 @@ struct GemmArgs {
   int up;                             // time scale of the OUTPUT rows
 };
 void launch_gemm_f32(const GroupCtx& g, const GemmArgs& a);
+
+// ---- tensor-core recipe (kernels_tc.cu) ------------------------------------------------------
+struct TcGemmArgs {
+  int epi;                         // EPI_*
+  const __half* A; int K;          // operand [n_items * a_rows][K] fp16, K contiguous; K per segment
+  int a_rows, a_lo;                // rows per item (all are iterated) and relative time of row 0
+  const __half* W; int N;          // [N][nseg*K] fp16 (EPI_CONVT: nseg = 2, N = s*Cout)
+  const float* bias;               // [N] (EPI_CONVT: [Cout]); nullable
+  int s, p, Cout;                  // EPI_CONVT only
+  float* out32; __half* out16;     // either may be null; same row pitch ldo
+  Rng o_r; int ldo;
+  const float* sn_alpha; const float* sn_inv;  // Snake applied to the fp16 output (nullable)
+  const float* R; Rng r_r; int ldr;            // EPI_RESID residual / EPI_NOISE carrier (fp32)
+  NoiseSrc noise;
+  int up;
+};
+cudaError_t launch_gemm_tc(const GroupCtx& g, const TcGemmArgs& a);
+int tc_tile_n(const TcGemmArgs& a);
+
+struct DwTcArgs {
+  const float* in; Rng in_r;
+  __half* out; Rng out_r;
+  int C, dil, up;
+  const float* w7; const float* bias;
+  const float* a1; const float* i1; const float* a2; const float* i2;
+};
+void launch_dw_tc(const GroupCtx& g, const DwTcArgs& a);
+void launch_dwconv_half(const GroupCtx& g, const DwArgs& a, __half* out16);  // plain dw k7 -> fp16 (decoder head)
+void launch_to_half(const float* in, __half* out, size_t n, cudaStream_t st);
 
 struct TailArgs {
   const float* x; Rng x_r;  // [item][rows][64]

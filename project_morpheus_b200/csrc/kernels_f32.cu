@@ -117,8 +117,12 @@ void launch_from_codes(const GroupCtx& g, const QuantW& q, const int32_t* c0, co
 
 // ============================================================================ depthwise k=7
 // out[t][c] = post( b[c] + sum_k w[k][c] * pre(in[t + (k-3)*dil][c]) ); pre/post = Snake or identity.
-template <bool PRE, bool POST>
-__global__ void __launch_bounds__(256) k_dwconv(const Item* items, int base, int out_len, int T0, DwArgs a) {
+template <typename T> __device__ __forceinline__ void store_act(T* p, float v);
+template <> __device__ __forceinline__ void store_act<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void store_act<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+
+template <bool PRE, bool POST, typename OutT = float>
+__global__ void __launch_bounds__(256) k_dwconv(const Item* items, int base, int out_len, int T0, DwArgs a, OutT* outp) {
   const int i = blockIdx.y;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   const int rows = a.out_r.n();
@@ -127,8 +131,8 @@ __global__ void __launch_bounds__(256) k_dwconv(const Item* items, int base, int
   const ItemRef it = get_item(items, base, i, out_len);
   const int t_rel = a.out_r.lo + j;
   const int t_abs = t_rel + it.shift0 * a.up;
-  float* o = a.out + ((size_t)i * rows + j) * a.C + c;
-  if (t_abs < 0 || t_abs >= T0 * a.up) { *o = 0.0f; return; }
+  OutT* o = outp + ((size_t)i * rows + j) * a.C + c;
+  if (t_abs < 0 || t_abs >= T0 * a.up) { store_act<OutT>(o, 0.0f); return; }
   const int in_rows = a.in_r.n();
   const float* x = a.in + (size_t)i * in_rows * a.C + c;
   float al = 0.f, iv = 0.f;
@@ -143,17 +147,24 @@ __global__ void __launch_bounds__(256) k_dwconv(const Item* items, int base, int
   }
   acc += a.bias[c];
   if (POST) acc = snake_exact(acc, a.a2[c], a.i2[c]);
-  *o = acc;
+  store_act<OutT>(o, acc);
 }
 
 void launch_dwconv(const GroupCtx& g, const DwArgs& a) {
   const long long n = (long long)a.out_r.n() * a.C;
   dim3 grid((unsigned)((n + 255) / 256), g.n_items);
   const bool pre = a.a1 != nullptr, post = a.a2 != nullptr;
-  if (pre && post) k_dwconv<true, true><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, a);
-  else if (!pre && !post) k_dwconv<false, false><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, a);
-  else if (pre) k_dwconv<true, false><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, a);
-  else k_dwconv<false, true><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, a);
+  if (pre && post) k_dwconv<true, true><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, a, a.out);
+  else if (!pre && !post) k_dwconv<false, false><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, a, a.out);
+  else if (pre) k_dwconv<true, false><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, a, a.out);
+  else k_dwconv<false, true><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, a, a.out);
+  ++*g.launches;
+}
+
+void launch_dwconv_half(const GroupCtx& g, const DwArgs& a, __half* out16) {
+  const long long n = (long long)a.out_r.n() * a.C;
+  dim3 grid((unsigned)((n + 255) / 256), g.n_items);
+  k_dwconv<false, false, __half><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, a, out16);
   ++*g.launches;
 }
 

@@ -1,0 +1,482 @@
+// Tensor-core recipe (SNACB_PREC_FP16) of the SNAC-24k decoder's GEMM-shaped layers for sm_100a:
+// tcgen05.mma (kind::f16, fp16 operands, fp32 accumulators in TMEM) fed by TMA, warp-specialised
+// (TMA producer / MMA issuer / 4 epilogue warps), with the layer's bias / residual / noise / Snake
+// work fused into the epilogue, plus the register-sliding-window depthwise k=7 kernel that produces
+// the fp16 GEMM operand of every ResidualUnit.
+//
+// Replaces (third-party `snac` decoder, called at Morpheus_Client/tts_engine/speechpipe.py:118):
+//   k_gemm_tc<.., EPI_BIAS>   decoder.model.1 (1x1 768->1024)  + the Snake of block 0
+//   k_gemm_tc<.., EPI_CONVT>  DecoderBlock ConvTranspose1d (k=2s, stride s) as a polyphase GEMM
+//   k_gemm_tc<.., EPI_NOISE>  NoiseBlock  x + n[t] * (W_n x)
+//   k_gemm_tc<.., EPI_RESID>  ResidualUnit 1x1 + residual add (+ the next block's Snake)
+//   k_dw_tc                   ResidualUnit Snake -> depthwise k7 (dil 1/3/9) -> Snake
+//
+// GEMM view: D[m][n] = sum_k A[m][k] * W[n][k]; rows m = time steps (channels-last activations, so K
+// is contiguous = "K-major" for both operands), n = output channels.  One CTA computes a 128 x BN
+// tile: 128 TMEM lanes x BN fp32 columns.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <cstdio>
+#include <mutex>
+#include <unordered_map>
+
+#include "kernels.h"
+#include "snacb.h"
+
+namespace snacb {
+namespace {
+
+constexpr int BM = 128;  // rows per tile = TMEM lanes
+constexpr int BK = 64;   // fp16 per k-block = one 128-byte swizzle span
+constexpr int kTcThreads = 192;
+constexpr uint32_t kLiveFlag = 0x40000000u;
+
+// ------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a trap (CUDA error) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) {
+      printf("snacb: mbarrier timeout, block (%d,%d) thread %d\n", (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives once every previously issued tcgen05.mma of this thread has completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor of a K-major operand tile written by TMA with SWIZZLE_128B:
+// rows of 128 bytes (64 fp16 of K), 8-row groups of 1024 bytes (SBO), tile base 1024-byte aligned.
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major), bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset = 8 rows * 128 B, bits [32,46)
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell), bits [46,48)
+  d |= (uint64_t)2 << 61;                    // layout type SWIZZLE_128B, bits [61,64)
+  return d;
+}
+// kind::f16 instruction descriptor: fp16 A/B (K-major), fp32 D, M = 128, N = BN.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int n) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float snake_fast(float x, float alpha, float inv) {
+  const float s = __sinf(alpha * x);
+  return fmaf(inv, s * s, x);
+}
+
+struct TcDev {
+  const Item* items; int base, out_len, T0, n_items;
+  int K, nseg;              // K per segment; ConvT has 2 segments (taps of q and q +- 1)
+  int a_rows, a_lo;         // operand rows per item, relative time of operand row 0
+  int s, p, Cout;           // ConvT only
+  const float* bias;
+  float* out32; __half* out16; int o_lo, o_rows, ldo;
+  const float* sn_alpha; const float* sn_inv;
+  const float* R; int r_lo, r_rows, ldr;
+  NoiseSrc noise;
+  int up;
+};
+
+template <int BN> struct TcSmem {
+  static constexpr int kStages = (BN == 64) ? 4 : 3;
+  static constexpr int kStageBytes = BM * BK * 2 + BN * BK * 2;
+  static constexpr int kMetaBytes = 3 * BM * 4 + 128;
+  static constexpr int kBytes = kStages * kStageBytes + kMetaBytes + 1024;  // + alignment slack
+  static_assert(kStages * kStageBytes >= 4 * 32 * 32 * 4, "epilogue staging aliases the pipeline stages");
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kTcThreads) k_gemm_tc(const __grid_constant__ CUtensorMap tmA,
+                                                         const __grid_constant__ CUtensorMap tmW, const TcDev a) {
+  using S = TcSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* meta = smem + S::kStages * S::kStageBytes;
+  int* meta_out = reinterpret_cast<int*>(meta);
+  int* meta_res = meta_out + BM;
+  float* meta_nz = reinterpret_cast<float*>(meta_res + BM);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(meta + 3 * BM * 4);  // full[kStages], empty[kStages], accum
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const long long Mtot = (long long)a.n_items * a.a_rows;
+  int phase = 0, delta = 0;
+  if (EPI == EPI_CONVT) { phase = n0 / a.Cout; delta = (phase < a.s - a.p) ? -1 : 1; }
+  const int kb_per_seg = a.K / BK;
+  const int num_kb = kb_per_seg * a.nseg;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S::kStages; ++i) {
+      mbar_init(smem_u32(&bars[i]), 1);
+      mbar_init(smem_u32(&bars[S::kStages + i]), 1);
+    }
+    mbar_init(smem_u32(&bars[2 * S::kStages]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int st = kb % S::kStages;
+        mbar_wait(smem_u32(&bars[S::kStages + st]), ((kb / S::kStages) & 1) ^ 1);
+        const uint32_t full = smem_u32(&bars[st]);
+        const uint32_t sa = smem_u32(smem + st * S::kStageBytes), sb = sa + BM * BK * 2;
+        const int seg = kb / kb_per_seg, kk = (kb - seg * kb_per_seg) * BK;
+        mbar_arrive_expect_tx(full, S::kStageBytes);
+        tma_load_2d(sa, &tmA, full, kk, m0 + (seg ? delta : 0));
+        tma_load_2d(sb, &tmW, full, seg * a.K + kk, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int st = kb % S::kStages;
+        mbar_wait(smem_u32(&bars[st]), (kb / S::kStages) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + st * S::kStageBytes), sb = sa + BM * BK * 2;
+        const uint64_t da = umma_desc_k_sw128(sa), db = umma_desc_k_sw128(sb);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)  // UMMA_K = 16 fp16 = 32 bytes: advance the start address by 2 (x16 B)
+          umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+        umma_commit(smem_u32(&bars[S::kStages + st]));  // frees the stage once these MMAs have read it
+      }
+      umma_commit(smem_u32(&bars[2 * S::kStages]));     // accumulator complete
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int q = warp & 3;            // TMEM lane quarter this warp may read
+    const int trow = q * 32 + lane;    // tile row owned in TMEM
+    {
+      const long long gm = (long long)m0 + trow;
+      int oi = -1, ri = -1;
+      float nz = 0.0f;
+      if (gm < Mtot) {
+        const int item = (int)(gm / a.a_rows), j = (int)(gm - (long long)item * a.a_rows);
+        const ItemRef it = get_item(a.items, a.base, item, a.out_len);
+        int t_rel = a.a_lo + j;
+        if (EPI == EPI_CONVT) t_rel = t_rel * a.s + phase;
+        const int orow = t_rel - a.o_lo;
+        if (orow >= 0 && orow < a.o_rows) {
+          const int t_abs = t_rel + it.shift0 * a.up;
+          const bool live = (t_abs >= 0) && (t_abs < a.T0 * a.up);
+          oi = item * a.o_rows + orow;
+          if (EPI == EPI_RESID || EPI == EPI_NOISE) ri = item * a.r_rows + (t_rel - a.r_lo);
+          if (EPI == EPI_NOISE && live) nz = noise_at(a.noise, it.code_row, t_abs);
+          if (!live) oi |= (int)kLiveFlag;
+        }
+      }
+      meta_out[trow] = oi; meta_res[trow] = ri; meta_nz[trow] = nz;
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(&bars[2 * S::kStages]), 0);
+    tc_fence_after();
+    float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 32);  // aliases stage 0: all MMAs are done
+    const int cg = lane & 7, rr = lane >> 3;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+            make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                        __uint_as_float(r[4 * j + 3]));
+      __syncwarp();
+      const int ocol = n0 + c * 32 + cg * 4 - ((EPI == EPI_CONVT) ? phase * a.Cout : 0);
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), al = b4, iv = b4;
+      if (a.bias) b4 = *reinterpret_cast<const float4*>(a.bias + ocol);
+      if (a.sn_alpha) { al = *reinterpret_cast<const float4*>(a.sn_alpha + ocol); iv = *reinterpret_cast<const float4*>(a.sn_inv + ocol); }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = rr + 4 * i;
+        int oi = meta_out[q * 32 + row];
+        if (oi < 0) continue;
+        const bool live = !(oi & (int)kLiveFlag);
+        oi &= (int)(kLiveFlag - 1);
+        float4 v = *reinterpret_cast<const float4*>(stg + row * 32 + ((cg ^ (row & 7)) << 2));
+        v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+        if (EPI == EPI_RESID || EPI == EPI_NOISE) {
+          const float4 r4 = *reinterpret_cast<const float4*>(a.R + (size_t)meta_res[q * 32 + row] * a.ldr + ocol);
+          if (EPI == EPI_NOISE) {
+            const float nz = meta_nz[q * 32 + row];
+            v.x = fmaf(nz, v.x, r4.x); v.y = fmaf(nz, v.y, r4.y); v.z = fmaf(nz, v.z, r4.z); v.w = fmaf(nz, v.w, r4.w);
+          } else {
+            v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
+          }
+        }
+        if (!live) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const size_t o = (size_t)oi * a.ldo + ocol;
+        if (a.out32) *reinterpret_cast<float4*>(a.out32 + o) = v;
+        if (a.out16) {
+          if (a.sn_alpha) {
+            v.x = snake_fast(v.x, al.x, iv.x); v.y = snake_fast(v.y, al.y, iv.y);
+            v.z = snake_fast(v.z, al.z, iv.z); v.w = snake_fast(v.w, al.w, iv.w);
+          }
+          const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+          pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+          *reinterpret_cast<uint2*>(a.out16 + o) = pk;
+        }
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+struct MapKey {
+  const void* p; long long rows; int cols, box_rows;
+  bool operator==(const MapKey& o) const { return p == o.p && rows == o.rows && cols == o.cols && box_rows == o.box_rows; }
+};
+struct MapHash {
+  size_t operator()(const MapKey& k) const {
+    return std::hash<const void*>()(k.p) ^ (std::hash<long long>()(k.rows) * 1000003u) ^ ((size_t)k.cols << 20) ^ (size_t)k.box_rows;
+  }
+};
+
+// [rows][cols] fp16 row-major, box = 64 columns x box_rows rows, 128-byte swizzle, zero fill out of bounds.
+bool get_tmap(const void* ptr, long long rows, int cols, int box_rows, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapHash> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  const MapKey key{ptr, rows, cols, box_rows};
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return true; }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, m);
+  *out = m;
+  return true;
+}
+
+template <int BN, int EPI>
+cudaError_t launch_tc_t(const CUtensorMap& ma, const CUtensorMap& mw, const TcDev& d, dim3 grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::kBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  k_gemm_tc<BN, EPI><<<grid, kTcThreads, TcSmem<BN>::kBytes, st>>>(ma, mw, d);
+  return cudaGetLastError();
+}
+
+template <int BN>
+cudaError_t launch_tc_bn(int epi, const CUtensorMap& ma, const CUtensorMap& mw, const TcDev& d, dim3 grid, cudaStream_t st) {
+  switch (epi) {
+    case EPI_BIAS: return launch_tc_t<BN, EPI_BIAS>(ma, mw, d, grid, st);
+    case EPI_RESID: return launch_tc_t<BN, EPI_RESID>(ma, mw, d, grid, st);
+    case EPI_NOISE: return launch_tc_t<BN, EPI_NOISE>(ma, mw, d, grid, st);
+    default: return launch_tc_t<BN, EPI_CONVT>(ma, mw, d, grid, st);
+  }
+}
+
+}  // namespace
+
+int tc_tile_n(const TcGemmArgs& a) {
+  const int per = (a.epi == EPI_CONVT) ? a.Cout : a.N;
+  return per >= 128 ? 128 : 64;
+}
+
+cudaError_t launch_gemm_tc(const GroupCtx& g, const TcGemmArgs& a) {
+  const long long Mtot = (long long)g.n_items * a.a_rows;
+  if (Mtot <= 0) return cudaSuccess;
+  const int nseg = (a.epi == EPI_CONVT) ? 2 : 1;
+  const int bn = tc_tile_n(a);
+  if (a.K % BK || a.N % bn || (a.epi == EPI_CONVT && a.Cout % bn)) return cudaErrorInvalidValue;
+  CUtensorMap ma, mw;
+  if (!get_tmap(a.A, Mtot, a.K, BM, &ma) || !get_tmap(a.W, a.N, nseg * a.K, bn, &mw)) return cudaErrorNotSupported;
+  TcDev d{};
+  d.items = g.items; d.base = g.base; d.out_len = g.out_len; d.T0 = g.T0; d.n_items = g.n_items;
+  d.K = a.K; d.nseg = nseg; d.a_rows = a.a_rows; d.a_lo = a.a_lo; d.s = a.s; d.p = a.p; d.Cout = a.Cout;
+  d.bias = a.bias; d.out32 = a.out32; d.out16 = a.out16; d.o_lo = a.o_r.lo; d.o_rows = a.o_r.n(); d.ldo = a.ldo;
+  d.sn_alpha = a.sn_alpha; d.sn_inv = a.sn_inv; d.R = a.R; d.r_lo = a.r_r.lo; d.r_rows = a.r_r.n(); d.ldr = a.ldr;
+  d.noise = a.noise; d.up = a.up;
+  dim3 grid((unsigned)((Mtot + BM - 1) / BM), (unsigned)(a.N / bn));
+  cudaError_t e = (bn == 128) ? launch_tc_bn<128>(a.epi, ma, mw, d, grid, g.stream) : launch_tc_bn<64>(a.epi, ma, mw, d, grid, g.stream);
+  ++*g.launches;
+  return e;
+}
+
+// ============================================================================ depthwise k=7 -> fp16
+// Each thread owns two adjacent channels and walks one residue class (mod dil) of a 32*dil-row
+// segment: a 7-deep register window slides along time, so every input is loaded and Snake'd once
+// (38 loads for 32 outputs).  Output = Snake(b + sum_k w[k] * Snake(x[t + (k-3)*dil])) as fp16, the
+// K-major operand of the ResidualUnit's 1x1 GEMM.
+template <int DIL>
+__global__ void __launch_bounds__(256) k_dw_tc(const Item* items, int base, int out_len, int T0, DwTcArgs a) {
+  const int CP = a.C >> 1;
+  const int item = blockIdx.y;
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const int cp = idx % CP, rest = idx / CP;
+  const int rho = rest % DIL, seg = rest / DIL;
+  const int out_rows = a.out_r.n(), in_rows = a.in_r.n();
+  const int row0 = seg * 32 * DIL + rho;
+  if (row0 >= out_rows) return;
+  const int c = cp * 2;
+  const ItemRef it = get_item(items, base, item, out_len);
+  const float2 al1 = *reinterpret_cast<const float2*>(a.a1 + c), iv1 = *reinterpret_cast<const float2*>(a.i1 + c);
+  const float2 al2 = *reinterpret_cast<const float2*>(a.a2 + c), iv2 = *reinterpret_cast<const float2*>(a.i2 + c);
+  const float2 bs = *reinterpret_cast<const float2*>(a.bias + c);
+  float2 w[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) w[k] = *reinterpret_cast<const float2*>(a.w7 + k * a.C + c);
+  const float* x = a.in + (size_t)item * in_rows * a.C + c;
+  __half* o = a.out + (size_t)item * out_rows * a.C + c;
+  const int t_first = a.out_r.lo + row0;                 // relative time of this thread's first output
+  const int in_first = t_first - 3 * DIL - a.in_r.lo;    // operand row of window element 0
+  const int t_hi = T0 * a.up;
+  float2 win[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) win[k] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int m = 0; m < 38; ++m) {
+    const int r = in_first + m * DIL;
+    float2 v = make_float2(0.f, 0.f);
+    if (r >= 0 && r < in_rows) v = *reinterpret_cast<const float2*>(x + (size_t)r * a.C);
+    v.x = snake_fast(v.x, al1.x, iv1.x);
+    v.y = snake_fast(v.y, al1.y, iv1.y);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) win[k] = win[k + 1];
+    win[6] = v;
+    if (m >= 6) {
+      const int j = m - 6;
+      const int orow = row0 + j * DIL;
+      if (orow < out_rows) {
+        float2 acc = bs;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) { acc.x = fmaf(w[k].x, win[k].x, acc.x); acc.y = fmaf(w[k].y, win[k].y, acc.y); }
+        acc.x = snake_fast(acc.x, al2.x, iv2.x);
+        acc.y = snake_fast(acc.y, al2.y, iv2.y);
+        const int t_abs = t_first + j * DIL + it.shift0 * a.up;
+        if (t_abs < 0 || t_abs >= t_hi) acc = make_float2(0.f, 0.f);
+        *reinterpret_cast<__half2*>(o + (size_t)orow * a.C) = __floats2half2_rn(acc.x, acc.y);
+      }
+    }
+  }
+}
+
+void launch_dw_tc(const GroupCtx& g, const DwTcArgs& a) {
+  const int CP = a.C / 2;
+  const int nseg = (a.out_r.n() + 32 * a.dil - 1) / (32 * a.dil);
+  dim3 grid((unsigned)(((long long)nseg * a.dil * CP + 255) / 256), g.n_items);
+  if (a.dil == 1) k_dw_tc<1><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, a);
+  else if (a.dil == 3) k_dw_tc<3><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, a);
+  else k_dw_tc<9><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, a);
+  ++*g.launches;
+}
+
+// fp32 -> fp16 weight conversion (load time)
+__global__ void k_to_half(const float* __restrict__ in, __half* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) out[i] = __float2half_rn(in[i]);
+}
+void launch_to_half(const float* in, __half* out, size_t n, cudaStream_t st) {
+  if (n) k_to_half<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
+}
+
+}  // namespace snacb

@@ -53,7 +53,10 @@ inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b
 
 // Back-propagate the needed row ranges from the requested output samples.
 // clip: intersect every range with [0, T_stage) - valid when every item of the group has shift0 = 0.
-inline Plan make_plan(int T0, Rng out, bool clip) {
+// halo_in: keep each block's input range unclipped, so the rows q-1 / q+1 the transposed conv reads
+// at the sequence edges exist as explicit zero rows (needed by the TMA-fed tensor-core path, whose
+// shifted operand tile is a plain row offset into the flattened [items x rows] operand).
+inline Plan make_plan(int T0, Rng out, bool clip, bool halo_in = false) {
   Plan P{};
   P.T0 = T0;
   P.out = out;
@@ -78,7 +81,8 @@ inline Plan make_plan(int T0, Rng out, bool clip) {
     int q0 = floordiv(B.ct.lo, B.s), r0 = B.ct.lo - q0 * B.s;
     int q1 = floordiv(B.ct.hi - 1, B.s), r1 = (B.ct.hi - 1) - q1 * B.s;
     B.q = Rng{q0, q1 + 1};
-    B.in = clipr(Rng{(r0 < B.s - B.p) ? q0 - 1 : q0, ((r1 >= B.s - B.p) ? q1 + 1 : q1) + 1}, B.up_in);
+    B.in = Rng{(r0 < B.s - B.p) ? q0 - 1 : q0, ((r1 >= B.s - B.p) ? q1 + 1 : q1) + 1};
+    if (!halo_in) B.in = clipr(B.in, B.up_in);
     B.q = clipr(B.q, B.up_in);
     need = B.in;
   }

