@@ -51,6 +51,9 @@ extern "C" {
 #define SNACB_PREC_FP32 0     /* CUDA-core fp32 FMA: the exact/bring-up path              */
 #define SNACB_PREC_FP16 1     /* tcgen05 kind::f16, fp16 operands, fp32 TMEM accumulators */
 
+/* snacb_config.flags */
+#define SNACB_FLAG_NO_RU_FUSION 1 /* tensor-core recipe: run every ResidualUnit as dw kernel + GEMM kernel */
+
 /* fixed geometry of hubertsiuzdak/snac_24khz (the only model the reference loads, speechpipe.py:42) */
 #define SNACB_LATENT 768
 #define SNACB_DECODER_DIM 1024
@@ -69,7 +72,8 @@ typedef struct snacb_config {
   int32_t chunk_items;   /* windows processed per pass through the layer stack (0 = default);
                             sized so one pass's activations stay L2-resident */
   int32_t trim;          /* 1 = compute only the dependency cone of the emitted slice (exact) */
-  int32_t reserved[11];
+  int32_t flags;         /* SNACB_FLAG_* (bring-up switches; 0 = production)                  */
+  int32_t reserved[10];
 } snacb_config;
 
 /* One residual unit: x + W_pw * Snake(dw7_dil(Snake(x))) */

@@ -13,6 +13,7 @@ OK = 0
 WIN_OK, WIN_REJECTED, WIN_CODE4096, WIN_EMPTY = 0, 1, 2, 3
 NOISE_OFF, NOISE_TENSOR, NOISE_PHILOX = 0, 1, 2
 PREC_FP32, PREC_FP16 = 0, 1
+FLAG_NO_RU_FUSION = 1
 NOISE_PER_FRAME = 3360
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsnacb.so")
@@ -27,7 +28,8 @@ class Config(C.Structure):
         ("precision", C.c_int32),
         ("chunk_items", C.c_int32),
         ("trim", C.c_int32),
-        ("reserved", C.c_int32 * 11),
+        ("flags", C.c_int32),
+        ("reserved", C.c_int32 * 10),
     ]
 
 

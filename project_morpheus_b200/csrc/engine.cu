@@ -33,9 +33,9 @@ struct DevWeights {
   float *tail_alpha, *tail_inv, *tail_w /*[7][64]*/, *tail_b;
 };
 
-enum KClass { KC_DEINT = 0, KC_CODES, KC_DW, KC_SNAKE, KC_GEMM1, KC_CONVT, KC_TAIL, KC_COUNT };
+enum KClass { KC_DEINT = 0, KC_CODES, KC_DW, KC_SNAKE, KC_GEMM1, KC_CONVT, KC_TAIL, KC_RU, KC_COUNT };
 const char* const kClassName[KC_COUNT] = {"deinterleave", "from_codes", "dwconv_snake", "snake", "gemm_1x1",
-                                          "gemm_convt", "tail_pack"};
+                                          "gemm_convt", "tail_pack", "block_ru_fused"};
 
 struct Prof {
   bool on = false;
@@ -397,6 +397,23 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
       Rng cur = B.ct;
       for (int r = 0; r < 3 && ce == cudaSuccess; ++r) {
         const RuDev& R = Wb.ru[r];
+        if (ru_tc_supported(B.Cout) && !(e->cfg.flags & SNACB_FLAG_NO_RU_FUSION)) {  // fused dw + 1x1 + residual (blocks 2, 3)
+          const bool last = (r == 2) && (b < 3);
+          const bool want32 = !last || e->tap_stage == sid + 4 + 2 * r;
+          RuTcArgs u{X, cur, B.r[r], B.Cout, kDil[r], B.up_out, R.dw_w, R.dw_b, R.a1, R.i1, R.a2, R.i2, R.pw16, R.pw_b,
+                     want32 ? Y : nullptr, last ? Anext : nullptr, last ? W.blk[b + 1].alpha : nullptr,
+                     last ? W.blk[b + 1].inv : nullptr};
+          if (ce == cudaSuccess) {
+            const double el = (double)n * B.r[r].n() * B.Cout;
+            ProfScope ps(e, KC_RU, 2.0 * el * B.Cout + el * 24.0,
+                         (double)n * cur.n() * B.Cout * 4.0 + el * ((want32 ? 4.0 : 0.0) + (last ? 2.0 : 0.0)), st);
+            ce = launch_ru_tc(g, u);
+          }
+          tap(e, sid + 4 + 2 * r, Y, B.r[r], B.Cout, n, first, st);
+          std::swap(X, Y);
+          cur = B.r[r];
+          continue;
+        }
         {
           DwTcArgs d{X, cur, D16, B.r[r], B.Cout, kDil[r], B.up_out, R.dw_w, R.dw_b, R.a1, R.i1, R.a2, R.i2};
           const double el = (double)n * B.r[r].n() * B.Cout;
@@ -441,7 +458,7 @@ size_t per_item_bytes(const snacb_engine* e, const Plan& P) {
   return Zb + pad256((size_t)P.h.n() * kLatent * 4) + 3 * Sb + 1024;
 }
 constexpr size_t kActBudget = size_t(6) << 30;  // activation workspace cap per engine
-int default_chunk(const snacb_engine* e) { return e->cfg.chunk_items > 0 ? e->cfg.chunk_items : 32; }
+int default_chunk(const snacb_engine* e) { return e->cfg.chunk_items > 0 ? e->cfg.chunk_items : 1024; }
 size_t act_bytes(const snacb_engine* e, const Plan& P, int count) {
   const size_t per = per_item_bytes(e, P);
   const int chunk = std::max(1, std::min(count, default_chunk(e)));

@@ -87,6 +87,16 @@ struct DwTcArgs {
   const float* a1; const float* i1; const float* a2; const float* i2;
 };
 void launch_dw_tc(const GroupCtx& g, const DwTcArgs& a);
+// Fused ResidualUnit (C = 64 / 128): x' = x + W * Snake(dw7(Snake(x))) + b in one kernel.
+struct RuTcArgs {
+  const float* x; Rng in_r;        // residual stream in (fp32)
+  Rng out_r; int C, dil, up;
+  const float* w7; const float* dw_b; const float* a1; const float* i1; const float* a2; const float* i2;
+  const __half* pw16; const float* pw_b;
+  float* out32; __half* out16; const float* sn_alpha; const float* sn_inv;
+};
+bool ru_tc_supported(int C);
+cudaError_t launch_ru_tc(const GroupCtx& g, const RuTcArgs& a);
 void launch_dwconv_half(const GroupCtx& g, const DwArgs& a, __half* out16);  // plain dw k7 -> fp16 (decoder head)
 void launch_to_half(const float* in, __half* out, size_t n, cudaStream_t st);
 

@@ -470,11 +470,273 @@ void launch_dw_tc(const GroupCtx& g, const DwTcArgs& a) {
   ++*g.launches;
 }
 
+// ============================================================================ fused ResidualUnit
+// x' = x + W_pw * Snake(dw7_dil(Snake(x))) + b for one 128-row time tile of one item, all C channels
+// (C = 64 or 128: decoder blocks 3 and 2, where the 1x1 weight fits in shared memory whole and the
+// layer is bound by activation traffic, not by the GEMM).  Nine worker warps build the fp16 GEMM
+// operand straight into the 128-byte-swizzled K-major shared-memory layout tcgen05 reads (register
+// sliding windows over global loads: every input Snake'd once per residue class), one control warp
+// TMA-loads the weight and issues the MMAs, then eight warps run the epilogue out of TMEM (bias +
+// residual + optional next-block Snake) with coalesced stores.  Versus k_dw_tc + k_gemm_tc this
+// removes the fp16 operand round trip through HBM and one launch per unit.
+namespace {
+constexpr int kRuThreads = 320;
+constexpr int kRuWorkers = 288;
+
+struct RuDev {
+  const Item* items; int base, out_len, T0;
+  const float* x; int in_lo, in_rows;   // residual stream in: rows per item, relative time of row 0
+  int out_lo, out_rows, up;
+  const float* w7; const float* dw_b; const float* a1; const float* i1; const float* a2; const float* i2;
+  const float* pw_b;
+  float* out32; __half* out16; const float* sn_alpha; const float* sn_inv;
+};
+
+template <int C> struct RuSmem {
+  static constexpr int kABytes = BM * C * 2;
+  static constexpr int kWBytes = C * C * 2;
+  static constexpr int kStgBytes = 8 * 32 * 32 * 4;
+  static constexpr int kMetaBytes = BM * 4 + 64;
+  static constexpr int kBytes = kABytes + kWBytes + kStgBytes + kMetaBytes + 1024;
+};
+
+template <int C, int DIL>
+__global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const __grid_constant__ CUtensorMap tmW, const RuDev a) {
+  using S = RuSmem<C>;
+  constexpr int KB = C / BK;  // k-blocks of 64 channels
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + S::kABytes;
+  float* sStg = reinterpret_cast<float*>(smem + S::kABytes + S::kWBytes);
+  int* meta_out = reinterpret_cast<int*>(smem + S::kABytes + S::kWBytes + S::kStgBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(meta_out + BM);  // [0] weight landed, [1] accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int item = blockIdx.y;
+  const int row0 = blockIdx.x * BM;  // first output row (index into the item's out rows) of this tile
+  const ItemRef it = get_item(a.items, a.base, item, a.out_len);
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) tmem_alloc(smem_u32(tmem_slot), C);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 9) {
+    if (lane == 0) {  // 1x1 weight [C][C] fp16 -> KB swizzled k-block tiles of [C rows][128 B]
+      mbar_arrive_expect_tx(smem_u32(&bars[0]), S::kWBytes);
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(smem_u32(sW + kb * C * 128), &tmW, smem_u32(&bars[0]), kb * BK, 0);
+    }
+  } else {
+    // ---- epilogue row metadata (threads 0..127 <-> tile rows)
+    if (tid < BM) {
+      int oi = -1;
+      const int orow = row0 + tid;
+      if (orow < a.out_rows) {
+        const int t_abs = a.out_lo + orow + it.shift0 * a.up;
+        oi = item * a.out_rows + orow;
+        if (t_abs < 0 || t_abs >= a.T0 * a.up) oi |= (int)kLiveFlag;
+      }
+      meta_out[tid] = oi;
+    }
+    // ---- depthwise stage: unit = (channel pair, residue class / segment), 16 outputs, 22 loads
+    constexpr int CP = C / 2;
+    constexpr int U = (DIL == 1) ? 8 : 9;
+    const float* xin = a.x + (size_t)item * a.in_rows * C;
+#pragma unroll 1
+    for (int idx = tid; idx < CP * U; idx += kRuWorkers) {
+      const int cp = idx % CP, u = idx / CP;
+      int first;  // tile-relative row of the unit's first output
+      if (DIL == 1) first = u * 16;
+      else if (DIL == 3) first = (u % 3) + (u / 3) * 48;
+      else first = u;
+      const int c = cp * 2;
+      const float2 al1 = *reinterpret_cast<const float2*>(a.a1 + c), iv1 = *reinterpret_cast<const float2*>(a.i1 + c);
+      const float2 al2 = *reinterpret_cast<const float2*>(a.a2 + c), iv2 = *reinterpret_cast<const float2*>(a.i2 + c);
+      const float2 bs = *reinterpret_cast<const float2*>(a.dw_b + c);
+      float2 w[7];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) w[k] = *reinterpret_cast<const float2*>(a.w7 + k * C + c);
+      const int in_first = a.out_lo + row0 + first - 3 * DIL - a.in_lo;  // operand row of window element 0
+      // A tile address pieces: k-block of this channel pair, byte column inside the 128-byte row
+      uint8_t* a_kb = sA + (c / BK) * (BM * 128);
+      const int bcol = (c % BK) * 2;
+      float2 win[7];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) win[k] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int m = 0; m < 22; ++m) {
+        const int r = in_first + m * DIL;
+        float2 v = make_float2(0.f, 0.f);
+        if (r >= 0 && r < a.in_rows) v = *reinterpret_cast<const float2*>(xin + (size_t)r * C + c);
+        v.x = snake_fast(v.x, al1.x, iv1.x);
+        v.y = snake_fast(v.y, al1.y, iv1.y);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) win[k] = win[k + 1];
+        win[6] = v;
+        if (m >= 6) {
+          const int trow = first + (m - 6) * DIL;
+          if (trow < BM) {
+            float2 acc = bs;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) { acc.x = fmaf(w[k].x, win[k].x, acc.x); acc.y = fmaf(w[k].y, win[k].y, acc.y); }
+            acc.x = snake_fast(acc.x, al2.x, iv2.x);
+            acc.y = snake_fast(acc.y, al2.y, iv2.y);
+            // K-major SWIZZLE_128B: 16-byte chunk index XOR (row % 8) inside each 1024-byte 8-row group
+            const int off = (trow >> 3) * 1024 + (trow & 7) * 128 + ((((bcol >> 4) ^ (trow & 7)) << 4) | (bcol & 15));
+            *reinterpret_cast<__half2*>(a_kb + off) = __floats2half2_rn(acc.x, acc.y);
+          }
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+  }
+  __syncthreads();
+
+  if (warp == 9) {
+    if (lane == 0) {
+      mbar_wait(smem_u32(&bars[0]), 0);
+      tc_fence_after();
+      constexpr uint32_t idesc = umma_idesc_f16(C);
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        const uint64_t da = umma_desc_k_sw128(smem_u32(sA + kb * (BM * 128)));
+        const uint64_t db = umma_desc_k_sw128(smem_u32(sW + kb * (C * 128)));
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+      }
+      umma_commit(smem_u32(&bars[1]));
+    }
+  } else if (warp < 8) {
+    // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., the two warps of a quarter split the columns
+    const int q = warp & 3, half = warp >> 2;
+    constexpr int NCH = C / 64;  // 32-column chunks per warp
+    const int cg = lane & 7, rr = lane >> 3;
+    float* stg = sStg + warp * (32 * 32);
+    const float* xin = a.x + (size_t)item * a.in_rows * C;
+    const int res_row0 = a.out_lo + row0 + q * 32 - a.in_lo;  // operand row of tile row q*32
+    float4 res[8];
+    {
+      const int col = (half * NCH) * 32 + cg * 4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = rr + 4 * i;
+        res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (meta_out[q * 32 + row] >= 0) res[i] = *reinterpret_cast<const float4*>(xin + (size_t)(res_row0 + row) * C + col);
+      }
+    }
+    mbar_wait(smem_u32(&bars[1]), 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int ci = 0; ci < NCH; ++ci) {
+      const int chunk = half * NCH + ci;
+      const int col = chunk * 32 + cg * 4;
+      if (ci > 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = rr + 4 * i;
+          res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (meta_out[q * 32 + row] >= 0) res[i] = *reinterpret_cast<const float4*>(xin + (size_t)(res_row0 + row) * C + col);
+        }
+      }
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(chunk * 32), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+            make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                        __uint_as_float(r[4 * j + 3]));
+      __syncwarp();
+      const float4 b4 = *reinterpret_cast<const float4*>(a.pw_b + col);
+      float4 al = make_float4(0.f, 0.f, 0.f, 0.f), iv = al;
+      if (a.sn_alpha) { al = *reinterpret_cast<const float4*>(a.sn_alpha + col); iv = *reinterpret_cast<const float4*>(a.sn_inv + col); }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = rr + 4 * i;
+        int oi = meta_out[q * 32 + row];
+        if (oi < 0) continue;
+        const bool live = !(oi & (int)kLiveFlag);
+        oi &= (int)(kLiveFlag - 1);
+        float4 v = *reinterpret_cast<const float4*>(stg + row * 32 + ((cg ^ (row & 7)) << 2));
+        v.x += b4.x + res[i].x; v.y += b4.y + res[i].y; v.z += b4.z + res[i].z; v.w += b4.w + res[i].w;
+        if (!live) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const size_t o = (size_t)oi * C + col;
+        if (a.out32) *reinterpret_cast<float4*>(a.out32 + o) = v;
+        if (a.out16) {
+          if (a.sn_alpha) {
+            v.x = snake_fast(v.x, al.x, iv.x); v.y = snake_fast(v.y, al.y, iv.y);
+            v.z = snake_fast(v.z, al.z, iv.z); v.w = snake_fast(v.w, al.w, iv.w);
+          }
+          const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+          pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+          *reinterpret_cast<uint2*>(a.out16 + o) = pk;
+        }
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C);
+  }
+}
+
+template <int C, int DIL>
+cudaError_t launch_ru_t(const CUtensorMap& mw, const RuDev& d, dim3 grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_ru_tc<C, DIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, RuSmem<C>::kBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  k_ru_tc<C, DIL><<<grid, kRuThreads, RuSmem<C>::kBytes, st>>>(mw, d);
+  return cudaGetLastError();
+}
+template <int C>
+cudaError_t launch_ru_c(int dil, const CUtensorMap& mw, const RuDev& d, dim3 grid, cudaStream_t st) {
+  if (dil == 1) return launch_ru_t<C, 1>(mw, d, grid, st);
+  if (dil == 3) return launch_ru_t<C, 3>(mw, d, grid, st);
+  return launch_ru_t<C, 9>(mw, d, grid, st);
+}
+
+}  // namespace
+
+bool ru_tc_supported(int C) { return C == 64 || C == 128; }
+
+cudaError_t launch_ru_tc(const GroupCtx& g, const RuTcArgs& a) {
+  if (!ru_tc_supported(a.C) || g.n_items <= 0 || a.out_r.n() <= 0) return cudaErrorInvalidValue;
+  CUtensorMap mw;
+  if (!get_tmap(a.pw16, a.C, a.C, a.C, &mw)) return cudaErrorNotSupported;
+  RuDev d{};
+  d.items = g.items; d.base = g.base; d.out_len = g.out_len; d.T0 = g.T0;
+  d.x = a.x; d.in_lo = a.in_r.lo; d.in_rows = a.in_r.n(); d.out_lo = a.out_r.lo; d.out_rows = a.out_r.n(); d.up = a.up;
+  d.w7 = a.w7; d.dw_b = a.dw_b; d.a1 = a.a1; d.i1 = a.i1; d.a2 = a.a2; d.i2 = a.i2; d.pw_b = a.pw_b;
+  d.out32 = a.out32; d.out16 = a.out16; d.sn_alpha = a.sn_alpha; d.sn_inv = a.sn_inv;
+  dim3 grid((unsigned)((a.out_r.n() + BM - 1) / BM), (unsigned)g.n_items);
+  cudaError_t e = (a.C == 64) ? launch_ru_c<64>(a.dil, mw, d, grid, g.stream) : launch_ru_c<128>(a.dil, mw, d, grid, g.stream);
+  ++*g.launches;
+  return e;
+}
+
+namespace {
 // fp32 -> fp16 weight conversion (load time)
 __global__ void k_to_half(const float* __restrict__ in, __half* __restrict__ out, size_t n) {
   const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (i < n) out[i] = __float2half_rn(in[i]);
 }
+}  // namespace
 void launch_to_half(const float* in, __half* out, size_t n, cudaStream_t st) {
   if (n) k_to_half<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
 }
