@@ -302,7 +302,7 @@ int run_group_f32(snacb_engine* e, const Plan& P, const Item* d_items, int n_tot
         cur = B.r[r];
       }
     }
-    TailArgs t{X, P.b[3].r[2], tail_out, W.tail_alpha, W.tail_inv, W.tail_w, W.tail_b, d_status, wav, pcm};
+    TailArgs t{X, P.b[3].r[2], tail_out, W.tail_alpha, W.tail_inv, W.tail_w, W.tail_b, d_status, wav, pcm, false};
     {
       const double smp = (double)n * tail_out.n();
       ProfScope ps(e, KC_TAIL, smp * (2.0 * 448 + 4.0 * 64), 4.0 * (double)n * P.b[3].r[2].n() * 64 + smp * 2.0, st);
@@ -439,7 +439,7 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
     {
       const double smp = (double)n * tail_out.n();
       ProfScope ps(e, KC_TAIL, smp * (2.0 * 448 + 4.0 * 64), 4.0 * (double)n * P.b[3].r[2].n() * 64 + smp * 2.0, st);
-      TailArgs t{X, P.b[3].r[2], tail_out, W.tail_alpha, W.tail_inv, W.tail_w, W.tail_b, d_status, wav, pcm};
+      TailArgs t{X, P.b[3].r[2], tail_out, W.tail_alpha, W.tail_inv, W.tail_w, W.tail_b, d_status, wav, pcm, true};
       launch_tail(g, t);
     }
     int rc = check_launch(e, "tensor-core layer pipeline");

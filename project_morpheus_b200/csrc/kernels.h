@@ -109,6 +109,7 @@ struct TailArgs {
   const int32_t* status;  // per code_row; nullptr or skip rows whose status != 0
   float* wav;   // nullable
   int16_t* pcm; // nullable
+  bool fast;    // MUFU sin for the Snake (tensor-core recipe)
 };
 void launch_tail(const GroupCtx& g, const TailArgs& a);
 

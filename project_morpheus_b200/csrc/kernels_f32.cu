@@ -307,6 +307,7 @@ void launch_gemm_f32(const GroupCtx& g, const GemmArgs& a) {
 // ============================================================================ tail + NS-4 pack
 // y[t] = tanh( b + sum_{c,k} w[k][c] * Snake(x[t+k-3][c]) );  pcm = (int16) trunc(y * 32767)
 // (speechpipe.py:127: no rounding, no clip).  64 samples per CTA, 4 channel quarters per sample.
+template <bool FAST>
 __global__ void __launch_bounds__(256) k_tail(const Item* items, int base, int out_len, int T0, TailArgs a) {
   __shared__ float xs[70][65];
   __shared__ float ws[7][64];
@@ -320,7 +321,8 @@ __global__ void __launch_bounds__(256) k_tail(const Item* items, int base, int o
     const int r = e >> 6, c = e & 63;
     const int row = t0 - 3 + r - a.x_r.lo;
     float v = (row >= 0 && row < x_rows) ? x[(size_t)row * 64 + c] : 0.0f;
-    xs[r][c] = snake_exact(v, a.alpha[c], a.inv[c]);
+    if (FAST) { const float sn = __sinf(a.alpha[c] * v); xs[r][c] = fmaf(a.inv[c], sn * sn, v); }
+    else xs[r][c] = snake_exact(v, a.alpha[c], a.inv[c]);
   }
   for (int e = tid; e < 7 * 64; e += 256) ws[e >> 6][e & 63] = a.w7[e];
   __syncthreads();
@@ -346,7 +348,8 @@ __global__ void __launch_bounds__(256) k_tail(const Item* items, int base, int o
 
 void launch_tail(const GroupCtx& g, const TailArgs& a) {
   dim3 grid((a.out_r.n() + 63) / 64, g.n_items);
-  k_tail<<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, a);
+  if (a.fast) k_tail<true><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, a);
+  else k_tail<false><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, a);
   ++*g.launches;
 }
 

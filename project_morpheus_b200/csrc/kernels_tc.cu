@@ -126,9 +126,66 @@ __device__ __forceinline__ float snake_fast(float x, float alpha, float inv) {
   return fmaf(inv, s * s, x);
 }
 
+// Packed fp32x2 arithmetic (sm_100 FFMA2/FMUL2/FADD2): the depthwise + Snake work is issue-bound, and
+// every value here comes as a channel pair.
+__device__ __forceinline__ float2 snake2(float2 x, float2 al, float2 iv) {
+  const float2 t = __fmul2_rn(al, x);
+  float2 s = make_float2(__sinf(t.x), __sinf(t.y));
+  s = __fmul2_rn(s, s);
+  return __ffma2_rn(iv, s, x);
+}
+
+// One depthwise unit: L outputs at rows first, first+DIL, ... of one channel pair from L+6 inputs at
+// p0 + m*DIL*C (m = 0..L+5; bit m of `mask` says the row exists, absent rows are the conv's zero pad).
+// Output j = Snake2(b + sum_k w[k] * Snake1(in[j + k])) is handed to sink(j, value).
+struct DwPairW {
+  float2 al1, iv1, al2, iv2, bias, w[7];
+  __device__ __forceinline__ void load(const float* w7, const float* dw_b, const float* a1, const float* i1, const float* a2,
+                                       const float* i2, int C, int c) {
+    al1 = *reinterpret_cast<const float2*>(a1 + c); iv1 = *reinterpret_cast<const float2*>(i1 + c);
+    al2 = *reinterpret_cast<const float2*>(a2 + c); iv2 = *reinterpret_cast<const float2*>(i2 + c);
+    bias = *reinterpret_cast<const float2*>(dw_b + c);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) w[k] = *reinterpret_cast<const float2*>(w7 + k * C + c);
+  }
+};
+template <int C, int DIL, int L, typename Sink>
+__device__ __forceinline__ void dw_unit(const float* p0, uint32_t mask_lo, uint32_t mask_hi, const DwPairW& W, Sink&& sink) {
+  float2 win[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) win[k] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int m = 0; m < L + 6; ++m) {
+    float2 v = make_float2(0.f, 0.f);
+    const bool ok = (m < 32) ? ((mask_lo >> m) & 1u) : ((mask_hi >> (m - 32)) & 1u);
+    if (ok) v = __ldg(reinterpret_cast<const float2*>(p0 + (long long)m * (DIL * C)));
+    v = snake2(v, W.al1, W.iv1);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) win[k] = win[k + 1];
+    win[6] = v;
+    if (m >= 6) {
+      float2 acc = W.bias;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) acc = __ffma2_rn(W.w[k], win[k], acc);
+      sink(m - 6, snake2(acc, W.al2, W.iv2));
+    }
+  }
+}
+// bit m set <=> 0 <= r0 + m*DIL < rows, for m in [0, n)
+template <int DIL>
+__device__ __forceinline__ void row_mask(int r0, int rows, int n, uint32_t& lo, uint32_t& hi) {
+  // first valid m: ceil(-r0 / DIL) if r0 < 0; one past last valid m: ceil((rows - r0) / DIL)
+  int m0 = (r0 < 0) ? (-r0 + DIL - 1) / DIL : 0;
+  int m1 = (rows - r0 + DIL - 1) / DIL;
+  m0 = min(max(m0, 0), n); m1 = min(max(m1, m0), n);
+  const unsigned long long bits = (m1 >= 64 ? ~0ull : ((1ull << m1) - 1ull)) & ~((1ull << m0) - 1ull);
+  lo = (uint32_t)bits; hi = (uint32_t)(bits >> 32);
+}
+
 struct TcDev {
   const Item* items; int base, out_len, T0, n_items;
   int K, nseg;              // K per segment; ConvT has 2 segments (taps of q and q +- 1)
+  int stages;               // smem pipeline depth of this launch
   int a_rows, a_lo;         // operand rows per item, relative time of operand row 0
   int s, p, Cout;           // ConvT only
   const float* bias;
@@ -140,25 +197,27 @@ struct TcDev {
 };
 
 template <int BN> struct TcSmem {
-  static constexpr int kStages = (BN == 64) ? 4 : 3;
+  static constexpr int kMaxStages = (BN == 64) ? 4 : 3;
   static constexpr int kStageBytes = BM * BK * 2 + BN * BK * 2;
   static constexpr int kMetaBytes = 3 * BM * 4 + 128;
-  static constexpr int kBytes = kStages * kStageBytes + kMetaBytes + 1024;  // + alignment slack
-  static_assert(kStages * kStageBytes >= 4 * 32 * 32 * 4, "epilogue staging aliases the pipeline stages");
+  // stages = min(k-blocks, kMaxStages): short-K layers keep little shared memory so more CTAs share an SM
+  static constexpr int bytes(int stages) { return stages * kStageBytes + kMetaBytes + 1024; }  // + alignment slack
+  static_assert(kStageBytes >= 4 * 32 * 32 * 4, "epilogue staging aliases pipeline stage 0");
 };
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(kTcThreads) k_gemm_tc(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(kTcThreads, 3) k_gemm_tc(const __grid_constant__ CUtensorMap tmA,
                                                          const __grid_constant__ CUtensorMap tmW, const TcDev a) {
   using S = TcSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* meta = smem + S::kStages * S::kStageBytes;
+  const int kStages = a.stages;
+  uint8_t* meta = smem + kStages * S::kStageBytes;
   int* meta_out = reinterpret_cast<int*>(meta);
   int* meta_res = meta_out + BM;
   float* meta_nz = reinterpret_cast<float*>(meta_res + BM);
   uint64_t* bars = reinterpret_cast<uint64_t*>(meta + 3 * BM * 4);  // full[kStages], empty[kStages], accum
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kStages + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kMaxStages + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -169,11 +228,11 @@ __global__ void __launch_bounds__(kTcThreads) k_gemm_tc(const __grid_constant__ 
   const int num_kb = kb_per_seg * a.nseg;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < S::kStages; ++i) {
+    for (int i = 0; i < kStages; ++i) {
       mbar_init(smem_u32(&bars[i]), 1);
-      mbar_init(smem_u32(&bars[S::kStages + i]), 1);
+      mbar_init(smem_u32(&bars[kStages + i]), 1);
     }
-    mbar_init(smem_u32(&bars[2 * S::kStages]), 1);
+    mbar_init(smem_u32(&bars[2 * kStages]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), BN);
@@ -186,8 +245,8 @@ __global__ void __launch_bounds__(kTcThreads) k_gemm_tc(const __grid_constant__ 
     // ===================================================================== TMA producer
     if (lane == 0) {
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int st = kb % S::kStages;
-        mbar_wait(smem_u32(&bars[S::kStages + st]), ((kb / S::kStages) & 1) ^ 1);
+        const int st = kb % kStages;
+        mbar_wait(smem_u32(&bars[kStages + st]), ((kb / kStages) & 1) ^ 1);
         const uint32_t full = smem_u32(&bars[st]);
         const uint32_t sa = smem_u32(smem + st * S::kStageBytes), sb = sa + BM * BK * 2;
         const int seg = kb / kb_per_seg, kk = (kb - seg * kb_per_seg) * BK;
@@ -201,17 +260,17 @@ __global__ void __launch_bounds__(kTcThreads) k_gemm_tc(const __grid_constant__ 
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(BN);
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int st = kb % S::kStages;
-        mbar_wait(smem_u32(&bars[st]), (kb / S::kStages) & 1);
+        const int st = kb % kStages;
+        mbar_wait(smem_u32(&bars[st]), (kb / kStages) & 1);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + st * S::kStageBytes), sb = sa + BM * BK * 2;
         const uint64_t da = umma_desc_k_sw128(sa), db = umma_desc_k_sw128(sb);
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k)  // UMMA_K = 16 fp16 = 32 bytes: advance the start address by 2 (x16 B)
           umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
-        umma_commit(smem_u32(&bars[S::kStages + st]));  // frees the stage once these MMAs have read it
+        umma_commit(smem_u32(&bars[kStages + st]));  // frees the stage once these MMAs have read it
       }
-      umma_commit(smem_u32(&bars[2 * S::kStages]));     // accumulator complete
+      umma_commit(smem_u32(&bars[2 * kStages]));     // accumulator complete
     }
   } else {
     // ===================================================================== epilogue (warps 2..5)
@@ -239,12 +298,24 @@ __global__ void __launch_bounds__(kTcThreads) k_gemm_tc(const __grid_constant__ 
       meta_out[trow] = oi; meta_res[trow] = ri; meta_nz[trow] = nz;
     }
     __syncwarp();
-    mbar_wait(smem_u32(&bars[2 * S::kStages]), 0);
+    const int cg = lane & 7, rr = lane >> 3;
+    const int ocol0 = n0 + cg * 4 - ((EPI == EPI_CONVT) ? phase * a.Cout : 0);
+    float4 res[8];
+    auto load_res = [&](int c) {  // residual / carrier rows of this lane for 32-column chunk c (independent of the MMA)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int ri = meta_res[q * 32 + rr + 4 * i];
+        res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ri >= 0) res[i] = __ldg(reinterpret_cast<const float4*>(a.R + (size_t)ri * a.ldr + ocol0 + c * 32));
+      }
+    };
+    if (EPI == EPI_RESID || EPI == EPI_NOISE) load_res(0);
+    mbar_wait(smem_u32(&bars[2 * kStages]), 0);
     tc_fence_after();
     float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 32);  // aliases stage 0: all MMAs are done
-    const int cg = lane & 7, rr = lane >> 3;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
+      if ((EPI == EPI_RESID || EPI == EPI_NOISE) && c > 0) load_res(c);
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
 #pragma unroll
@@ -267,7 +338,7 @@ __global__ void __launch_bounds__(kTcThreads) k_gemm_tc(const __grid_constant__ 
         float4 v = *reinterpret_cast<const float4*>(stg + row * 32 + ((cg ^ (row & 7)) << 2));
         v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
         if (EPI == EPI_RESID || EPI == EPI_NOISE) {
-          const float4 r4 = *reinterpret_cast<const float4*>(a.R + (size_t)meta_res[q * 32 + row] * a.ldr + ocol);
+          const float4 r4 = res[i];
           if (EPI == EPI_NOISE) {
             const float nz = meta_nz[q * 32 + row];
             v.x = fmaf(nz, v.x, r4.x); v.y = fmaf(nz, v.y, r4.y); v.z = fmaf(nz, v.z, r4.z); v.w = fmaf(nz, v.w, r4.w);
@@ -357,11 +428,12 @@ template <int BN, int EPI>
 cudaError_t launch_tc_t(const CUtensorMap& ma, const CUtensorMap& mw, const TcDev& d, dim3 grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::kBytes);
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TcSmem<BN>::bytes(TcSmem<BN>::kMaxStages));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  k_gemm_tc<BN, EPI><<<grid, kTcThreads, TcSmem<BN>::kBytes, st>>>(ma, mw, d);
+  k_gemm_tc<BN, EPI><<<grid, kTcThreads, TcSmem<BN>::bytes(d.stages), st>>>(ma, mw, d);
   return cudaGetLastError();
 }
 
@@ -392,6 +464,7 @@ cudaError_t launch_gemm_tc(const GroupCtx& g, const TcGemmArgs& a) {
   if (!get_tmap(a.A, Mtot, a.K, BM, &ma) || !get_tmap(a.W, a.N, nseg * a.K, bn, &mw)) return cudaErrorNotSupported;
   TcDev d{};
   d.items = g.items; d.base = g.base; d.out_len = g.out_len; d.T0 = g.T0; d.n_items = g.n_items;
+  d.stages = std::min((a.K / BK) * nseg, bn == 128 ? TcSmem<128>::kMaxStages : TcSmem<64>::kMaxStages);
   d.K = a.K; d.nseg = nseg; d.a_rows = a.a_rows; d.a_lo = a.a_lo; d.s = a.s; d.p = a.p; d.Cout = a.Cout;
   d.bias = a.bias; d.out32 = a.out32; d.out16 = a.out16; d.o_lo = a.o_r.lo; d.o_rows = a.o_r.n(); d.ldo = a.ldo;
   d.sn_alpha = a.sn_alpha; d.sn_inv = a.sn_inv; d.R = a.R; d.r_lo = a.r_r.lo; d.r_rows = a.r_r.n(); d.ldr = a.ldr;
@@ -407,9 +480,9 @@ cudaError_t launch_gemm_tc(const GroupCtx& g, const TcGemmArgs& a) {
 // segment: a 7-deep register window slides along time, so every input is loaded and Snake'd once
 // (38 loads for 32 outputs).  Output = Snake(b + sum_k w[k] * Snake(x[t + (k-3)*dil])) as fp16, the
 // K-major operand of the ResidualUnit's 1x1 GEMM.
-template <int DIL>
+template <int C, int DIL>
 __global__ void __launch_bounds__(256) k_dw_tc(const Item* items, int base, int out_len, int T0, DwTcArgs a) {
-  const int CP = a.C >> 1;
+  constexpr int CP = C / 2;
   const int item = blockIdx.y;
   const int idx = blockIdx.x * 256 + threadIdx.x;
   const int cp = idx % CP, rest = idx / CP;
@@ -419,54 +492,42 @@ __global__ void __launch_bounds__(256) k_dw_tc(const Item* items, int base, int 
   if (row0 >= out_rows) return;
   const int c = cp * 2;
   const ItemRef it = get_item(items, base, item, out_len);
-  const float2 al1 = *reinterpret_cast<const float2*>(a.a1 + c), iv1 = *reinterpret_cast<const float2*>(a.i1 + c);
-  const float2 al2 = *reinterpret_cast<const float2*>(a.a2 + c), iv2 = *reinterpret_cast<const float2*>(a.i2 + c);
-  const float2 bs = *reinterpret_cast<const float2*>(a.bias + c);
-  float2 w[7];
-#pragma unroll
-  for (int k = 0; k < 7; ++k) w[k] = *reinterpret_cast<const float2*>(a.w7 + k * a.C + c);
-  const float* x = a.in + (size_t)item * in_rows * a.C + c;
-  __half* o = a.out + (size_t)item * out_rows * a.C + c;
+  DwPairW W;
+  W.load(a.w7, a.bias, a.a1, a.i1, a.a2, a.i2, C, c);
+  const float* x = a.in + (size_t)item * in_rows * C + c;
+  __half* o = a.out + (size_t)item * out_rows * C + c;
   const int t_first = a.out_r.lo + row0;                 // relative time of this thread's first output
   const int in_first = t_first - 3 * DIL - a.in_r.lo;    // operand row of window element 0
   const int t_hi = T0 * a.up;
-  float2 win[7];
-#pragma unroll
-  for (int k = 0; k < 7; ++k) win[k] = make_float2(0.f, 0.f);
-#pragma unroll
-  for (int m = 0; m < 38; ++m) {
-    const int r = in_first + m * DIL;
-    float2 v = make_float2(0.f, 0.f);
-    if (r >= 0 && r < in_rows) v = *reinterpret_cast<const float2*>(x + (size_t)r * a.C);
-    v.x = snake_fast(v.x, al1.x, iv1.x);
-    v.y = snake_fast(v.y, al1.y, iv1.y);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) win[k] = win[k + 1];
-    win[6] = v;
-    if (m >= 6) {
-      const int j = m - 6;
-      const int orow = row0 + j * DIL;
-      if (orow < out_rows) {
-        float2 acc = bs;
-#pragma unroll
-        for (int k = 0; k < 7; ++k) { acc.x = fmaf(w[k].x, win[k].x, acc.x); acc.y = fmaf(w[k].y, win[k].y, acc.y); }
-        acc.x = snake_fast(acc.x, al2.x, iv2.x);
-        acc.y = snake_fast(acc.y, al2.y, iv2.y);
-        const int t_abs = t_first + j * DIL + it.shift0 * a.up;
-        if (t_abs < 0 || t_abs >= t_hi) acc = make_float2(0.f, 0.f);
-        *reinterpret_cast<__half2*>(o + (size_t)orow * a.C) = __floats2half2_rn(acc.x, acc.y);
-      }
+  const int t_abs0 = t_first + it.shift0 * a.up;
+  uint32_t mlo, mhi;
+  row_mask<DIL>(in_first, in_rows, 38, mlo, mhi);
+  dw_unit<C, DIL, 32>(x + (long long)in_first * C, mlo, mhi, W, [&](int j, float2 v) {
+    const int orow = row0 + j * DIL;
+    if (orow < out_rows) {
+      const int t_abs = t_abs0 + j * DIL;
+      if (t_abs < 0 || t_abs >= t_hi) v = make_float2(0.f, 0.f);
+      *reinterpret_cast<__half2*>(o + (size_t)orow * C) = __floats2half2_rn(v.x, v.y);
     }
-  }
+  });
+}
+
+template <int C>
+void launch_dw_tc_c(const GroupCtx& g, const DwTcArgs& a) {
+  const int nseg = (a.out_r.n() + 32 * a.dil - 1) / (32 * a.dil);
+  dim3 grid((unsigned)(((long long)nseg * a.dil * (C / 2) + 255) / 256), g.n_items);
+  if (a.dil == 1) k_dw_tc<C, 1><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, a);
+  else if (a.dil == 3) k_dw_tc<C, 3><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, a);
+  else k_dw_tc<C, 9><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, a);
 }
 
 void launch_dw_tc(const GroupCtx& g, const DwTcArgs& a) {
-  const int CP = a.C / 2;
-  const int nseg = (a.out_r.n() + 32 * a.dil - 1) / (32 * a.dil);
-  dim3 grid((unsigned)(((long long)nseg * a.dil * CP + 255) / 256), g.n_items);
-  if (a.dil == 1) k_dw_tc<1><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, a);
-  else if (a.dil == 3) k_dw_tc<3><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, a);
-  else k_dw_tc<9><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, a);
+  switch (a.C) {
+    case 64: launch_dw_tc_c<64>(g, a); break;
+    case 128: launch_dw_tc_c<128>(g, a); break;
+    case 256: launch_dw_tc_c<256>(g, a); break;
+    default: launch_dw_tc_c<512>(g, a); break;
+  }
   ++*g.launches;
 }
 
@@ -559,43 +620,19 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
       else if (DIL == 3) first = (u % 3) + (u / 3) * 48;
       else first = u;
       const int c = cp * 2;
-      const float2 al1 = *reinterpret_cast<const float2*>(a.a1 + c), iv1 = *reinterpret_cast<const float2*>(a.i1 + c);
-      const float2 al2 = *reinterpret_cast<const float2*>(a.a2 + c), iv2 = *reinterpret_cast<const float2*>(a.i2 + c);
-      const float2 bs = *reinterpret_cast<const float2*>(a.dw_b + c);
-      float2 w[7];
-#pragma unroll
-      for (int k = 0; k < 7; ++k) w[k] = *reinterpret_cast<const float2*>(a.w7 + k * C + c);
+      DwPairW W;
+      W.load(a.w7, a.dw_b, a.a1, a.i1, a.a2, a.i2, C, c);
       const int in_first = a.out_lo + row0 + first - 3 * DIL - a.in_lo;  // operand row of window element 0
-      // A tile address pieces: k-block of this channel pair, byte column inside the 128-byte row
-      uint8_t* a_kb = sA + (c / BK) * (BM * 128);
-      const int bcol = (c % BK) * 2;
-      float2 win[7];
-#pragma unroll
-      for (int k = 0; k < 7; ++k) win[k] = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int m = 0; m < 22; ++m) {
-        const int r = in_first + m * DIL;
-        float2 v = make_float2(0.f, 0.f);
-        if (r >= 0 && r < a.in_rows) v = *reinterpret_cast<const float2*>(xin + (size_t)r * C + c);
-        v.x = snake_fast(v.x, al1.x, iv1.x);
-        v.y = snake_fast(v.y, al1.y, iv1.y);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) win[k] = win[k + 1];
-        win[6] = v;
-        if (m >= 6) {
-          const int trow = first + (m - 6) * DIL;
-          if (trow < BM) {
-            float2 acc = bs;
-#pragma unroll
-            for (int k = 0; k < 7; ++k) { acc.x = fmaf(w[k].x, win[k].x, acc.x); acc.y = fmaf(w[k].y, win[k].y, acc.y); }
-            acc.x = snake_fast(acc.x, al2.x, iv2.x);
-            acc.y = snake_fast(acc.y, al2.y, iv2.y);
-            // K-major SWIZZLE_128B: 16-byte chunk index XOR (row % 8) inside each 1024-byte 8-row group
-            const int off = (trow >> 3) * 1024 + (trow & 7) * 128 + ((((bcol >> 4) ^ (trow & 7)) << 4) | (bcol & 15));
-            *reinterpret_cast<__half2*>(a_kb + off) = __floats2half2_rn(acc.x, acc.y);
-          }
-        }
-      }
+      uint32_t mlo, mhi;
+      row_mask<DIL>(in_first, a.in_rows, 22, mlo, mhi);
+      // K-major SWIZZLE_128B operand tile: byte (row, col) -> row*128 + ((col/16 ^ row%8) * 16) + col%16
+      uint8_t* a_kb = sA + (c / BK) * (BM * 128) + ((c % BK) * 2 & 15);
+      const int chunk = ((c % BK) * 2) >> 4;
+      dw_unit<C, DIL, 16>(xin + (long long)in_first * C + c, mlo, mhi, W, [&](int j, float2 v) {
+        const int trow = first + j * DIL;
+        if (trow < BM)
+          *reinterpret_cast<__half2*>(a_kb + trow * 128 + (((chunk ^ trow) & 7) << 4)) = __floats2half2_rn(v.x, v.y);
+      });
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
   }
@@ -630,7 +667,7 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
       for (int i = 0; i < 8; ++i) {
         const int row = rr + 4 * i;
         res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (meta_out[q * 32 + row] >= 0) res[i] = *reinterpret_cast<const float4*>(xin + (size_t)(res_row0 + row) * C + col);
+        if (meta_out[q * 32 + row] >= 0) res[i] = __ldg(reinterpret_cast<const float4*>(xin + (size_t)(res_row0 + row) * C + col));
       }
     }
     mbar_wait(smem_u32(&bars[1]), 0);
@@ -644,7 +681,7 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
         for (int i = 0; i < 8; ++i) {
           const int row = rr + 4 * i;
           res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (meta_out[q * 32 + row] >= 0) res[i] = *reinterpret_cast<const float4*>(xin + (size_t)(res_row0 + row) * C + col);
+          if (meta_out[q * 32 + row] >= 0) res[i] = __ldg(reinterpret_cast<const float4*>(xin + (size_t)(res_row0 + row) * C + col));
         }
       }
       uint32_t r[32];
@@ -666,7 +703,11 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
         const bool live = !(oi & (int)kLiveFlag);
         oi &= (int)(kLiveFlag - 1);
         float4 v = *reinterpret_cast<const float4*>(stg + row * 32 + ((cg ^ (row & 7)) << 2));
-        v.x += b4.x + res[i].x; v.y += b4.y + res[i].y; v.z += b4.z + res[i].z; v.w += b4.w + res[i].w;
+        {
+          const float2 lo = __fadd2_rn(__fadd2_rn(make_float2(v.x, v.y), make_float2(b4.x, b4.y)), make_float2(res[i].x, res[i].y));
+          const float2 hi = __fadd2_rn(__fadd2_rn(make_float2(v.z, v.w), make_float2(b4.z, b4.w)), make_float2(res[i].z, res[i].w));
+          v = make_float4(lo.x, lo.y, hi.x, hi.y);
+        }
         if (!live) v = make_float4(0.f, 0.f, 0.f, 0.f);
         const size_t o = (size_t)oi * C + col;
         if (a.out32) *reinterpret_cast<float4*>(a.out32 + o) = v;

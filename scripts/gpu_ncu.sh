@@ -9,7 +9,7 @@ $CMD > $OUT/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s $SKIP -c $CNT --csv --log-file $OUT/launches.csv $CMD > $OUT/ncu_list.log 2>&1
 echo "list rc=$?"
 $CMD > $OUT/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:$KRE -s 100 -c 3 -o $OUT/prof $CMD > $OUT/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:$KRE -s ${FSKIP:-24} -c ${FCNT:-3} -o $OUT/prof $CMD > $OUT/ncu_full.log 2>&1
 echo "full rc=$?"
 tail -3 $OUT/ncu_list.log $OUT/ncu_full.log
 ls -la $OUT
