@@ -320,3 +320,60 @@ def test_snac_shim_runs_decode_like_reference(oracle_w1, state_dict_w1):
     assert float((y.cpu() - ref).abs().max()) <= TOL_FP32_MAX_ABS
     with pytest.raises(IndexError):
         m.decode([torch.full((1, k), 4096, dtype=torch.int32, device="cuda") for k in (1, 2, 4)])
+
+
+def test_tick_scheduler_on_gpu_matches_per_stream_decoder(monkeypatch):
+    """BASELINE config 5 pattern: ragged windows (7/28/49 tokens), stream insert/evict per tick; every
+    stream's bytes equal what the per-stream tokens_decoder yields (same CUDA path, noise off)."""
+    monkeypatch.setenv("SNACB_NOISE", "off")
+    monkeypatch.setenv("SNACB_PRECISION", "fp16")
+    monkeypatch.setenv("SNACB_RANDOM_INIT", "0:w1")
+    monkeypatch.delenv("ORPHEUS_SNAC_PATH", raising=False)
+    import importlib
+    import sys
+    sys.modules.pop("project_morpheus_b200.speechpipe", None)
+    speechpipe = importlib.import_module("project_morpheus_b200.speechpipe")
+    from project_morpheus_b200.scheduler import TickScheduler
+
+    lifetimes = {0: 2, 1: 60 // 6, 2: 5, 3: 6, 4: 9, 5: 12, 6: 3, 7: 8}  # frames per stream (scene-like mix)
+    streams = {i: sp.synth_token_strings(800 + i, f) for i, f in lifetimes.items()}
+
+    async def per_stream(strings):
+        async def gen():
+            for s in strings:
+                yield s
+        return [c async for c in speechpipe.tokens_decoder(gen())]
+
+    want = {i: asyncio.run(per_stream(s)) for i, s in streams.items()}
+    sched = TickScheduler(speechpipe.convert_to_audio_batch)
+    got = {i: [] for i in streams}
+    for i in streams:
+        sched.add_stream(i)
+    cur = {i: 0 for i in streams}
+    rng = np.random.default_rng(1)
+    evicted = None
+    while any(cur[i] < len(streams[i]) for i in streams if i != evicted):
+        for i in streams:
+            if i == evicted:
+                continue
+            n = int(rng.integers(0, 15))
+            part = streams[i][cur[i]: cur[i] + n]
+            cur[i] += len(part)
+            sched.push_many(i, part)
+        sched.tick()
+        for i in streams:
+            if i != evicted:
+                got[i] += sched.pop_audio(i)
+        if evicted is None and cur[2] >= 21:  # barge-in on stream 2 after three frames
+            sched.evict(2)
+            evicted = 2
+    for i in streams:
+        if i != evicted:
+            sched.finish(i)
+    sched.drain()
+    for i in streams:
+        if i == evicted:
+            assert got[i] == want[i][: len(got[i])]  # a prefix of the full stream, then nothing
+            continue
+        got[i] += sched.pop_audio(i)
+        assert got[i] == want[i], f"stream {i}"
