@@ -29,7 +29,7 @@ namespace {
 
 constexpr int BM = 128;  // rows per tile = TMEM lanes
 constexpr int BK = 64;   // fp16 per k-block = one 128-byte swizzle span
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr uint32_t kLiveFlag = 0x40000000u;
 
 // ------------------------------------------------------------------------------------ PTX wrappers
@@ -104,6 +104,48 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// Epilogue transpose: a warp holds a 32-row x 16-column fp32 block one row per lane (tcgen05.ld
+// 32x32b.x16); after the trip through its private 2 KB of swizzled shared memory lane l holds, for
+// i = 0..3, the float4 of row (l/4 + 8i), columns 4*(l%4)..+3 - so global accesses are 64-byte row
+// segments.  16-byte chunk index is XORed with (row/2)%4: conflict-free on both sides.
+__device__ __forceinline__ void epi_transpose16(float* stg, int lane, const uint32_t (&r)[16], float4 (&v)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<float4*>(stg + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) =
+        make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                    __uint_as_float(r[4 * j + 3]));
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = (lane >> 2) + 8 * i;
+    v[i] = *reinterpret_cast<const float4*>(stg + row * 16 + (((lane & 3) ^ ((row >> 1) & 3)) << 2));
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void store_half4(__half* p, float4 v) {
+  const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+  pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+  *reinterpret_cast<uint2*>(p) = pk;
+}
+__device__ __forceinline__ float4 add4(float4 a, float4 b) {
+  const float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+  const float2 hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+// 1024-byte aligned view of the dynamic shared memory that keeps the shared address space (no generic ld/st)
+__device__ __forceinline__ uint8_t* smem_align1024(uint8_t* raw) { return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u); }
 
 // Shared-memory matrix descriptor of a K-major operand tile written by TMA with SWIZZLE_128B:
 // rows of 128 bytes (64 fp16 of K), 8-row groups of 1024 bytes (SBO), tile base 1024-byte aligned.
@@ -202,7 +244,7 @@ template <int BN> struct TcSmem {
   static constexpr int kMetaBytes = 3 * BM * 4 + 128;
   // stages = min(k-blocks, kMaxStages): short-K layers keep little shared memory so more CTAs share an SM
   static constexpr int bytes(int stages) { return stages * kStageBytes + kMetaBytes + 1024; }  // + alignment slack
-  static_assert(kStageBytes >= 4 * 32 * 32 * 4, "epilogue staging aliases pipeline stage 0");
+  static_assert(kStageBytes >= 8 * 32 * 16 * 4, "epilogue staging aliases pipeline stage 0");
 };
 
 template <int BN, int EPI>
@@ -210,7 +252,7 @@ __global__ void __launch_bounds__(kTcThreads, 3) k_gemm_tc(const __grid_constant
                                                          const __grid_constant__ CUtensorMap tmW, const TcDev a) {
   using S = TcSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   const int kStages = a.stages;
   uint8_t* meta = smem + kStages * S::kStageBytes;
   int* meta_out = reinterpret_cast<int*>(meta);
@@ -273,10 +315,11 @@ __global__ void __launch_bounds__(kTcThreads, 3) k_gemm_tc(const __grid_constant
       umma_commit(smem_u32(&bars[2 * kStages]));     // accumulator complete
     }
   } else {
-    // ===================================================================== epilogue (warps 2..5)
+    // ===================================================================== epilogue (warps 2..9)
     const int q = warp & 3;            // TMEM lane quarter this warp may read
-    const int trow = q * 32 + lane;    // tile row owned in TMEM
-    {
+    const int half = (warp - 2) >> 2;  // the two warps of a quarter split the tile's columns
+    if (half == 0) {                   // row metadata, one tile row per thread of the first four warps
+      const int trow = q * 32 + lane;
       const long long gm = (long long)m0 + trow;
       int oi = -1, ri = -1;
       float nz = 0.0f;
@@ -297,71 +340,65 @@ __global__ void __launch_bounds__(kTcThreads, 3) k_gemm_tc(const __grid_constant
       }
       meta_out[trow] = oi; meta_res[trow] = ri; meta_nz[trow] = nz;
     }
-    __syncwarp();
-    const int cg = lane & 7, rr = lane >> 3;
-    const int ocol0 = n0 + cg * 4 - ((EPI == EPI_CONVT) ? phase * a.Cout : 0);
-    float4 res[8];
-    auto load_res = [&](int c) {  // residual / carrier rows of this lane for 32-column chunk c (independent of the MMA)
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue warps only
+    const int c4 = lane & 3, r8 = lane >> 2;
+    constexpr int NH = BN / 32;  // 16-column half-chunks per warp
+    const int ocol0 = n0 + half * (BN / 2) + c4 * 4 - ((EPI == EPI_CONVT) ? phase * a.Cout : 0);
+    int oi4[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int ri = meta_res[q * 32 + rr + 4 * i];
+    for (int i = 0; i < 4; ++i) oi4[i] = meta_out[q * 32 + r8 + 8 * i];
+    float4 res[4];
+    auto load_res = [&](int h) {  // residual / carrier values of this lane for half-chunk h (independent of the MMA)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
         res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ri >= 0) res[i] = __ldg(reinterpret_cast<const float4*>(a.R + (size_t)ri * a.ldr + ocol0 + c * 32));
+        if (oi4[i] >= 0)
+          res[i] = __ldg(reinterpret_cast<const float4*>(a.R + (size_t)meta_res[q * 32 + r8 + 8 * i] * a.ldr + ocol0 + h * 16));
       }
     };
     if (EPI == EPI_RESID || EPI == EPI_NOISE) load_res(0);
     mbar_wait(smem_u32(&bars[2 * kStages]), 0);
     tc_fence_after();
-    float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 32);  // aliases stage 0: all MMAs are done
+    float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 16);  // aliases stage 0: all MMAs are done
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      if ((EPI == EPI_RESID || EPI == EPI_NOISE) && c > 0) load_res(c);
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-            make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                        __uint_as_float(r[4 * j + 3]));
-      __syncwarp();
-      const int ocol = n0 + c * 32 + cg * 4 - ((EPI == EPI_CONVT) ? phase * a.Cout : 0);
+    for (int h = 0; h < NH; ++h) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2) + h * 16), r);
+      float4 v[4];
+      epi_transpose16(stg, lane, r, v);
+      const int ocol = ocol0 + h * 16;
       float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), al = b4, iv = b4;
       if (a.bias) b4 = *reinterpret_cast<const float4*>(a.bias + ocol);
       if (a.sn_alpha) { al = *reinterpret_cast<const float4*>(a.sn_alpha + ocol); iv = *reinterpret_cast<const float4*>(a.sn_inv + ocol); }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = rr + 4 * i;
-        int oi = meta_out[q * 32 + row];
+      for (int i = 0; i < 4; ++i) {
+        int oi = oi4[i];
         if (oi < 0) continue;
         const bool live = !(oi & (int)kLiveFlag);
         oi &= (int)(kLiveFlag - 1);
-        float4 v = *reinterpret_cast<const float4*>(stg + row * 32 + ((cg ^ (row & 7)) << 2));
-        v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-        if (EPI == EPI_RESID || EPI == EPI_NOISE) {
-          const float4 r4 = res[i];
-          if (EPI == EPI_NOISE) {
-            const float nz = meta_nz[q * 32 + row];
-            v.x = fmaf(nz, v.x, r4.x); v.y = fmaf(nz, v.y, r4.y); v.z = fmaf(nz, v.z, r4.z); v.w = fmaf(nz, v.w, r4.w);
-          } else {
-            v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
-          }
+        float4 x = add4(v[i], b4);
+        if (EPI == EPI_NOISE) {
+          const float nz = meta_nz[q * 32 + r8 + 8 * i];
+          const float2 n2 = make_float2(nz, nz);
+          const float2 lo = __ffma2_rn(n2, make_float2(x.x, x.y), make_float2(res[i].x, res[i].y));
+          const float2 hi = __ffma2_rn(n2, make_float2(x.z, x.w), make_float2(res[i].z, res[i].w));
+          x = make_float4(lo.x, lo.y, hi.x, hi.y);
+        } else if (EPI == EPI_RESID) {
+          x = add4(x, res[i]);
         }
-        if (!live) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!live) x = make_float4(0.f, 0.f, 0.f, 0.f);
         const size_t o = (size_t)oi * a.ldo + ocol;
-        if (a.out32) *reinterpret_cast<float4*>(a.out32 + o) = v;
+        if (a.out32) *reinterpret_cast<float4*>(a.out32 + o) = x;
         if (a.out16) {
           if (a.sn_alpha) {
-            v.x = snake_fast(v.x, al.x, iv.x); v.y = snake_fast(v.y, al.y, iv.y);
-            v.z = snake_fast(v.z, al.z, iv.z); v.w = snake_fast(v.w, al.w, iv.w);
+            const float2 lo = snake2(make_float2(x.x, x.y), make_float2(al.x, al.y), make_float2(iv.x, iv.y));
+            const float2 hi = snake2(make_float2(x.z, x.w), make_float2(al.z, al.w), make_float2(iv.z, iv.w));
+            x = make_float4(lo.x, lo.y, hi.x, hi.y);
           }
-          const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-          uint2 pk;
-          pk.x = *reinterpret_cast<const uint32_t*>(&h0);
-          pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-          *reinterpret_cast<uint2*>(a.out16 + o) = pk;
+          store_half4(a.out16 + o, x);
         }
       }
-      __syncwarp();
+      if ((EPI == EPI_RESID || EPI == EPI_NOISE) && h + 1 < NH) load_res(h + 1);
     }
     tc_fence_before();
   }
@@ -554,11 +591,11 @@ struct RuDev {
 };
 
 template <int C> struct RuSmem {
-  static constexpr int kABytes = BM * C * 2;
+  static constexpr int kABytes = BM * C * 2;   // operand tile; the epilogue staging (16 KB) aliases it after the MMAs
   static constexpr int kWBytes = C * C * 2;
-  static constexpr int kStgBytes = 8 * 32 * 32 * 4;
   static constexpr int kMetaBytes = BM * 4 + 64;
-  static constexpr int kBytes = kABytes + kWBytes + kStgBytes + kMetaBytes + 1024;
+  static constexpr int kBytes = kABytes + kWBytes + kMetaBytes + 1024;
+  static_assert(kABytes >= 8 * 32 * 16 * 4, "staging aliases the operand tile");
 };
 
 template <int C, int DIL>
@@ -566,11 +603,11 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
   using S = RuSmem<C>;
   constexpr int KB = C / BK;  // k-blocks of 64 channels
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sA = smem;
   uint8_t* sW = smem + S::kABytes;
-  float* sStg = reinterpret_cast<float*>(smem + S::kABytes + S::kWBytes);
-  int* meta_out = reinterpret_cast<int*>(smem + S::kABytes + S::kWBytes + S::kStgBytes);
+  float* sStg = reinterpret_cast<float*>(smem);  // valid once the accumulator barrier has fired
+  int* meta_out = reinterpret_cast<int*>(smem + S::kABytes + S::kWBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(meta_out + BM);  // [0] weight landed, [1] accumulator complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
@@ -655,75 +692,60 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
   } else if (warp < 8) {
     // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., the two warps of a quarter split the columns
     const int q = warp & 3, half = warp >> 2;
-    constexpr int NCH = C / 64;  // 32-column chunks per warp
-    const int cg = lane & 7, rr = lane >> 3;
-    float* stg = sStg + warp * (32 * 32);
+    constexpr int NH = C / 32;  // 16-column half-chunks per warp
+    const int c4 = lane & 3, r8 = lane >> 2;
+    float* stg = sStg + warp * (32 * 16);
     const float* xin = a.x + (size_t)item * a.in_rows * C;
-    const int res_row0 = a.out_lo + row0 + q * 32 - a.in_lo;  // operand row of tile row q*32
-    float4 res[8];
-    {
-      const int col = (half * NCH) * 32 + cg * 4;
+    const int col0 = half * (C / 2) + c4 * 4;
+    int oi4[4];
+    const float* rrow[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = rr + 4 * i;
-        res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (meta_out[q * 32 + row] >= 0) res[i] = __ldg(reinterpret_cast<const float4*>(xin + (size_t)(res_row0 + row) * C + col));
-      }
+    for (int i = 0; i < 4; ++i) {
+      const int row = q * 32 + r8 + 8 * i;
+      oi4[i] = meta_out[row];
+      rrow[i] = xin + (size_t)(a.out_lo + row0 + row - a.in_lo) * C + col0;
     }
+    float4 res[4];
+    auto load_res = [&](int h) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (oi4[i] >= 0) res[i] = __ldg(reinterpret_cast<const float4*>(rrow[i] + h * 16));
+      }
+    };
+    load_res(0);
     mbar_wait(smem_u32(&bars[1]), 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int ci = 0; ci < NCH; ++ci) {
-      const int chunk = half * NCH + ci;
-      const int col = chunk * 32 + cg * 4;
-      if (ci > 0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = rr + 4 * i;
-          res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (meta_out[q * 32 + row] >= 0) res[i] = __ldg(reinterpret_cast<const float4*>(xin + (size_t)(res_row0 + row) * C + col));
-        }
-      }
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(chunk * 32), r);
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-            make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                        __uint_as_float(r[4 * j + 3]));
-      __syncwarp();
+    for (int h = 0; h < NH; ++h) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (C / 2) + h * 16), r);
+      float4 v[4];
+      epi_transpose16(stg, lane, r, v);
+      const int col = col0 + h * 16;
       const float4 b4 = *reinterpret_cast<const float4*>(a.pw_b + col);
       float4 al = make_float4(0.f, 0.f, 0.f, 0.f), iv = al;
       if (a.sn_alpha) { al = *reinterpret_cast<const float4*>(a.sn_alpha + col); iv = *reinterpret_cast<const float4*>(a.sn_inv + col); }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = rr + 4 * i;
-        int oi = meta_out[q * 32 + row];
+      for (int i = 0; i < 4; ++i) {
+        int oi = oi4[i];
         if (oi < 0) continue;
         const bool live = !(oi & (int)kLiveFlag);
         oi &= (int)(kLiveFlag - 1);
-        float4 v = *reinterpret_cast<const float4*>(stg + row * 32 + ((cg ^ (row & 7)) << 2));
-        {
-          const float2 lo = __fadd2_rn(__fadd2_rn(make_float2(v.x, v.y), make_float2(b4.x, b4.y)), make_float2(res[i].x, res[i].y));
-          const float2 hi = __fadd2_rn(__fadd2_rn(make_float2(v.z, v.w), make_float2(b4.z, b4.w)), make_float2(res[i].z, res[i].w));
-          v = make_float4(lo.x, lo.y, hi.x, hi.y);
-        }
-        if (!live) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 x = add4(add4(v[i], b4), res[i]);
+        if (!live) x = make_float4(0.f, 0.f, 0.f, 0.f);
         const size_t o = (size_t)oi * C + col;
-        if (a.out32) *reinterpret_cast<float4*>(a.out32 + o) = v;
+        if (a.out32) *reinterpret_cast<float4*>(a.out32 + o) = x;
         if (a.out16) {
           if (a.sn_alpha) {
-            v.x = snake_fast(v.x, al.x, iv.x); v.y = snake_fast(v.y, al.y, iv.y);
-            v.z = snake_fast(v.z, al.z, iv.z); v.w = snake_fast(v.w, al.w, iv.w);
+            const float2 lo = snake2(make_float2(x.x, x.y), make_float2(al.x, al.y), make_float2(iv.x, iv.y));
+            const float2 hi = snake2(make_float2(x.z, x.w), make_float2(al.z, al.w), make_float2(iv.z, iv.w));
+            x = make_float4(lo.x, lo.y, hi.x, hi.y);
           }
-          const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-          uint2 pk;
-          pk.x = *reinterpret_cast<const uint32_t*>(&h0);
-          pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-          *reinterpret_cast<uint2*>(a.out16 + o) = pk;
+          store_half4(a.out16 + o, x);
         }
       }
-      __syncwarp();
+      if (h + 1 < NH) load_res(h + 1);
     }
     tc_fence_before();
   }
