@@ -375,15 +375,28 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
       const int sid = 3 + 9 * b;
       const bool noisy = nz.mode != SNACB_NOISE_OFF;
       __half* Y16 = Aother;  // transposed-conv output as the noise GEMM operand
+      const bool fuse_cn = noisy && convt_noise_supported(B.Cin, B.Cout) && !(e->cfg.flags & SNACB_FLAG_NO_CONVT_NOISE_FUSION) &&
+                           e->tap_stage != sid + 1;
       {
         TcGemmArgs a{};
         a.epi = EPI_CONVT; a.A = Ain; a.K = B.Cin; a.a_rows = B.in.n(); a.a_lo = B.in.lo; a.W = Wb.ct16; a.N = B.s * B.Cout;
         a.bias = Wb.ct_b; a.s = B.s; a.p = B.p; a.Cout = B.Cout; a.o_r = B.ct; a.ldo = B.Cout; a.up = B.up_out;
-        a.out32 = noisy ? Y : X; a.out16 = noisy ? Y16 : nullptr;
-        gemm(a);
-        tap(e, sid + 1, noisy ? Y : X, B.ct, B.Cout, n, first, st);
+        if (fuse_cn) {
+          a.out32 = X;
+          a.noise = NoiseSrc{nz.mode, nz.tensor, nz.stride, noise_off[b], (unsigned long long)nz.seed, nz.d_keys, b};
+          if (ce == cudaSuccess) {
+            const double M = (double)n * a.a_rows;
+            ProfScope ps(e, KC_CONVT, 2.0 * M * a.N * a.K * 2.0 + 2.0 * M * B.s * B.Cout * B.Cout,
+                         2.0 * (M * a.K * 2.0 + (double)a.N * a.K * 2.0) + 4.0 * (double)n * B.ct.n() * B.Cout, st);
+            ce = launch_convt_noise_tc(g, a, Wb.noise16);
+          }
+        } else {
+          a.out32 = noisy ? Y : X; a.out16 = noisy ? Y16 : nullptr;
+          gemm(a);
+          tap(e, sid + 1, noisy ? Y : X, B.ct, B.Cout, n, first, st);
+        }
       }
-      if (noisy) {
+      if (noisy && !fuse_cn) {
         TcGemmArgs a{};
         a.epi = EPI_NOISE; a.A = Y16; a.K = B.Cout; a.a_rows = B.ct.n(); a.a_lo = B.ct.lo; a.W = Wb.noise16; a.N = B.Cout;
         a.out32 = X; a.o_r = B.ct; a.ldo = B.Cout; a.R = Y; a.r_r = B.ct; a.ldr = B.Cout; a.up = B.up_out;

@@ -78,6 +78,9 @@ struct TcGemmArgs {
 };
 cudaError_t launch_gemm_tc(const GroupCtx& g, const TcGemmArgs& a);
 int tc_tile_n(const TcGemmArgs& a);
+// ConvTranspose1d + NoiseBlock in one kernel (blocks whose Cout is 64 / 128)
+bool convt_noise_supported(int Cin, int Cout);
+cudaError_t launch_convt_noise_tc(const GroupCtx& g, const TcGemmArgs& convt, const __half* noise_w16);
 
 struct DwTcArgs {
   const float* in; Rng in_r;

@@ -409,6 +409,192 @@ __global__ void __launch_bounds__(kTcThreads, 3) k_gemm_tc(const __grid_constant
   }
 }
 
+// ============================================================================ ConvT + NoiseBlock fused
+// x = y + n[t] * (W_n y),  y = ConvTranspose1d(Snake(x_in)) + b, for decoder blocks whose output width
+// Cout fits one tile (blocks 2 and 3: Cout = 128 / 64).  The polyphase transposed conv accumulates a
+// 128 x Cout tile in TMEM (D1); the epilogue warps add the bias, round to fp16 and write the tile
+// straight into the swizzled K-major operand layout in the (now idle) pipeline stage 0 while the
+// producer TMA-loads W_n into stage 1; a second tcgen05.mma chain builds D2 = fp16(y) W_n^T beside D1;
+// the final epilogue combines D1 + b + n*D2 per row and stores fp32 x coalesced.  Saves the fp32 +
+// fp16 round trip of y through HBM (12 B per element) and one launch per block.
+template <int BN>
+__global__ void __launch_bounds__(kTcThreads, 2) k_convt_noise_tc(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmW,
+                                                                const __grid_constant__ CUtensorMap tmN, const TcDev a) {
+  using S = TcSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_align1024(smem_raw);
+  const int kStages = a.stages;  // >= 3 (host-checked): stage 0 = fp16 y tile, stage 1 = W_n, stage 2 = transposes
+  uint8_t* meta = smem + kStages * S::kStageBytes;
+  int* meta_out = reinterpret_cast<int*>(meta);
+  float* meta_nz = reinterpret_cast<float*>(meta_out + BM);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(meta + 3 * BM * 4);  // full[], empty[], accum1, wn_full, y_ready, accum2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kMaxStages + 4);
+  const uint32_t bar_acc1 = smem_u32(&bars[2 * S::kMaxStages]), bar_wn = smem_u32(&bars[2 * S::kMaxStages + 1]);
+  const uint32_t bar_y = smem_u32(&bars[2 * S::kMaxStages + 2]), bar_acc2 = smem_u32(&bars[2 * S::kMaxStages + 3]);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM;
+  const int phase = blockIdx.y;  // one N tile per polyphase component (BN == Cout)
+  const int delta = (phase < a.s - a.p) ? -1 : 1;
+  const long long Mtot = (long long)a.n_items * a.a_rows;
+  const int kb_per_seg = a.K / BK;
+  const int num_kb = kb_per_seg * 2;
+  constexpr int KB2 = BN / BK;  // k-blocks of the noise GEMM (K = Cout)
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(smem_u32(&bars[i]), 1);
+      mbar_init(smem_u32(&bars[S::kMaxStages + i]), 1);
+    }
+    mbar_init(bar_acc1, 1); mbar_init(bar_wn, 1); mbar_init(bar_y, 1); mbar_init(bar_acc2, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  uint8_t* sY = smem;                       // [KB2][128 rows][128 B]
+  uint8_t* sWn = smem + S::kStageBytes;     // [KB2][BN rows][128 B]
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int st = kb % kStages;
+        mbar_wait(smem_u32(&bars[S::kMaxStages + st]), ((kb / kStages) & 1) ^ 1);
+        const uint32_t full = smem_u32(&bars[st]);
+        const uint32_t sa = smem_u32(smem + st * S::kStageBytes), sb = sa + BM * BK * 2;
+        const int seg = kb / kb_per_seg, kk = (kb - seg * kb_per_seg) * BK;
+        mbar_arrive_expect_tx(full, S::kStageBytes);
+        tma_load_2d(sa, &tmA, full, kk, m0 + (seg ? delta : 0));
+        tma_load_2d(sb, &tmW, full, seg * a.K + kk, phase * BN);
+      }
+      mbar_wait(bar_acc1, 0);  // every conv MMA has finished reading the stages
+      mbar_arrive_expect_tx(bar_wn, BN * BN * 2);
+#pragma unroll
+      for (int kb = 0; kb < KB2; ++kb) tma_load_2d(smem_u32(sWn + kb * BN * 128), &tmN, bar_wn, kb * BK, 0);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int st = kb % kStages;
+        mbar_wait(smem_u32(&bars[st]), (kb / kStages) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + st * S::kStageBytes), sb = sa + BM * BK * 2;
+        const uint64_t da = umma_desc_k_sw128(sa), db = umma_desc_k_sw128(sb);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+        umma_commit(smem_u32(&bars[S::kMaxStages + st]));
+      }
+      umma_commit(bar_acc1);
+      mbar_wait(bar_wn, 0);
+      mbar_wait(bar_y, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int kb = 0; kb < KB2; ++kb) {
+        const uint64_t da = umma_desc_k_sw128(smem_u32(sY + kb * BM * 128));
+        const uint64_t db = umma_desc_k_sw128(smem_u32(sWn + kb * BN * 128));
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_base + BN, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+      }
+      umma_commit(bar_acc2);
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int trow = q * 32 + lane;  // TMEM lane == tile row owned by this thread in the row-per-lane phases
+    int my_oi = -1;
+    float my_nz = 0.0f;
+    {
+      const long long gm = (long long)m0 + trow;
+      if (gm < Mtot) {
+        const int item = (int)(gm / a.a_rows), j = (int)(gm - (long long)item * a.a_rows);
+        const ItemRef it = get_item(a.items, a.base, item, a.out_len);
+        const int t_rel = (a.a_lo + j) * a.s + phase;
+        const int orow = t_rel - a.o_lo;
+        if (orow >= 0 && orow < a.o_rows) {
+          const int t_abs = t_rel + it.shift0 * a.up;
+          const bool live = (t_abs >= 0) && (t_abs < a.T0 * a.up);
+          my_oi = item * a.o_rows + orow;
+          if (live) my_nz = noise_at(a.noise, it.code_row, t_abs);
+          else my_oi |= (int)kLiveFlag;
+        }
+      }
+      if (half == 0) meta_out[trow] = my_oi;
+    }
+    constexpr int NH = BN / 32;  // 16-column half-chunks per warp
+    const int colbase = half * (BN / 2);
+    mbar_wait(bar_acc1, 0);
+    tc_fence_after();
+    // ---- phase 1: y = D1 + b -> fp16 -> operand tile (row per lane is exactly the K-major layout)
+#pragma unroll 1
+    for (int h = 0; h < NH; ++h) {
+      const int col = colbase + h * 16;
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, r);
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + col + 4 * j));
+        const __half2 h0 = __floats2half2_rn(__uint_as_float(r[4 * j]) + b4.x, __uint_as_float(r[4 * j + 1]) + b4.y);
+        const __half2 h1 = __floats2half2_rn(__uint_as_float(r[4 * j + 2]) + b4.z, __uint_as_float(r[4 * j + 3]) + b4.w);
+        pk[2 * j] = *reinterpret_cast<const uint32_t*>(&h0);
+        pk[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+      }
+      uint8_t* rowp = sY + (col / BK) * (BM * 128) + trow * 128;
+      const int ch = ((col % BK) * 2) >> 4;  // first of the two 16-byte chunks
+      *reinterpret_cast<uint4*>(rowp + (((ch) ^ (trow & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(rowp + (((ch + 1) ^ (trow & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (warp == 2 && lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_y) : "memory");
+    // ---- phase 2: x = (D1 + b) + n * D2, transposed through stage 2, stored coalesced
+    const int c4 = lane & 3, r8 = lane >> 2;
+    int oi4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) oi4[i] = meta_out[q * 32 + r8 + 8 * i];
+    float* stg = reinterpret_cast<float*>(smem + 2 * S::kStageBytes) + (warp - 2) * (32 * 16);
+    const bool live = my_oi >= 0 && !(my_oi & (int)kLiveFlag);
+    mbar_wait(bar_acc2, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int h = 0; h < NH; ++h) {
+      const int col = colbase + h * 16;
+      uint32_t d1[16], d2[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, d1);
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + col), d2);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + col + 4 * j));
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float y = __uint_as_float(d1[4 * j + e]) + bb[e];
+          const float x = fmaf(my_nz, __uint_as_float(d2[4 * j + e]), y);
+          d1[4 * j + e] = __float_as_uint(live ? x : 0.0f);
+        }
+      }
+      float4 v[4];
+      epi_transpose16(stg, lane, d1, v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (oi4[i] < 0) continue;
+        const size_t o = (size_t)(oi4[i] & (int)(kLiveFlag - 1)) * a.ldo + col + c4 * 4;
+        *reinterpret_cast<float4*>(a.out32 + o) = v[i];
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
 // ------------------------------------------------------------------------------------ tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -484,7 +670,43 @@ cudaError_t launch_tc_bn(int epi, const CUtensorMap& ma, const CUtensorMap& mw, 
   }
 }
 
+template <int BN>
+cudaError_t launch_cn_t(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mn, const TcDev& d, dim3 grid,
+                        cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_convt_noise_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TcSmem<BN>::bytes(TcSmem<BN>::kMaxStages));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  k_convt_noise_tc<BN><<<grid, kTcThreads, TcSmem<BN>::bytes(d.stages), st>>>(ma, mw, mn, d);
+  return cudaGetLastError();
+}
+
 }  // namespace
+
+bool convt_noise_supported(int Cin, int Cout) { return (Cout == 64 || Cout == 128) && (2 * Cin / BK) >= 3; }
+
+// a: the EPI_CONVT arguments (out32 = x, out16 unused); noise_w16 [Cout][Cout] fp16; a.noise set.
+cudaError_t launch_convt_noise_tc(const GroupCtx& g, const TcGemmArgs& a, const __half* noise_w16) {
+  const long long Mtot = (long long)g.n_items * a.a_rows;
+  if (Mtot <= 0) return cudaSuccess;
+  const int bn = a.Cout;
+  if (!convt_noise_supported(a.K, a.Cout) || a.N != a.s * a.Cout || !a.out32) return cudaErrorInvalidValue;
+  CUtensorMap ma, mw, mn;
+  if (!get_tmap(a.A, Mtot, a.K, BM, &ma) || !get_tmap(a.W, a.N, 2 * a.K, bn, &mw) || !get_tmap(noise_w16, bn, bn, bn, &mn))
+    return cudaErrorNotSupported;
+  TcDev d{};
+  d.items = g.items; d.base = g.base; d.out_len = g.out_len; d.T0 = g.T0; d.n_items = g.n_items;
+  d.stages = std::min((a.K / BK) * 2, bn == 128 ? TcSmem<128>::kMaxStages : TcSmem<64>::kMaxStages);
+  d.K = a.K; d.nseg = 2; d.a_rows = a.a_rows; d.a_lo = a.a_lo; d.s = a.s; d.p = a.p; d.Cout = a.Cout;
+  d.bias = a.bias; d.out32 = a.out32; d.o_lo = a.o_r.lo; d.o_rows = a.o_r.n(); d.ldo = a.ldo; d.noise = a.noise; d.up = a.up;
+  dim3 grid((unsigned)((Mtot + BM - 1) / BM), (unsigned)a.s);
+  cudaError_t e = (bn == 128) ? launch_cn_t<128>(ma, mw, mn, d, grid, g.stream) : launch_cn_t<64>(ma, mw, mn, d, grid, g.stream);
+  ++*g.launches;
+  return e;
+}
 
 int tc_tile_n(const TcGemmArgs& a) {
   const int per = (a.epi == EPI_CONVT) ? a.Cout : a.N;
