@@ -3,6 +3,7 @@
 // (Morpheus_Client/tts_engine/speechpipe.py:64-137) for whole decode ticks.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <vector>
@@ -72,6 +73,7 @@ struct snacb_engine {
   size_t pin_items_cap = 0;
   cudaEvent_t items_ev = nullptr;
   int64_t launches = 0;
+  int prefetch_ahead = 0;  // SM count when L2 prefetch-ahead is on (SNACB_PREFETCH env, default on)
   Prof prof;
   // tap
   int tap_stage = -1;
@@ -415,7 +417,7 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
           const bool want32 = !last || e->tap_stage == sid + 4 + 2 * r;
           RuTcArgs u{X, cur, B.r[r], B.Cout, kDil[r], B.up_out, R.dw_w, R.dw_b, R.a1, R.i1, R.a2, R.i2, R.pw16, R.pw_b,
                      want32 ? Y : nullptr, last ? Anext : nullptr, last ? W.blk[b + 1].alpha : nullptr,
-                     last ? W.blk[b + 1].inv : nullptr};
+                     last ? W.blk[b + 1].inv : nullptr, e->prefetch_ahead * (B.Cout == 64 ? 3 : 2)};
           if (ce == cudaSuccess) {
             const double el = (double)n * B.r[r].n() * B.Cout;
             ProfScope ps(e, KC_RU, 2.0 * el * B.Cout + el * 24.0,
@@ -533,6 +535,10 @@ int snacb_create(snacb_engine** out, const snacb_config* cfg) {
   snacb_engine* e = new snacb_engine();
   e->cfg = *cfg;
   e->device = cfg->device;
+  {
+    const char* pf = getenv("SNACB_PREFETCH");
+    e->prefetch_ahead = (pf && pf[0] == '0') ? 0 : prop.multiProcessorCount;
+  }
   *out = e;
   return SNACB_OK;
 }

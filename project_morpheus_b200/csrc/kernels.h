@@ -97,6 +97,7 @@ struct RuTcArgs {
   const float* w7; const float* dw_b; const float* a1; const float* i1; const float* a2; const float* i2;
   const __half* pw16; const float* pw_b;
   float* out32; __half* out16; const float* sn_alpha; const float* sn_inv;
+  int prefetch_ahead;
 };
 bool ru_tc_supported(int C);
 cudaError_t launch_ru_tc(const GroupCtx& g, const RuTcArgs& a);

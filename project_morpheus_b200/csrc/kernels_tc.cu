@@ -810,6 +810,7 @@ struct RuDev {
   const float* w7; const float* dw_b; const float* a1; const float* i1; const float* a2; const float* i2;
   const float* pw_b;
   float* out32; __half* out16; const float* sn_alpha; const float* sn_inv;
+  int prefetch_ahead;   // CTAs resident on the whole GPU: the tile this far ahead in launch order is prefetched into L2
 };
 
 template <int C> struct RuSmem {
@@ -844,6 +845,19 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 9) tmem_alloc(smem_u32(tmem_slot), C);
+  if (a.prefetch_ahead > 0) {
+    // Pull the input rows of the tile that will take this CTA's place into L2 now: its loads then cost an
+    // L2 hit instead of a DRAM round trip (the kernel streams, nothing is resident at chunk = 1024 items).
+    const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + a.prefetch_ahead;
+    const int pit = (int)(lin / gridDim.x), ptile = (int)(lin - (long long)pit * gridDim.x);
+    if (pit < (int)gridDim.y) {
+      const int r_lo = max(a.out_lo + ptile * BM - 3 * DIL - a.in_lo, 0);
+      const int r_hi = min(a.out_lo + ptile * BM + BM + 3 * DIL - a.in_lo, a.in_rows);
+      const char* p = reinterpret_cast<const char*>(a.x + ((size_t)pit * a.in_rows + r_lo) * C);
+      const int lines = ((r_hi - r_lo) * C * 4 + 127) >> 7;
+      for (int i = tid; i < lines; i += kRuThreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (size_t)i * 128));
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1009,6 +1023,7 @@ cudaError_t launch_ru_tc(const GroupCtx& g, const RuTcArgs& a) {
   d.x = a.x; d.in_lo = a.in_r.lo; d.in_rows = a.in_r.n(); d.out_lo = a.out_r.lo; d.out_rows = a.out_r.n(); d.up = a.up;
   d.w7 = a.w7; d.dw_b = a.dw_b; d.a1 = a.a1; d.i1 = a.i1; d.a2 = a.a2; d.i2 = a.i2; d.pw_b = a.pw_b;
   d.out32 = a.out32; d.out16 = a.out16; d.sn_alpha = a.sn_alpha; d.sn_inv = a.sn_inv;
+  d.prefetch_ahead = a.prefetch_ahead;
   dim3 grid((unsigned)((a.out_r.n() + BM - 1) / BM), (unsigned)g.n_items);
   cudaError_t e = (a.C == 64) ? launch_ru_c<64>(a.dil, mw, d, grid, g.stream) : launch_ru_c<128>(a.dil, mw, d, grid, g.stream);
   ++*g.launches;
