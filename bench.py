@@ -208,7 +208,7 @@ def run_ours(args) -> None:
 
     S, F, K, W = args.streams, args.frames, args.steps, max(3, args.warmup)
     eng = SnacEngine(weights.random_state_dict(0, "w1"), device=local, precision=args.precision, trim=not args.no_trim,
-                     chunk_items=args.chunk)
+                     chunk_items=args.chunk, lanes=args.lanes)
     tok_host = synth_tokens(rank * S, S, F)                      # this rank's stream partition
     keys = np.arange(rank * S, rank * S + S, dtype=np.uint64)    # Philox stream keys
     tok_dev = torch.from_numpy(tok_host).to(dev)
@@ -293,6 +293,25 @@ def run_ours(args) -> None:
             extra[name] = {"p50_ms": 1e3 * p50, "p95_ms": 1e3 * sorted(lat)[int(0.95 * (len(lat) - 1))],
                            "audio_s_per_s": n * AUDIO_S_PER_WINDOW / p50, "reps": len(lat)}
 
+        # BASELINE config 3 (long_read): one-shot decode of 720-frame utterances, time-tiled; reduced batch by default
+        if args.long_read_batch > 0:
+            Fl, Bl = 720, args.long_read_batch
+            lr_tok = synth_tokens(50000, Bl, Fl).reshape(Bl, Fl, 7)
+            c0 = torch.from_numpy(np.ascontiguousarray(lr_tok[:, :, 0])).to(dev)
+            c1 = torch.from_numpy(np.ascontiguousarray(lr_tok[:, :, [1, 4]].reshape(Bl, 2 * Fl))).to(dev)
+            c2 = torch.from_numpy(np.ascontiguousarray(lr_tok[:, :, [2, 3, 5, 6]].reshape(Bl, 4 * Fl))).to(dev)
+            eng.decode_codes([c0, c1, c2], noise="philox", seed=1)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            reps = 3
+            for i in range(reps):
+                eng.decode_codes([c0, c1, c2], noise="philox", seed=2 + i)
+            torch.cuda.synchronize(dev)
+            dt = (time.perf_counter() - t0) / reps
+            extra["cfg3_long_read"] = {"batch": Bl, "frames": Fl, "ms": 1e3 * dt,
+                                       "audio_s_per_s": Bl * Fl * AUDIO_S_PER_WINDOW / dt,
+                                       "note": "one-shot decode, 8-frame time tiles with halo recompute, no slice"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -369,11 +388,13 @@ def main() -> None:
     ap.add_argument("--frames", type=int, default=4)
     ap.add_argument("--precision", choices=["fp16", "fp32"], default="fp16")
     ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--lanes", type=int, default=1)
     ap.add_argument("--no-trim", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline leg")
     ap.add_argument("--ref-windows", type=int, default=32, help="windows per step of the CPU reference sample")
     ap.add_argument("--latency-reps", type=int, default=200)
+    ap.add_argument("--long-read-batch", type=int, default=8, help="streams of the config-3 long_read side measurement (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -74,7 +74,8 @@ typedef struct snacb_config {
                             sized so one pass's activations stay L2-resident */
   int32_t trim;          /* 1 = compute only the dependency cone of the emitted slice (exact) */
   int32_t flags;         /* SNACB_FLAG_* (bring-up switches; 0 = production)                  */
-  int32_t reserved[10];
+  int32_t lanes;         /* chunks of one call that run concurrently on internal streams (0/1 = none) */
+  int32_t reserved[9];
 } snacb_config;
 
 /* One residual unit: x + W_pw * Snake(dw7_dil(Snake(x))) */

@@ -29,7 +29,8 @@ class Config(C.Structure):
         ("chunk_items", C.c_int32),
         ("trim", C.c_int32),
         ("flags", C.c_int32),
-        ("reserved", C.c_int32 * 10),
+        ("lanes", C.c_int32),
+        ("reserved", C.c_int32 * 9),
     ]
 
 

@@ -74,6 +74,10 @@ struct snacb_engine {
   cudaEvent_t items_ev = nullptr;
   int64_t launches = 0;
   int prefetch_ahead = 0;  // SM count when L2 prefetch-ahead is on (SNACB_PREFETCH env, default on)
+  // chunk lanes: chunks of one call run concurrently on side streams (L2-resident working sets, no wave tails)
+  std::vector<cudaStream_t> lane_streams;
+  std::vector<cudaEvent_t> lane_done;
+  cudaEvent_t lane_fork = nullptr;
   Prof prof;
   // tap
   int tap_stage = -1;
@@ -321,23 +325,39 @@ int run_group_f32(snacb_engine* e, const Plan& P, const Item* d_items, int n_tot
 int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_total, int out_len, Rng tail_out,
                  const int32_t* c0, const int32_t* c1, const int32_t* c2, int pitch0, const NoiseCfg& nz,
                  const int32_t* d_status, float* wav, int16_t* pcm, char* ws_free, size_t ws_avail, int chunk,
-                 cudaStream_t st) {
+                 int lanes, cudaStream_t st_caller) {
   const DevWeights& W = e->w;
   const size_t Zf = (size_t)P.z.n() * kLatent, S = P.max_stage_floats;
   const int F = P.T0 / 4;
   const int noise_off[4] = {0, 32 * F, 288 * F, 1312 * F};
   cudaError_t ce = cudaSuccess;
+  const int n_chunks = (n_total + chunk - 1) / chunk;
+  lanes = std::max(1, std::min(lanes, n_chunks));
+  const size_t lane_bytes = lanes > 1 ? (ws_avail / lanes) & ~size_t(255) : ws_avail;
+  if (lanes > 1) {
+    while ((int)e->lane_streams.size() < lanes) {
+      cudaStream_t s2; cudaEvent_t ev;
+      CU(e, cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+      CU(e, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      e->lane_streams.push_back(s2); e->lane_done.push_back(ev);
+    }
+    if (!e->lane_fork) CU(e, cudaEventCreateWithFlags(&e->lane_fork, cudaEventDisableTiming));
+    CU(e, cudaEventRecord(e->lane_fork, st_caller));
+    for (int l = 0; l < lanes; ++l) CU(e, cudaStreamWaitEvent(e->lane_streams[l], e->lane_fork, 0));
+  }
 
-  for (int start = 0; start < n_total; start += chunk) {
+  for (int start = 0, ci = 0; start < n_total; start += chunk, ++ci) {
     const int n = std::min(chunk, n_total - start);
     const bool first = start == 0;
-    Bump bp(ws_free);
+    const int lane = ci % lanes;
+    cudaStream_t st = lanes > 1 ? e->lane_streams[lane] : st_caller;
+    Bump bp(ws_free + (size_t)lane * (lanes > 1 ? lane_bytes : 0));
     float* Z = bp.take<float>(Zf * n);
     float* X = bp.take<float>(S * n);
     float* Y = bp.take<float>(S * n);
     __half* P16 = bp.take<__half>(S * n);
     __half* Q16 = bp.take<__half>(S * n);
-    if (bp.off > ws_avail) return fail(e, SNACB_ENOMEM, "workspace overflow in tensor-core pipeline");
+    if (bp.off > lane_bytes) return fail(e, SNACB_ENOMEM, "workspace overflow in tensor-core pipeline");
     GroupCtx g{d_items ? d_items + start : nullptr, start, n, out_len, P.T0, st, &e->launches};
 
     auto gemm = [&](const TcGemmArgs& a) {
@@ -460,6 +480,12 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
     int rc = check_launch(e, "tensor-core layer pipeline");
     if (rc) return rc;
   }
+  if (lanes > 1) {
+    for (int l = 0; l < lanes; ++l) {
+      CU(e, cudaEventRecord(e->lane_done[l], e->lane_streams[l]));
+      CU(e, cudaStreamWaitEvent(st_caller, e->lane_done[l], 0));
+    }
+  }
   return SNACB_OK;
 }
 
@@ -474,10 +500,12 @@ size_t per_item_bytes(const snacb_engine* e, const Plan& P) {
 }
 constexpr size_t kActBudget = size_t(6) << 30;  // activation workspace cap per engine
 int default_chunk(const snacb_engine* e) { return e->cfg.chunk_items > 0 ? e->cfg.chunk_items : 1024; }
+int default_lanes(const snacb_engine* e) { return e->cfg.precision == SNACB_PREC_FP16 ? std::max(1, std::min(e->cfg.lanes, 8)) : 1; }
 size_t act_bytes(const snacb_engine* e, const Plan& P, int count) {
   const size_t per = per_item_bytes(e, P);
   const int chunk = std::max(1, std::min(count, default_chunk(e)));
-  return std::max(per, std::min(kActBudget, per * chunk)) + 4096;
+  const int lanes = std::max(1, std::min(default_lanes(e), (count + chunk - 1) / chunk));
+  return std::max(per, std::min(kActBudget, per * chunk * lanes)) + 4096 + 256 * (size_t)lanes;
 }
 
 int run_group(snacb_engine* e, const Plan& P, const Item* d_items, int n_total, int out_len, Rng tail_out,
@@ -485,11 +513,13 @@ int run_group(snacb_engine* e, const Plan& P, const Item* d_items, int n_total, 
               const int32_t* d_status, float* wav, int16_t* pcm, char* ws_free, size_t ws_avail, cudaStream_t st) {
   if (e->cfg.precision == SNACB_PREC_FP16) {
     const size_t per = per_item_bytes(e, P);
-    int chunk = default_chunk(e);
+    int chunk = std::min(default_chunk(e), std::max(1, n_total));
+    int lanes = std::max(1, std::min(default_lanes(e), (n_total + chunk - 1) / chunk));
+    if ((size_t)chunk * per * lanes + 256 * (size_t)lanes > ws_avail) { lanes = 1; }
     if ((size_t)chunk * per > ws_avail) chunk = (int)(ws_avail / per);
     if (chunk < 1) return fail(e, SNACB_ENOMEM, "workspace too small for one item");
     return run_group_tc(e, P, d_items, n_total, out_len, tail_out, c0, c1, c2, pitch0, nz, d_status, wav, pcm, ws_free,
-                        ws_avail, chunk, st);
+                        ws_avail, chunk, lanes, st);
   }
   return run_group_f32(e, P, d_items, n_total, out_len, tail_out, c0, c1, c2, pitch0, nz, d_status, wav, pcm, ws_free,
                        ws_avail, st);
@@ -554,6 +584,9 @@ void snacb_destroy(snacb_engine* e) {
   if (e->pin) cudaFreeHost(e->pin);
   if (e->pin_items) cudaFreeHost(e->pin_items);
   if (e->items_ev) cudaEventDestroy(e->items_ev);
+  for (auto sidestream : e->lane_streams) cudaStreamDestroy(sidestream);
+  for (auto ev : e->lane_done) cudaEventDestroy(ev);
+  if (e->lane_fork) cudaEventDestroy(e->lane_fork);
   for (auto& r : e->prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto ev : e->prof.pool) cudaEventDestroy(ev);
   delete e;

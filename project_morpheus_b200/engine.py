@@ -28,7 +28,7 @@ class SnacEngine:
     """Owns packed weights + workspace on one CUDA device; not re-entrant."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], device: int = 0, precision: str = "fp16",
-                 chunk_items: int = 0, trim: bool = True, fuse_ru: bool = True):
+                 chunk_items: int = 0, trim: bool = True, fuse_ru: bool = True, lanes: int = 1):
         self._lib = _lib.load()
         self._h = C.c_void_p()
         if not torch.cuda.is_available():
@@ -39,7 +39,7 @@ class SnacEngine:
         prec = {"fp32": _lib.PREC_FP32, "fp16": _lib.PREC_FP16}[precision]
         cfg = _lib.Config(abi_version=_lib.ABI_VERSION, device=self.device, precision=prec,
                           chunk_items=int(chunk_items), trim=1 if trim else 0,
-                          flags=0 if fuse_ru else _lib.FLAG_NO_RU_FUSION)
+                          flags=0 if fuse_ru else _lib.FLAG_NO_RU_FUSION, lanes=int(lanes))
         torch.cuda.init()
         with torch.cuda.device(self.device):
             torch.zeros(1, device=self.torch_device)  # make sure the primary context exists

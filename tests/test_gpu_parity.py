@@ -377,3 +377,34 @@ def test_tick_scheduler_on_gpu_matches_per_stream_decoder(monkeypatch):
             continue
         got[i] += sched.pop_audio(i)
         assert got[i] == want[i], f"stream {i}"
+
+
+def test_long_read_full_size_properties(engines):
+    """BASELINE config 3 shape (720 frames = 61.44 s per stream, time-tiled with halo recompute), checked
+    through size-independent properties: (1) any interior stretch of the one-shot decode equals a
+    standalone decode of that stretch with >= 3 frames of context on both sides (the receptive field is
+    ~10 latent steps), (2) the first and last frames equal standalone decodes anchored at the sequence
+    edges (true zero padding), (3) determinism.  Noise off so absolute-time noise keys do not matter."""
+    eng = engines("fp16")
+    F, B = 720, 2
+    tok = windows_tokens(B, F, 4000)
+    lv = [sp.split_levels(row.tolist()) for row in tok]
+    codes = [torch.from_numpy(np.stack([l[k] for l in lv])) for k in range(3)]
+    full = eng.decode_codes(codes, noise="off")[:, 0].cpu().numpy()
+    assert full.shape == (B, 2048 * F) and np.isfinite(full).all() and np.abs(full).max() < 1.0
+    again = eng.decode_codes(codes, noise="off")[:, 0].cpu().numpy()
+    assert np.array_equal(full, again)
+
+    def sub(f0, f1):
+        c = [codes[0][:, f0:f1], codes[1][:, 2 * f0: 2 * f1], codes[2][:, 4 * f0: 4 * f1]]
+        return eng.decode_codes(c, noise="off")[:, 0].cpu().numpy()
+
+    ctx = 4
+    for f0, f1 in ((100, 109), (351, 360), (7, 25), (640, 700)):
+        part = sub(f0 - ctx, f1 + ctx)[:, 2048 * ctx: 2048 * (ctx + f1 - f0)]
+        ref = full[:, 2048 * f0: 2048 * f1]
+        assert np.abs(part - ref).max() <= 2e-3 and snr_db(ref, part) >= 55.0, (f0, f1, np.abs(part - ref).max())
+    head = sub(0, 12)[:, : 2048 * 8]
+    assert np.abs(head - full[:, : 2048 * 8]).max() <= 2e-3
+    tail = sub(F - 12, F)[:, -2048 * 8:]
+    assert np.abs(tail - full[:, -2048 * 8:]).max() <= 2e-3
