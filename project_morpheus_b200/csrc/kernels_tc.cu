@@ -114,33 +114,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// 256-bit global accesses (sm_100): in the epilogues every lane owns one tile row (tcgen05.ld 32x32b gives
-// row-per-lane), so a lane reads / writes 32-byte sectors of its own row - full sectors without a
-// shared-memory transpose.
-struct f8 { float v[8]; };
-__device__ __forceinline__ f8 ldg_f8(const float* p) {
-  f8 r;
-  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
-               : "l"(p));
-  return r;
-}
-__device__ __forceinline__ void stg_f8(float* p, const float* v) {
-  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
-               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
-               : "memory");
-}
-// 16 floats -> 16 fp16 (32 bytes) in one store
-__device__ __forceinline__ void stg_h16(__half* p, const float* v) {
-  uint32_t u[8];
+// Epilogue transpose: a warp holds a 32-row x 16-column fp32 block one row per lane (tcgen05.ld
+// 32x32b.x16); after the trip through its private 2 KB of swizzled shared memory lane l holds, for
+// i = 0..3, the float4 of row (l/4 + 8i), columns 4*(l%4)..+3 - so global accesses are 64-byte row
+// segments.  16-byte chunk index is XORed with (row/2)%4: conflict-free on both sides.
+__device__ __forceinline__ void epi_transpose16(float* stg, int lane, const uint32_t (&r)[16], float4 (&v)[4]) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-    u[i] = *reinterpret_cast<const uint32_t*>(&h);
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<float4*>(stg + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) =
+        make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                    __uint_as_float(r[4 * j + 3]));
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = (lane >> 2) + 8 * i;
+    v[i] = *reinterpret_cast<const float4*>(stg + row * 16 + (((lane & 3) ^ ((row >> 1) & 3)) << 2));
   }
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]),
-               "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
-               : "memory");
+  __syncwarp();
 }
 __device__ __forceinline__ void store_half4(__half* p, float4 v) {
   const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
@@ -326,16 +316,13 @@ __global__ void __launch_bounds__(kTcThreads, 3) k_gemm_tc(const __grid_constant
     }
   } else {
     // ===================================================================== epilogue (warps 2..9)
-    // Row-per-lane all the way: lane <-> tile row (TMEM lane), the two warps of a lane quarter split the
-    // columns; per 16-column step a lane touches 64 contiguous bytes of its own row with 256-bit accesses.
     const int q = warp & 3;            // TMEM lane quarter this warp may read
-    const int half = (warp - 2) >> 2;
-    const int trow = q * 32 + lane;
-    int oi = -1, ri = -1;
-    bool live = false;
-    float nz = 0.0f;
-    {
+    const int half = (warp - 2) >> 2;  // the two warps of a quarter split the tile's columns
+    if (half == 0) {                   // row metadata, one tile row per thread of the first four warps
+      const int trow = q * 32 + lane;
       const long long gm = (long long)m0 + trow;
+      int oi = -1, ri = -1;
+      float nz = 0.0f;
       if (gm < Mtot) {
         const int item = (int)(gm / a.a_rows), j = (int)(gm - (long long)item * a.a_rows);
         const ItemRef it = get_item(a.items, a.base, item, a.out_len);
@@ -344,62 +331,74 @@ __global__ void __launch_bounds__(kTcThreads, 3) k_gemm_tc(const __grid_constant
         const int orow = t_rel - a.o_lo;
         if (orow >= 0 && orow < a.o_rows) {
           const int t_abs = t_rel + it.shift0 * a.up;
-          live = (t_abs >= 0) && (t_abs < a.T0 * a.up);
+          const bool live = (t_abs >= 0) && (t_abs < a.T0 * a.up);
           oi = item * a.o_rows + orow;
           if (EPI == EPI_RESID || EPI == EPI_NOISE) ri = item * a.r_rows + (t_rel - a.r_lo);
           if (EPI == EPI_NOISE && live) nz = noise_at(a.noise, it.code_row, t_abs);
+          if (!live) oi |= (int)kLiveFlag;
         }
       }
+      meta_out[trow] = oi; meta_res[trow] = ri; meta_nz[trow] = nz;
     }
-    constexpr int NH = BN / 32;  // 16-column steps per warp
-    const int ocol0 = n0 + half * (BN / 2) - ((EPI == EPI_CONVT) ? phase * a.Cout : 0);
-    const float* rp = (EPI == EPI_RESID || EPI == EPI_NOISE) ? a.R + (size_t)max(ri, 0) * a.ldr + ocol0 : nullptr;
-    const size_t obase = (size_t)max(oi, 0) * a.ldo + ocol0;
-    f8 res0, res1;
-    if ((EPI == EPI_RESID || EPI == EPI_NOISE) && oi >= 0) { res0 = ldg_f8(rp); res1 = ldg_f8(rp + 8); }  // before the MMAs finish
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue warps only
+    const int c4 = lane & 3, r8 = lane >> 2;
+    constexpr int NH = BN / 32;  // 16-column half-chunks per warp
+    const int ocol0 = n0 + half * (BN / 2) + c4 * 4 - ((EPI == EPI_CONVT) ? phase * a.Cout : 0);
+    int oi4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) oi4[i] = meta_out[q * 32 + r8 + 8 * i];
+    float4 res[4];
+    auto load_res = [&](int h) {  // residual / carrier values of this lane for half-chunk h (independent of the MMA)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (oi4[i] >= 0)
+          res[i] = __ldg(reinterpret_cast<const float4*>(a.R + (size_t)meta_res[q * 32 + r8 + 8 * i] * a.ldr + ocol0 + h * 16));
+      }
+    };
+    if (EPI == EPI_RESID || EPI == EPI_NOISE) load_res(0);
     mbar_wait(smem_u32(&bars[2 * kStages]), 0);
     tc_fence_after();
+    float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 16);  // aliases stage 0: all MMAs are done
 #pragma unroll 1
     for (int h = 0; h < NH; ++h) {
       uint32_t r[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2) + h * 16), r);
-      if (oi < 0) continue;  // warp-uniform instructions are done; this row has no output
-      float x[16];
+      float4 v[4];
+      epi_transpose16(stg, lane, r, v);
+      const int ocol = ocol0 + h * 16;
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), al = b4, iv = b4;
+      if (a.bias) b4 = *reinterpret_cast<const float4*>(a.bias + ocol);
+      if (a.sn_alpha) { al = *reinterpret_cast<const float4*>(a.sn_alpha + ocol); iv = *reinterpret_cast<const float4*>(a.sn_inv + ocol); }
 #pragma unroll
-      for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(r[j]);
-      if (a.bias) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + ocol0 + h * 16 + 4 * j));
-          x[4 * j] += b4.x; x[4 * j + 1] += b4.y; x[4 * j + 2] += b4.z; x[4 * j + 3] += b4.w;
+      for (int i = 0; i < 4; ++i) {
+        int oi = oi4[i];
+        if (oi < 0) continue;
+        const bool live = !(oi & (int)kLiveFlag);
+        oi &= (int)(kLiveFlag - 1);
+        float4 x = add4(v[i], b4);
+        if (EPI == EPI_NOISE) {
+          const float nz = meta_nz[q * 32 + r8 + 8 * i];
+          const float2 n2 = make_float2(nz, nz);
+          const float2 lo = __ffma2_rn(n2, make_float2(x.x, x.y), make_float2(res[i].x, res[i].y));
+          const float2 hi = __ffma2_rn(n2, make_float2(x.z, x.w), make_float2(res[i].z, res[i].w));
+          x = make_float4(lo.x, lo.y, hi.x, hi.y);
+        } else if (EPI == EPI_RESID) {
+          x = add4(x, res[i]);
         }
-      }
-      if (EPI == EPI_RESID) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { x[j] += res0.v[j]; x[8 + j] += res1.v[j]; }
-      } else if (EPI == EPI_NOISE) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { x[j] = fmaf(nz, x[j], res0.v[j]); x[8 + j] = fmaf(nz, x[8 + j], res1.v[j]); }
-      }
-      if ((EPI == EPI_RESID || EPI == EPI_NOISE) && h + 1 < NH) { res0 = ldg_f8(rp + (h + 1) * 16); res1 = ldg_f8(rp + (h + 1) * 16 + 8); }
-      if (!live) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = 0.0f;
-      }
-      if (a.out32) { stg_f8(a.out32 + obase + h * 16, x); stg_f8(a.out32 + obase + h * 16 + 8, x + 8); }
-      if (a.out16) {
-        if (a.sn_alpha) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 al = __ldg(reinterpret_cast<const float4*>(a.sn_alpha + ocol0 + h * 16 + 4 * j));
-            const float4 iv = __ldg(reinterpret_cast<const float4*>(a.sn_inv + ocol0 + h * 16 + 4 * j));
-            const float2 lo = snake2(make_float2(x[4 * j], x[4 * j + 1]), make_float2(al.x, al.y), make_float2(iv.x, iv.y));
-            const float2 hi = snake2(make_float2(x[4 * j + 2], x[4 * j + 3]), make_float2(al.z, al.w), make_float2(iv.z, iv.w));
-            x[4 * j] = lo.x; x[4 * j + 1] = lo.y; x[4 * j + 2] = hi.x; x[4 * j + 3] = hi.y;
+        if (!live) x = make_float4(0.f, 0.f, 0.f, 0.f);
+        const size_t o = (size_t)oi * a.ldo + ocol;
+        if (a.out32) *reinterpret_cast<float4*>(a.out32 + o) = x;
+        if (a.out16) {
+          if (a.sn_alpha) {
+            const float2 lo = snake2(make_float2(x.x, x.y), make_float2(al.x, al.y), make_float2(iv.x, iv.y));
+            const float2 hi = snake2(make_float2(x.z, x.w), make_float2(al.z, al.w), make_float2(iv.z, iv.w));
+            x = make_float4(lo.x, lo.y, hi.x, hi.y);
           }
+          store_half4(a.out16 + o, x);
         }
-        stg_h16(a.out16 + obase + h * 16, x);
       }
+      if ((EPI == EPI_RESID || EPI == EPI_NOISE) && h + 1 < NH) load_res(h + 1);
     }
     tc_fence_before();
   }
@@ -552,10 +551,13 @@ __global__ void __launch_bounds__(kTcThreads, 2) k_convt_noise_tc(const __grid_c
     tc_fence_before();
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (warp == 2 && lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_y) : "memory");
-    // ---- phase 2: x = (D1 + b) + n * D2, row per lane, 256-bit stores
-    const bool has_out = my_oi >= 0;
-    const bool live = has_out && !(my_oi & (int)kLiveFlag);
-    const size_t obase = (size_t)(max(my_oi, 0) & (int)(kLiveFlag - 1)) * a.ldo + colbase;
+    // ---- phase 2: x = (D1 + b) + n * D2, transposed through stage 2, stored coalesced
+    const int c4 = lane & 3, r8 = lane >> 2;
+    int oi4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) oi4[i] = meta_out[q * 32 + r8 + 8 * i];
+    float* stg = reinterpret_cast<float*>(smem + 2 * S::kStageBytes) + (warp - 2) * (32 * 16);
+    const bool live = my_oi >= 0 && !(my_oi & (int)kLiveFlag);
     mbar_wait(bar_acc2, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -564,8 +566,6 @@ __global__ void __launch_bounds__(kTcThreads, 2) k_convt_noise_tc(const __grid_c
       uint32_t d1[16], d2[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, d1);
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + col), d2);
-      if (!has_out) continue;
-      float x[16];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + col + 4 * j));
@@ -573,11 +573,18 @@ __global__ void __launch_bounds__(kTcThreads, 2) k_convt_noise_tc(const __grid_c
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float y = __uint_as_float(d1[4 * j + e]) + bb[e];
-          x[4 * j + e] = live ? fmaf(my_nz, __uint_as_float(d2[4 * j + e]), y) : 0.0f;
+          const float x = fmaf(my_nz, __uint_as_float(d2[4 * j + e]), y);
+          d1[4 * j + e] = __float_as_uint(live ? x : 0.0f);
         }
       }
-      stg_f8(a.out32 + obase + h * 16, x);
-      stg_f8(a.out32 + obase + h * 16 + 8, x + 8);
+      float4 v[4];
+      epi_transpose16(stg, lane, d1, v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (oi4[i] < 0) continue;
+        const size_t o = (size_t)(oi4[i] & (int)(kLiveFlag - 1)) * a.ldo + col + c4 * 4;
+        *reinterpret_cast<float4*>(a.out32 + o) = v[i];
+      }
     }
     tc_fence_before();
   }
@@ -838,7 +845,7 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 9) tmem_alloc(smem_u32(tmem_slot), C);
-  if (a.prefetch_ahead > 0) {
+  if (a.prefetch_ahead > 0 && tid == 64) {
     // Pull the input rows of the tile that will take this CTA's place into L2 now: its loads then cost an
     // L2 hit instead of a DRAM round trip (the kernel streams, nothing is resident at chunk = 1024 items).
     const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + a.prefetch_ahead;
@@ -848,7 +855,7 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
       const int r_hi = min(a.out_lo + ptile * BM + BM + 3 * DIL - a.in_lo, a.in_rows);
       const char* p = reinterpret_cast<const char*>(a.x + ((size_t)pit * a.in_rows + r_lo) * C);
       const uint32_t bytes = (uint32_t)(r_hi - r_lo) * C * 4;  // rows are contiguous: one bulk prefetch covers the tile
-      if (tid == 32 && r_hi > r_lo) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+      if (r_hi > r_lo) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
     }
   }
   tc_fence_before();
@@ -863,17 +870,6 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
       for (int kb = 0; kb < KB; ++kb) tma_load_2d(smem_u32(sW + kb * C * 128), &tmW, smem_u32(&bars[0]), kb * BK, 0);
     }
   } else {
-    // ---- epilogue row metadata (threads 0..127 <-> tile rows)
-    if (tid < BM) {
-      int oi = -1;
-      const int orow = row0 + tid;
-      if (orow < a.out_rows) {
-        const int t_abs = a.out_lo + orow + it.shift0 * a.up;
-        oi = item * a.out_rows + orow;
-        if (t_abs < 0 || t_abs >= a.T0 * a.up) oi |= (int)kLiveFlag;
-      }
-      meta_out[tid] = oi;
-    }
     // ---- depthwise stage: unit = (channel pair, residue class / segment), 16 outputs, 22 loads
     constexpr int CP = C / 2;
     constexpr int U = (DIL == 1) ? 8 : 9;
@@ -919,53 +915,77 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
       umma_commit(smem_u32(&bars[1]));
     }
   } else if (warp < 8) {
-    // ---- epilogue: lane <-> tile row; warp w reads TMEM lanes 32*(w%4).., the two warps of a quarter
-    // split the columns; 64 contiguous bytes of the lane's own row per 16-column step (256-bit accesses)
+    // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., the two warps of a quarter split the columns.
+    // After the 16-column transpose lane l owns rows (l/4 + 8i), i = 0..3, columns 4*(l%4)..+3: its four
+    // rows are an arithmetic progression, so one base pointer + immediates address everything.
     const int q = warp & 3, half = warp >> 2;
-    constexpr int NH = C / 32;
-    const int trow = q * 32 + lane;
-    const int oi = meta_out[trow];
-    const bool has_out = oi >= 0, live = has_out && !(oi & (int)kLiveFlag);
-    const int col0 = half * (C / 2);
-    const float* rp = a.x + ((size_t)item * a.in_rows + (a.out_lo + row0 + trow - a.in_lo)) * C + col0;
-    const size_t obase = (size_t)(max(oi, 0) & (int)(kLiveFlag - 1)) * C + col0;
-    f8 res0, res1;
-    if (has_out) { res0 = ldg_f8(rp); res1 = ldg_f8(rp + 8); }
+    constexpr int NH = C / 32;  // 16-column half-chunks per warp
+    const int c4 = lane & 3, r8 = lane >> 2;
+    float* stg = sStg + warp * (32 * 16);
+    float* st_p = stg + lane * 16;
+    const int st_x = (lane >> 1) & 3;
+    const float* ld_p = stg + r8 * 16 + ((c4 ^ ((r8 >> 1) & 3)) << 2);
+    const int orow_b = row0 + q * 32 + r8;  // first of this lane's four rows (stride 8)
+    const int tabs_b = a.out_lo + orow_b + it.shift0 * a.up;
+    uint32_t vmask = 0, lmask = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (orow_b + 8 * i < a.out_rows) {
+        vmask |= 1u << i;
+        const int t = tabs_b + 8 * i;
+        if (t >= 0 && t < a.T0 * a.up) lmask |= 1u << i;
+      }
+    }
+    const int colb = half * (C / 2) + c4 * 4;
+    const size_t ob = ((size_t)item * a.out_rows + orow_b) * C + colb;
+    const float* rp = a.x + ((size_t)item * a.in_rows + (a.out_lo + orow_b - a.in_lo)) * C + colb;
+    float4 res[4];
+    auto load_res = [&](int h) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((vmask >> i) & 1u) res[i] = __ldg(reinterpret_cast<const float4*>(rp + i * 8 * C + h * 16));
+      }
+    };
+    load_res(0);
     mbar_wait(smem_u32(&bars[1]), 0);
     tc_fence_after();
-#pragma unroll 1
+#pragma unroll
     for (int h = 0; h < NH; ++h) {
       uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(col0 + h * 16), r);
-      if (!has_out) continue;
-      float x[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (C / 2) + h * 16), r);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.pw_b + col0 + h * 16 + 4 * j));
-        x[4 * j] = __uint_as_float(r[4 * j]) + b4.x; x[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
-        x[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z; x[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<float4*>(st_p + ((j ^ st_x) << 2)) =
+            make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                        __uint_as_float(r[4 * j + 3]));
+      __syncwarp();
+      float4 v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(ld_p + i * 128);
+      __syncwarp();
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.pw_b + colb + h * 16));
+      float4 al = make_float4(0.f, 0.f, 0.f, 0.f), iv = al;
+      if (a.sn_alpha) {
+        al = __ldg(reinterpret_cast<const float4*>(a.sn_alpha + colb + h * 16));
+        iv = __ldg(reinterpret_cast<const float4*>(a.sn_inv + colb + h * 16));
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { x[j] += res0.v[j]; x[8 + j] += res1.v[j]; }
-      if (h + 1 < NH) { res0 = ldg_f8(rp + (h + 1) * 16); res1 = ldg_f8(rp + (h + 1) * 16 + 8); }
-      if (!live) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = 0.0f;
-      }
-      if (a.out32) { stg_f8(a.out32 + obase + h * 16, x); stg_f8(a.out32 + obase + h * 16 + 8, x + 8); }
-      if (a.out16) {
-        if (a.sn_alpha) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 al = __ldg(reinterpret_cast<const float4*>(a.sn_alpha + col0 + h * 16 + 4 * j));
-            const float4 iv = __ldg(reinterpret_cast<const float4*>(a.sn_inv + col0 + h * 16 + 4 * j));
-            const float2 lo = snake2(make_float2(x[4 * j], x[4 * j + 1]), make_float2(al.x, al.y), make_float2(iv.x, iv.y));
-            const float2 hi = snake2(make_float2(x[4 * j + 2], x[4 * j + 3]), make_float2(al.z, al.w), make_float2(iv.z, iv.w));
-            x[4 * j] = lo.x; x[4 * j + 1] = lo.y; x[4 * j + 2] = hi.x; x[4 * j + 3] = hi.y;
+      for (int i = 0; i < 4; ++i) {
+        if (!((vmask >> i) & 1u)) continue;
+        float4 x = add4(add4(v[i], b4), res[i]);
+        if (!((lmask >> i) & 1u)) x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.out32) *reinterpret_cast<float4*>(a.out32 + ob + i * 8 * C + h * 16) = x;
+        if (a.out16) {
+          if (a.sn_alpha) {
+            const float2 lo = snake2(make_float2(x.x, x.y), make_float2(al.x, al.y), make_float2(iv.x, iv.y));
+            const float2 hi = snake2(make_float2(x.z, x.w), make_float2(al.z, al.w), make_float2(iv.z, iv.w));
+            x = make_float4(lo.x, lo.y, hi.x, hi.y);
           }
+          store_half4(a.out16 + ob + i * 8 * C + h * 16, x);
         }
-        stg_h16(a.out16 + obase + h * 16, x);
       }
+      if (h + 1 < NH) load_res(h + 1);
     }
     tc_fence_before();
   }
