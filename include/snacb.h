@@ -127,6 +127,9 @@ int snacb_load_weights(snacb_engine* e, const snacb_weights* w);
 size_t snacb_workspace_bytes(const snacb_engine* e);
 /* Number of kernels this engine has launched since creation (bench.py's gpu_launches claim). */
 int64_t snacb_launch_count(const snacb_engine* e);
+/* Number of CUDA-graph replays: small uniform ticks of snacb_decode_windows_host (<= 256 windows, env
+ * SNACB_GRAPHS=<max windows>, 0 = off) are captured once per shape and replayed as ONE launch. */
+int64_t snacb_graph_launch_count(const snacb_engine* e);
 
 /* ---- NS-1: integer de-interleave + validate ------------------------------------------------ */
 

@@ -72,6 +72,7 @@ SIGNATURES = {
     "snacb_load_weights": (_i32, [_vp, C.POINTER(Weights)]),
     "snacb_workspace_bytes": (_sz, [_vp]),
     "snacb_launch_count": (_i64, [_vp]),
+    "snacb_graph_launch_count": (_i64, [_vp]),
     "snacb_deinterleave": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "snacb_deinterleave_raw": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "snacb_decode_windows": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _i64, _u64, _vp, _vp, _vp, _vp]),

@@ -74,6 +74,13 @@ struct snacb_engine {
   cudaEvent_t items_ev = nullptr;
   int64_t launches = 0;
   int prefetch_ahead = 0;  // SM count when L2 prefetch-ahead is on (SNACB_PREFETCH env, default on)
+  // CUDA graphs of small host-API ticks (latency mode): key -> instantiated graph
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t gen = 0; int calls = 0; bool disabled = false; };
+  std::map<std::vector<long long>, GraphEntry> graphs;
+  cudaStream_t cap_stream = nullptr;
+  uint64_t gen = 1;       // bumped whenever a buffer a captured graph points into is re-allocated
+  int graph_max_win = 256;
+  int64_t graph_launches = 0;
   // chunk lanes: chunks of one call run concurrently on side streams (L2-resident working sets, no wave tails)
   std::vector<cudaStream_t> lane_streams;
   std::vector<cudaEvent_t> lane_done;
@@ -130,6 +137,7 @@ struct ProfScope {
 
 int ensure_ws(snacb_engine* e, size_t bytes, cudaStream_t st) {
   if (bytes <= e->ws_bytes) return SNACB_OK;
+  ++e->gen;
   if (e->ws) {
     CU(e, cudaStreamSynchronize(st));
     CU(e, cudaDeviceSynchronize());
@@ -198,6 +206,7 @@ size_t add_convt(HostPack& hp, const float* w, int Cin, int Cout, int s) {
 // ---------------------------------------------------------------------------------- pipeline
 struct NoiseCfg {
   int mode; const float* tensor; long long stride; uint64_t seed; const unsigned long long* d_keys;
+  const unsigned long long* d_seed;  // device-resident seed or nullptr
 };
 
 void tap(snacb_engine* e, int stage, const float* p, Rng r, int C, int n_items, bool first_chunk, cudaStream_t st) {
@@ -286,7 +295,7 @@ int run_group_f32(snacb_engine* e, const Plan& P, const Item* d_items, int n_tot
         a.epi = EPI_NOISE; a.A = Y; a.lda = B.Cout; a.a_r = B.ct; a.W = Wb.noise_w; a.ldw = B.Cout;
         a.K = B.Cout; a.N = B.Cout; a.m_r = B.ct; a.out = X; a.o_r = B.ct; a.ldo = B.Cout;
         a.R = Y; a.r_r = B.ct; a.ldr = B.Cout; a.up = B.up_out;
-        a.noise = NoiseSrc{nz.mode, nz.tensor, nz.stride, noise_off[b], (unsigned long long)nz.seed, nz.d_keys, b};
+        a.noise = NoiseSrc{nz.mode, nz.tensor, nz.stride, noise_off[b], (unsigned long long)nz.seed, nz.d_keys, b, nz.d_seed};
         gemm(a);
       } else {
         std::swap(X, Y);  // x + 0 * h == x
@@ -405,7 +414,7 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
         a.bias = Wb.ct_b; a.s = B.s; a.p = B.p; a.Cout = B.Cout; a.o_r = B.ct; a.ldo = B.Cout; a.up = B.up_out;
         if (fuse_cn) {
           a.out32 = X;
-          a.noise = NoiseSrc{nz.mode, nz.tensor, nz.stride, noise_off[b], (unsigned long long)nz.seed, nz.d_keys, b};
+          a.noise = NoiseSrc{nz.mode, nz.tensor, nz.stride, noise_off[b], (unsigned long long)nz.seed, nz.d_keys, b, nz.d_seed};
           if (ce == cudaSuccess) {
             const double M = (double)n * a.a_rows;
             ProfScope ps(e, KC_CONVT, 2.0 * M * a.N * a.K * 2.0 + 2.0 * M * B.s * B.Cout * B.Cout,
@@ -422,7 +431,7 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
         TcGemmArgs a{};
         a.epi = EPI_NOISE; a.A = Y16; a.K = B.Cout; a.a_rows = B.ct.n(); a.a_lo = B.ct.lo; a.W = Wb.noise16; a.N = B.Cout;
         a.out32 = X; a.o_r = B.ct; a.ldo = B.Cout; a.R = Y; a.r_r = B.ct; a.ldr = B.Cout; a.up = B.up_out;
-        a.noise = NoiseSrc{nz.mode, nz.tensor, nz.stride, noise_off[b], (unsigned long long)nz.seed, nz.d_keys, b};
+        a.noise = NoiseSrc{nz.mode, nz.tensor, nz.stride, noise_off[b], (unsigned long long)nz.seed, nz.d_keys, b, nz.d_seed};
         gemm(a);
       }
       tap(e, sid + 2, X, B.ct, B.Cout, n, first, st);
@@ -568,6 +577,8 @@ int snacb_create(snacb_engine** out, const snacb_config* cfg) {
   {
     const char* pf = getenv("SNACB_PREFETCH");
     e->prefetch_ahead = (pf && pf[0] == '0') ? 0 : prop.multiProcessorCount;
+    const char* gr = getenv("SNACB_GRAPHS");
+    if (gr) e->graph_max_win = atoi(gr);  // 0 disables the CUDA-graph path
   }
   *out = e;
   return SNACB_OK;
@@ -584,6 +595,8 @@ void snacb_destroy(snacb_engine* e) {
   if (e->pin) cudaFreeHost(e->pin);
   if (e->pin_items) cudaFreeHost(e->pin_items);
   if (e->items_ev) cudaEventDestroy(e->items_ev);
+  for (auto& kv : e->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   for (auto sidestream : e->lane_streams) cudaStreamDestroy(sidestream);
   for (auto ev : e->lane_done) cudaEventDestroy(ev);
   if (e->lane_fork) cudaEventDestroy(e->lane_fork);
@@ -597,6 +610,7 @@ const char* snacb_last_error(const snacb_engine* e) { return e ? e->err.c_str() 
 size_t snacb_workspace_bytes(const snacb_engine* e) { return e ? e->ws_bytes + e->dstage_bytes : 0; }
 
 int64_t snacb_launch_count(const snacb_engine* e) { return e ? e->launches : 0; }
+int64_t snacb_graph_launch_count(const snacb_engine* e) { return e ? e->graph_launches : 0; }
 
 int snacb_load_weights(snacb_engine* e, const snacb_weights* w) {
   if (!e || !w) return fail(e, SNACB_EINVAL, "snacb_load_weights: null argument");
@@ -681,6 +695,7 @@ int snacb_load_weights(snacb_engine* e, const snacb_weights* w) {
     CU(e, cudaDeviceSynchronize());
   }
   e->loaded = true;
+  ++e->gen;
   return SNACB_OK;
 }
 
@@ -731,10 +746,12 @@ int snacb_deinterleave_raw(snacb_engine* e, const int32_t* d_raw, int32_t tokens
                              d_status, stream);
 }
 
-int snacb_decode_windows(snacb_engine* e, const int32_t* d_tokens, int32_t tokens_stride, const int32_t* h_ntok,
-                         int32_t ntok_uniform, int32_t n_win, int32_t noise_mode, const float* d_noise,
-                         int64_t noise_stride, uint64_t seed, const uint64_t* h_keys, int16_t* d_pcm,
-                         int32_t* d_status, void* stream) {
+// d_keys_in / d_seed_in: keys and seed already on the device (CUDA-graph path); else h_keys / seed are used.
+static int decode_windows_core(snacb_engine* e, const int32_t* d_tokens, int32_t tokens_stride, const int32_t* h_ntok,
+                               int32_t ntok_uniform, int32_t n_win, int32_t noise_mode, const float* d_noise,
+                               int64_t noise_stride, uint64_t seed, const uint64_t* h_keys,
+                               const unsigned long long* d_keys_in, const unsigned long long* d_seed_in, int16_t* d_pcm,
+                               int32_t* d_status, void* stream) {
   if (!e) return SNACB_EINVAL;
   if (!e->loaded) return fail(e, SNACB_ESTATE, "snacb_decode_windows: weights not loaded");
   if (n_win < 0 || !d_tokens || !d_pcm || !d_status) return fail(e, SNACB_EINVAL, "snacb_decode_windows: bad argument");
@@ -787,8 +804,8 @@ int snacb_decode_windows(snacb_engine* e, const int32_t* d_tokens, int32_t token
   const size_t ws_avail = e->ws_bytes - pad256(bp.off);
 
   if (h_ntok) CU(e, cudaMemcpyAsync(d_ntok, h_ntok, (size_t)n_win * 4, cudaMemcpyHostToDevice, st));
-  const unsigned long long* keys = nullptr;
-  if (noise_mode == SNACB_NOISE_PHILOX && h_keys) {
+  const unsigned long long* keys = d_keys_in;
+  if (noise_mode == SNACB_NOISE_PHILOX && h_keys && !d_keys_in) {
     CU(e, cudaMemcpyAsync(d_keys, h_keys, (size_t)n_win * 8, cudaMemcpyHostToDevice, st));
     keys = d_keys;
   }
@@ -798,7 +815,7 @@ int snacb_decode_windows(snacb_engine* e, const int32_t* d_tokens, int32_t token
                         d_status, st, &e->launches);
   }
   CU(e, cudaMemsetAsync(d_pcm, 0, (size_t)n_win * 2048 * sizeof(int16_t), st));
-  NoiseCfg nz{noise_mode, d_noise, (long long)noise_stride, seed, keys};
+  NoiseCfg nz{noise_mode, d_noise, (long long)noise_stride, seed, keys, d_seed_in};
 
   if (!h_ntok) {
     if (maxF >= 2 && ntok_uniform >= 14) {
@@ -829,6 +846,14 @@ int snacb_decode_windows(snacb_engine* e, const int32_t* d_tokens, int32_t token
   return check_launch(e, "decode_windows");
 }
 
+int snacb_decode_windows(snacb_engine* e, const int32_t* d_tokens, int32_t tokens_stride, const int32_t* h_ntok,
+                         int32_t ntok_uniform, int32_t n_win, int32_t noise_mode, const float* d_noise,
+                         int64_t noise_stride, uint64_t seed, const uint64_t* h_keys, int16_t* d_pcm,
+                         int32_t* d_status, void* stream) {
+  return decode_windows_core(e, d_tokens, tokens_stride, h_ntok, ntok_uniform, n_win, noise_mode, d_noise, noise_stride, seed,
+                             h_keys, nullptr, nullptr, d_pcm, d_status, stream);
+}
+
 static bool is_pinned(const void* p) {
   cudaPointerAttributes a{};
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -844,39 +869,94 @@ int snacb_decode_windows_host(snacb_engine* e, const int32_t* h_tokens, int32_t 
   if (n_win == 0) return SNACB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   CU(e, cudaSetDevice(e->device));
-  const size_t tok_b = pad256((size_t)n_win * tokens_stride * 4);
+  const size_t tok_n = (size_t)n_win * tokens_stride * 4;
+  const size_t tok_b = pad256(tok_n);
   const size_t pcm_b = pad256((size_t)n_win * 4096);
   const size_t st_b = pad256((size_t)n_win * 4);
   const size_t nz_b = (noise_mode == SNACB_NOISE_TENSOR && h_noise) ? pad256((size_t)n_win * noise_stride * 4) : 0;
-  const size_t total = tok_b + pcm_b + st_b + nz_b;
+  const size_t key_b = pad256((size_t)n_win * 8), seed_b = 256;
+  const size_t total = tok_b + pcm_b + st_b + nz_b + key_b + seed_b;
   if (total > e->pin_bytes) {
     CU(e, cudaStreamSynchronize(st));
     if (e->pin) CU(e, cudaFreeHost(e->pin));
     e->pin_bytes = total + total / 2;
     CU(e, cudaMallocHost((void**)&e->pin, e->pin_bytes));
+    ++e->gen;
   }
   // device staging lives in its own allocation (the workspace may be re-allocated by the decode)
-  static_assert(sizeof(int32_t) == 4, "");
   if (total > e->dstage_bytes) {
     CU(e, cudaDeviceSynchronize());
     if (e->dstage) CU(e, cudaFree(e->dstage));
     e->dstage_bytes = total + total / 2;
     CU(e, cudaMalloc((void**)&e->dstage, e->dstage_bytes));
+    ++e->gen;
   }
   char* hp = e->pin; char* dp = e->dstage;
-  const bool tok_pinned = is_pinned(h_tokens), pcm_pinned = is_pinned(h_pcm);
   int32_t* d_tok = reinterpret_cast<int32_t*>(dp);
   int16_t* d_pcm = reinterpret_cast<int16_t*>(dp + tok_b);
   int32_t* d_st = reinterpret_cast<int32_t*>(dp + tok_b + pcm_b);
   float* d_nz = nz_b ? reinterpret_cast<float*>(dp + tok_b + pcm_b + st_b) : nullptr;
+  const size_t key_off = tok_b + pcm_b + st_b + nz_b, seed_off = key_off + key_b;
+
+  // ---- latency mode: small uniform ticks replay a captured CUDA graph (H2D + every kernel + D2H in one launch)
+  const bool graph_ok = e->graph_max_win > 0 && n_win <= e->graph_max_win && !h_ntok && noise_mode != SNACB_NOISE_TENSOR &&
+                        !e->prof.on && e->tap_stage < 0 && e->loaded && ntok_uniform >= 0 && ntok_uniform <= tokens_stride;
+  if (graph_ok) {
+    const std::vector<long long> key{n_win, tokens_stride, ntok_uniform, noise_mode, h_keys ? 1 : 0};
+    snacb_engine::GraphEntry& ge = e->graphs[key];
+    if (ge.exec && ge.gen != e->gen) { cudaGraphExecDestroy(ge.exec); ge.exec = nullptr; ge.calls = 0; }
+    if (!ge.disabled && ge.calls >= 1) {
+      memcpy(hp, h_tokens, tok_n);
+      if (h_keys) memcpy(hp + key_off, h_keys, (size_t)n_win * 8);
+      memcpy(hp + seed_off, &seed, 8);
+      if (!ge.exec) {
+        if (!e->cap_stream) CU(e, cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+        cudaStream_t cs = e->cap_stream;
+        const uint64_t gen0 = e->gen;
+        cudaGraph_t graph = nullptr;
+        int rc = SNACB_OK;
+        if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); rc = SNACB_ECUDA; }
+        if (rc == SNACB_OK) {
+          cudaMemcpyAsync(d_tok, hp, tok_n, cudaMemcpyHostToDevice, cs);
+          if (h_keys) cudaMemcpyAsync(dp + key_off, hp + key_off, (size_t)n_win * 8, cudaMemcpyHostToDevice, cs);
+          cudaMemcpyAsync(dp + seed_off, hp + seed_off, 8, cudaMemcpyHostToDevice, cs);
+          rc = decode_windows_core(e, d_tok, tokens_stride, nullptr, ntok_uniform, n_win, noise_mode, nullptr, 0, seed, nullptr,
+                                   h_keys ? reinterpret_cast<const unsigned long long*>(dp + key_off) : nullptr,
+                                   reinterpret_cast<const unsigned long long*>(dp + seed_off), d_pcm, d_st, cs);
+          cudaMemcpyAsync(hp + tok_b, d_pcm, (size_t)n_win * 4096, cudaMemcpyDeviceToHost, cs);
+          cudaMemcpyAsync(hp + tok_b + pcm_b, d_st, (size_t)n_win * 4, cudaMemcpyDeviceToHost, cs);
+          const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+          if (ce != cudaSuccess || !graph) { cudaGetLastError(); rc = rc ? rc : SNACB_ECUDA; }
+        }
+        if (rc == SNACB_OK && e->gen == gen0 && cudaGraphInstantiate(&ge.exec, graph, 0) == cudaSuccess) {
+          ge.gen = e->gen;
+        } else {
+          cudaGetLastError();
+          ge.exec = nullptr; ge.disabled = true;  // this shape falls back to the plain path for good
+        }
+        if (graph) cudaGraphDestroy(graph);
+      }
+      if (ge.exec) {
+        ++ge.calls;
+        CU(e, cudaGraphLaunch(ge.exec, st));
+        ++e->graph_launches;
+        CU(e, cudaStreamSynchronize(st));
+        memcpy(h_pcm, hp + tok_b, (size_t)n_win * 4096);
+        memcpy(h_status, hp + tok_b + pcm_b, (size_t)n_win * 4);
+        return SNACB_OK;
+      }
+    }
+    ++ge.calls;  // first call of a shape runs the plain path (sizes the workspace, sets kernel attributes)
+  }
+
+  const bool tok_pinned = is_pinned(h_tokens), pcm_pinned = is_pinned(h_pcm);
   const void* src_tok = h_tokens;
-  if (!tok_pinned) { memcpy(hp, h_tokens, (size_t)n_win * tokens_stride * 4); src_tok = hp; }
-  CU(e, cudaMemcpyAsync(d_tok, src_tok, (size_t)n_win * tokens_stride * 4, cudaMemcpyHostToDevice, st));
+  if (!tok_pinned) { memcpy(hp, h_tokens, tok_n); src_tok = hp; }
+  CU(e, cudaMemcpyAsync(d_tok, src_tok, tok_n, cudaMemcpyHostToDevice, st));
   if (nz_b) {
     memcpy(hp + tok_b + pcm_b + st_b, h_noise, (size_t)n_win * noise_stride * 4);
     CU(e, cudaMemcpyAsync(d_nz, hp + tok_b + pcm_b + st_b, (size_t)n_win * noise_stride * 4, cudaMemcpyHostToDevice, st));
   }
-  // NOTE: snacb_decode_windows uses e->dstage for nothing (ntok goes to the workspace), so the staging is stable.
   int rc = snacb_decode_windows(e, d_tok, tokens_stride, h_ntok, ntok_uniform, n_win, noise_mode, d_nz, noise_stride, seed,
                                 h_keys, d_pcm, d_st, stream);
   if (rc) return rc;
@@ -900,7 +980,7 @@ int snacb_decode_codes(snacb_engine* e, const int32_t* d_c0, const int32_t* d_c1
   if (B == 0) return SNACB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   CU(e, cudaSetDevice(e->device));
-  NoiseCfg nz{noise_mode, d_noise, (long long)kNoisePerFrame * F, seed, nullptr};
+  NoiseCfg nz{noise_mode, d_noise, (long long)kNoisePerFrame * F, seed, nullptr, nullptr};
   const int kTileFrames = 8;
   if (F <= 2 * kTileFrames) {
     Plan P = plan_for(e, 4 * F, Rng{0, 2048 * F}, true);

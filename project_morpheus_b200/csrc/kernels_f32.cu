@@ -309,29 +309,45 @@ void launch_gemm_f32(const GroupCtx& g, const GemmArgs& a) {
 // (speechpipe.py:127: no rounding, no clip).  64 samples per CTA, 4 channel quarters per sample.
 template <bool FAST>
 __global__ void __launch_bounds__(256) k_tail(const Item* items, int base, int out_len, int T0, TailArgs a) {
-  __shared__ float xs[70][65];
-  __shared__ float ws[7][64];
+  __shared__ __align__(16) float xs[70][68];  // row pitch 68 floats: 16-byte aligned rows, conflict-free float4 reads
+  __shared__ __align__(16) float ws[7][64];
   __shared__ float part[4][64];
   const int i = blockIdx.y, tid = threadIdx.x;
   const ItemRef it = get_item(items, base, i, out_len);
   const int t0 = a.out_r.lo + blockIdx.x * 64;  // first output sample (relative) of this CTA
   const int x_rows = a.x_r.n();
   const float* x = a.x + (size_t)i * x_rows * 64;
-  for (int e = tid; e < 70 * 64; e += 256) {
-    const int r = e >> 6, c = e & 63;
+  for (int e = tid; e < 70 * 16; e += 256) {  // 16 float4 per row
+    const int r = e >> 4, c = (e & 15) * 4;
     const int row = t0 - 3 + r - a.x_r.lo;
-    float v = (row >= 0 && row < x_rows) ? x[(size_t)row * 64 + c] : 0.0f;
-    if (FAST) { const float sn = __sinf(a.alpha[c] * v); xs[r][c] = fmaf(a.inv[c], sn * sn, v); }
-    else xs[r][c] = snake_exact(v, a.alpha[c], a.inv[c]);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row >= 0 && row < x_rows) v = *reinterpret_cast<const float4*>(x + (size_t)row * 64 + c);
+    const float4 al = *reinterpret_cast<const float4*>(a.alpha + c), iv = *reinterpret_cast<const float4*>(a.inv + c);
+    float4 o;
+    if (FAST) {
+      float sn;
+      sn = __sinf(al.x * v.x); o.x = fmaf(iv.x, sn * sn, v.x);
+      sn = __sinf(al.y * v.y); o.y = fmaf(iv.y, sn * sn, v.y);
+      sn = __sinf(al.z * v.z); o.z = fmaf(iv.z, sn * sn, v.z);
+      sn = __sinf(al.w * v.w); o.w = fmaf(iv.w, sn * sn, v.w);
+    } else {
+      o.x = snake_exact(v.x, al.x, iv.x); o.y = snake_exact(v.y, al.y, iv.y);
+      o.z = snake_exact(v.z, al.z, iv.z); o.w = snake_exact(v.w, al.w, iv.w);
+    }
+    *reinterpret_cast<float4*>(&xs[r][c]) = o;
   }
   for (int e = tid; e < 7 * 64; e += 256) ws[e >> 6][e & 63] = a.w7[e];
   __syncthreads();
-  const int sx = tid & 63, qc = tid >> 6;
+  const int sx = tid & 63, qc = tid >> 6;  // output sample, channel quarter
   float acc = 0.0f;
 #pragma unroll
   for (int k = 0; k < 7; ++k)
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc = fmaf(ws[k][qc * 16 + c], xs[sx + k][qc * 16 + c], acc);
+    for (int c = 0; c < 16; c += 4) {
+      const float4 w4 = *reinterpret_cast<const float4*>(&ws[k][qc * 16 + c]);   // warp-uniform: broadcast
+      const float4 x4 = *reinterpret_cast<const float4*>(&xs[sx + k][qc * 16 + c]);
+      acc = fmaf(w4.x, x4.x, acc); acc = fmaf(w4.y, x4.y, acc); acc = fmaf(w4.z, x4.z, acc); acc = fmaf(w4.w, x4.w, acc);
+    }
   part[qc][sx] = acc;
   __syncthreads();
   if (qc != 0) return;

@@ -146,13 +146,14 @@ struct NoiseSrc {
   unsigned long long seed;
   const unsigned long long* keys;  // per code_row stream key (nullptr -> code_row)
   int block;
+  const unsigned long long* seed_ptr;  // device-resident seed (CUDA-graph replays); nullptr -> `seed`
 };
 
 __device__ __forceinline__ float noise_at(const NoiseSrc& ns, int code_row, int t_abs) {
   if (ns.mode == 1) return ns.tensor[(long long)code_row * ns.stride + ns.off + t_abs];
   if (ns.mode == 2) {
     unsigned long long key = ns.keys ? ns.keys[code_row] : (unsigned long long)code_row;
-    return philox_normal(ns.seed, key, (uint32_t)ns.block, (uint32_t)t_abs);
+    return philox_normal(ns.seed_ptr ? *ns.seed_ptr : ns.seed, key, (uint32_t)ns.block, (uint32_t)t_abs);
   }
   return 0.0f;
 }

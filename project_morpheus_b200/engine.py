@@ -97,6 +97,10 @@ class SnacEngine:
         return int(self._lib.snacb_launch_count(self._h))
 
     @property
+    def graph_launch_count(self) -> int:
+        return int(self._lib.snacb_graph_launch_count(self._h))
+
+    @property
     def workspace_bytes(self) -> int:
         return int(self._lib.snacb_workspace_bytes(self._h))
 

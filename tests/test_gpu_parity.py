@@ -417,3 +417,33 @@ def test_long_read_full_size_properties(engines):
     assert np.abs(head - full[:, : 2048 * 8]).max() <= 2e-3
     tail = sub(F - 12, F)[:, -2048 * 8:]
     assert np.abs(tail - full[:, -2048 * 8:]).max() <= 2e-3
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_cuda_graph_latency_path_is_bit_identical(engines, precision):
+    """Small uniform ticks through the host API are captured into a CUDA graph on their second call and
+    replayed afterwards; bytes must equal the plain launch path, and seed / keys / tokens must stay live
+    inputs of the replay (they are read from device memory, not baked into the graph)."""
+    eng = engines(precision)
+    n = 13 if precision == "fp16" else 11  # shapes no other test uses: the first call must be the plain path
+    tok = windows_tokens(n, 4, 7000)
+    tok2 = windows_tokens(n, 4, 7100)
+    keys = list(range(3, 3 + n))
+    g0 = eng.graph_launch_count
+    plain, st0 = eng.decode_windows(tok, noise="philox", seed=11, keys=keys); plain = plain.copy()      # call 1: plain
+    cap, _ = eng.decode_windows(tok, noise="philox", seed=11, keys=keys); cap = cap.copy()              # call 2: capture + launch
+    rep, _ = eng.decode_windows(tok, noise="philox", seed=11, keys=keys); rep = rep.copy()              # call 3: replay
+    assert eng.graph_launch_count == g0 + 2
+    assert (st0 == _lib.WIN_OK).all() and np.array_equal(plain, cap) and np.array_equal(plain, rep)
+    other_seed, _ = eng.decode_windows(tok, noise="philox", seed=12, keys=keys); other_seed = other_seed.copy()
+    other_keys, _ = eng.decode_windows(tok, noise="philox", seed=11, keys=[9] * n); other_keys = other_keys.copy()
+    other_tok, _ = eng.decode_windows(tok2, noise="philox", seed=11, keys=keys); other_tok = other_tok.copy()
+    assert not np.array_equal(plain, other_seed) and not np.array_equal(plain, other_keys) and not np.array_equal(plain, other_tok)
+    # the same three variations through the device-buffer API (never graphed) give the same bytes
+    for t, s, k, want in ((tok, 12, keys, other_seed), (tok, 11, [9] * n, other_keys), (tok2, 11, keys, other_tok)):
+        pcm, _ = eng.decode_windows_device(torch.from_numpy(t).cuda(), noise="philox", seed=s, keys=k)
+        assert np.array_equal(pcm.cpu().numpy(), want)
+    # a poisoned window inside a graphed shape still reports its status
+    bad = tok.copy(); bad[2, 5] = 5000
+    pcm, st = eng.decode_windows(bad, noise="philox", seed=11, keys=keys)
+    assert st.tolist() == [0, 0, _lib.WIN_REJECTED] + [0] * (n - 3) and not pcm[2].any() and np.array_equal(pcm[0], plain[0])
