@@ -18,6 +18,7 @@
 #include <cuda_fp16.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -31,6 +32,7 @@ constexpr int BM = 128;  // rows per tile = TMEM lanes
 constexpr int BK = 64;   // fp16 per k-block = one 128-byte swizzle span
 constexpr int kTcThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr uint32_t kLiveFlag = 0x40000000u;
+const bool g_no_ws = [] { const char* v = getenv("SNACB_NO_WS"); return v && v[0] == '1'; }();
 
 // ------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -409,6 +411,205 @@ __global__ void __launch_bounds__(kTcThreads, 3) k_gemm_tc(const __grid_constant
   }
 }
 
+// ============================================================================ weight-stationary 1x1 GEMM
+// Persistent variant of k_gemm_tc for the wide 1x1 layers of decoder blocks 0 and 1 (C = 512 / 256: the
+// ResidualUnit and NoiseBlock GEMMs).  With 128 x 128 tiles and K = C those GEMMs are bound by the L2 ->
+// shared-memory traffic of re-loading the weight tile for every M tile (64 FLOP/B).  Here a CTA owns one
+// 128-wide slice of output channels, keeps that slice of W ([128][K] fp16, K <= 512: <= 128 KB) in shared
+// memory for its whole life and streams M tiles through a 4-stage TMA ring; two TMEM accumulators let the
+// epilogue of tile i overlap the MMAs of tile i+1.  One CTA per SM, gridDim.x = (#N slices) * P.
+constexpr int kWsStages = 4;
+struct WsSmem {
+  static constexpr int kABytes = kWsStages * BM * BK * 2;       // 64 KB ring
+  static constexpr int kStgBytes = 8 * 32 * 16 * 4;             // epilogue transposes
+  static constexpr int kMetaBytes = 2 * 3 * BM * 4 + 256;       // two row-metadata buffers + barriers
+  static constexpr int bytes(int K) { return K * 128 * 2 + kABytes + kStgBytes + kMetaBytes + 1024; }
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(kTcThreads, 1) k_gemm_ws(const __grid_constant__ CUtensorMap tmA,
+                                                         const __grid_constant__ CUtensorMap tmW, const TcDev a) {
+  constexpr int BN = 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_align1024(smem_raw);
+  const int KB = a.K / BK;
+  uint8_t* sW = smem;                                 // [KB][128 rows][128 B]
+  uint8_t* sA = sW + KB * (BN * 128);                 // [kWsStages][128 rows][128 B]
+  float* sStg = reinterpret_cast<float*>(sA + WsSmem::kABytes);
+  int* meta = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(sStg) + WsSmem::kStgBytes);  // [2][3][BM]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(meta + 2 * 3 * BM);
+  // bars: [0] w_full, [1..4] a_full, [5..8] a_empty, [9..10] t_full, [11..12] t_empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_slices = a.ldo / BN;  // output width == N for these layers
+  const int slice = blockIdx.x % n_slices, p = blockIdx.x / n_slices, P = gridDim.x / n_slices;
+  const int n0 = slice * BN;
+  const long long Mtot = (long long)a.n_items * a.a_rows;
+  const int m_tiles = (int)((Mtot + BM - 1) / BM);
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    for (int i = 0; i < kWsStages; ++i) { mbar_init(smem_u32(&bars[1 + i]), 1); mbar_init(smem_u32(&bars[5 + i]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars[9 + i]), 1); mbar_init(smem_u32(&bars[11 + i]), 256); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(smem_u32(&bars[0]), (uint32_t)(KB * BN * 128));
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(smem_u32(sW + kb * (BN * 128)), &tmW, smem_u32(&bars[0]), kb * BK, n0);
+      int it = 0;  // running k-block counter across tiles
+      for (int mt = p; mt < m_tiles; mt += P) {
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int st = it % kWsStages;
+          mbar_wait(smem_u32(&bars[5 + st]), ((it / kWsStages) & 1) ^ 1);
+          mbar_arrive_expect_tx(smem_u32(&bars[1 + st]), BM * BK * 2);
+          tma_load_2d(smem_u32(sA + st * (BM * 128)), &tmA, smem_u32(&bars[1 + st]), kb * BK, mt * BM);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BN);
+      mbar_wait(smem_u32(&bars[0]), 0);
+      int it = 0, ti = 0;
+      for (int mt = p; mt < m_tiles; mt += P, ++ti) {
+        const int buf = ti & 1;
+        mbar_wait(smem_u32(&bars[11 + buf]), ((ti >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+        tc_fence_after();
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int st = it % kWsStages;
+          mbar_wait(smem_u32(&bars[1 + st]), (it / kWsStages) & 1);
+          tc_fence_after();
+          const uint64_t da = umma_desc_k_sw128(smem_u32(sA + st * (BM * 128)));
+          const uint64_t db = umma_desc_k_sw128(smem_u32(sW + kb * (BN * 128)));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_base + buf * BN, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          umma_commit(smem_u32(&bars[5 + st]));
+        }
+        umma_commit(smem_u32(&bars[9 + buf]));
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..9)
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int c4 = lane & 3, r8 = lane >> 2;
+    float* stg = sStg + (warp - 2) * (32 * 16);
+    float* st_p = stg + lane * 16;
+    const int st_x = (lane >> 1) & 3;
+    const float* ld_p = stg + r8 * 16 + ((c4 ^ ((r8 >> 1) & 3)) << 2);
+    constexpr int NH = BN / 32;
+    const int ocol0 = n0 + half * (BN / 2) + c4 * 4;
+    int ti = 0;
+    for (int mt = p; mt < m_tiles; mt += P, ++ti) {
+      const int buf = ti & 1;
+      int* m_out = meta + buf * 3 * BM;
+      int* m_res = m_out + BM;
+      float* m_nz = reinterpret_cast<float*>(m_res + BM);
+      if (half == 0) {  // row metadata of this tile, one row per thread of the first four epilogue warps
+        const int trow = q * 32 + lane;
+        const long long gm = (long long)mt * BM + trow;
+        int oi = -1, ri = -1;
+        float nz = 0.0f;
+        if (gm < Mtot) {
+          const int item = (int)(gm / a.a_rows), j = (int)(gm - (long long)item * a.a_rows);
+          const ItemRef itr = get_item(a.items, a.base, item, a.out_len);
+          const int t_rel = a.a_lo + j;
+          const int orow = t_rel - a.o_lo;
+          if (orow >= 0 && orow < a.o_rows) {
+            const int t_abs = t_rel + itr.shift0 * a.up;
+            const bool live = (t_abs >= 0) && (t_abs < a.T0 * a.up);
+            oi = item * a.o_rows + orow;
+            ri = item * a.r_rows + (t_rel - a.r_lo);
+            if (EPI == EPI_NOISE && live) nz = noise_at(a.noise, itr.code_row, t_abs);
+            if (!live) oi |= (int)kLiveFlag;
+          }
+        }
+        m_out[trow] = oi; m_res[trow] = ri; m_nz[trow] = nz;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      int oi4[4], ri4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { oi4[i] = m_out[q * 32 + r8 + 8 * i]; ri4[i] = m_res[q * 32 + r8 + 8 * i]; }
+      float4 res[4];
+      auto load_res = [&](int h) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (oi4[i] >= 0) res[i] = __ldg(reinterpret_cast<const float4*>(a.R + (size_t)ri4[i] * a.ldr + ocol0 + h * 16));
+        }
+      };
+      load_res(0);
+      mbar_wait(smem_u32(&bars[9 + buf]), (ti >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * (BN / 2) + h * 16), r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(st_p + ((j ^ st_x) << 2)) =
+              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                          __uint_as_float(r[4 * j + 3]));
+        __syncwarp();
+        float4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(ld_p + i * 128);
+        __syncwarp();
+        const int ocol = ocol0 + h * 16;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), al = b4, iv = b4;
+        if (a.bias) b4 = __ldg(reinterpret_cast<const float4*>(a.bias + ocol));
+        if (a.sn_alpha) { al = __ldg(reinterpret_cast<const float4*>(a.sn_alpha + ocol)); iv = __ldg(reinterpret_cast<const float4*>(a.sn_inv + ocol)); }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int oi = oi4[i];
+          if (oi < 0) continue;
+          const bool live = !(oi & (int)kLiveFlag);
+          oi &= (int)(kLiveFlag - 1);
+          float4 x = add4(v[i], b4);
+          if (EPI == EPI_NOISE) {
+            const float nz = m_nz[q * 32 + r8 + 8 * i];
+            const float2 n2 = make_float2(nz, nz);
+            const float2 lo = __ffma2_rn(n2, make_float2(x.x, x.y), make_float2(res[i].x, res[i].y));
+            const float2 hi = __ffma2_rn(n2, make_float2(x.z, x.w), make_float2(res[i].z, res[i].w));
+            x = make_float4(lo.x, lo.y, hi.x, hi.y);
+          } else {
+            x = add4(x, res[i]);
+          }
+          if (!live) x = make_float4(0.f, 0.f, 0.f, 0.f);
+          const size_t o = (size_t)oi * a.ldo + ocol;
+          if (a.out32) *reinterpret_cast<float4*>(a.out32 + o) = x;
+          if (a.out16) {
+            if (a.sn_alpha) {
+              const float2 lo = snake2(make_float2(x.x, x.y), make_float2(al.x, al.y), make_float2(iv.x, iv.y));
+              const float2 hi = snake2(make_float2(x.z, x.w), make_float2(al.z, al.w), make_float2(iv.z, iv.w));
+              x = make_float4(lo.x, lo.y, hi.x, hi.y);
+            }
+            store_half4(a.out16 + o, x);
+          }
+        }
+        if (h + 1 < NH) load_res(h + 1);
+      }
+      tc_fence_before();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[11 + buf])) : "memory");  // accumulator free
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
 // ============================================================================ ConvT + NoiseBlock fused
 // x = y + n[t] * (W_n y),  y = ConvTranspose1d(Snake(x_in)) + b, for decoder blocks whose output width
 // Cout fits one tile (blocks 2 and 3: Cout = 128 / 64).  The polyphase transposed conv accumulates a
@@ -670,6 +871,28 @@ cudaError_t launch_tc_bn(int epi, const CUtensorMap& ma, const CUtensorMap& mw, 
   }
 }
 
+template <int EPI>
+cudaError_t launch_ws_t(const CUtensorMap& ma, const CUtensorMap& mw, const TcDev& d, int grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_ws<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsSmem::bytes(512));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  k_gemm_ws<EPI><<<grid, kTcThreads, WsSmem::bytes(d.K), st>>>(ma, mw, d);
+  return cudaGetLastError();
+}
+
+int sm_count() {
+  static int n = [] {
+    int dev = 0, v = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v;
+  }();
+  return n;
+}
+
 template <int BN>
 cudaError_t launch_cn_t(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mn, const TcDev& d, dim3 grid,
                         cudaStream_t st) {
@@ -721,6 +944,9 @@ cudaError_t launch_gemm_tc(const GroupCtx& g, const TcGemmArgs& a) {
   if (a.K % BK || a.N % bn || (a.epi == EPI_CONVT && a.Cout % bn)) return cudaErrorInvalidValue;
   CUtensorMap ma, mw;
   if (!get_tmap(a.A, Mtot, a.K, BM, &ma) || !get_tmap(a.W, a.N, nseg * a.K, bn, &mw)) return cudaErrorNotSupported;
+  // wide square 1x1 layers (blocks 0 / 1): persistent weight-stationary kernel
+  const bool ws = !g_no_ws && (a.epi == EPI_RESID || a.epi == EPI_NOISE) && a.N == a.ldo && a.N == a.K && (a.K == 256 || a.K == 512) &&
+                  Mtot >= 4 * BM * (long long)(sm_count() / (a.N / 128));
   TcDev d{};
   d.items = g.items; d.base = g.base; d.out_len = g.out_len; d.T0 = g.T0; d.n_items = g.n_items;
   d.stages = std::min((a.K / BK) * nseg, bn == 128 ? TcSmem<128>::kMaxStages : TcSmem<64>::kMaxStages);
@@ -728,6 +954,13 @@ cudaError_t launch_gemm_tc(const GroupCtx& g, const TcGemmArgs& a) {
   d.bias = a.bias; d.out32 = a.out32; d.out16 = a.out16; d.o_lo = a.o_r.lo; d.o_rows = a.o_r.n(); d.ldo = a.ldo;
   d.sn_alpha = a.sn_alpha; d.sn_inv = a.sn_inv; d.R = a.R; d.r_lo = a.r_r.lo; d.r_rows = a.r_r.n(); d.ldr = a.ldr;
   d.noise = a.noise; d.up = a.up;
+  if (ws) {
+    const int n_slices = a.N / 128, P = std::max(1, sm_count() / n_slices);
+    cudaError_t e = (a.epi == EPI_RESID) ? launch_ws_t<EPI_RESID>(ma, mw, d, n_slices * P, g.stream)
+                                         : launch_ws_t<EPI_NOISE>(ma, mw, d, n_slices * P, g.stream);
+    ++*g.launches;
+    return e;
+  }
   dim3 grid((unsigned)((Mtot + BM - 1) / BM), (unsigned)(a.N / bn));
   cudaError_t e = (bn == 128) ? launch_tc_bn<128>(a.epi, ma, mw, d, grid, g.stream) : launch_tc_bn<64>(a.epi, ma, mw, d, grid, g.stream);
   ++*g.launches;
