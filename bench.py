@@ -208,7 +208,7 @@ def run_ours(args) -> None:
 
     S, F, K, W = args.streams, args.frames, args.steps, max(3, args.warmup)
     eng = SnacEngine(weights.random_state_dict(0, "w1"), device=local, precision=args.precision, trim=not args.no_trim,
-                     chunk_items=args.chunk, lanes=args.lanes)
+                     chunk_items=args.chunk, lanes=args.lanes, persistent_ru=args.persistent_ru)
     tok_host = synth_tokens(rank * S, S, F)                      # this rank's stream partition
     keys = np.arange(rank * S, rank * S + S, dtype=np.uint64)    # Philox stream keys
     tok_dev = torch.from_numpy(tok_host).to(dev)
@@ -389,6 +389,7 @@ def main() -> None:
     ap.add_argument("--precision", choices=["fp16", "fp32"], default="fp16")
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--lanes", type=int, default=1)
+    ap.add_argument("--persistent-ru", action="store_true")
     ap.add_argument("--no-trim", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline leg")

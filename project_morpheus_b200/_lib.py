@@ -14,6 +14,8 @@ WIN_OK, WIN_REJECTED, WIN_CODE4096, WIN_EMPTY = 0, 1, 2, 3
 NOISE_OFF, NOISE_TENSOR, NOISE_PHILOX = 0, 1, 2
 PREC_FP32, PREC_FP16 = 0, 1
 FLAG_NO_RU_FUSION = 1
+FLAG_NO_CONVT_NOISE_FUSION = 2
+FLAG_PERSISTENT_RU = 4
 NOISE_PER_FRAME = 3360
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsnacb.so")

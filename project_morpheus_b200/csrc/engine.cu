@@ -441,12 +441,13 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
       Rng cur = B.ct;
       for (int r = 0; r < 3 && ce == cudaSuccess; ++r) {
         const RuDev& R = Wb.ru[r];
-        if (ru_tc_supported(B.Cout) && !(e->cfg.flags & SNACB_FLAG_NO_RU_FUSION)) {  // fused dw + 1x1 + residual (blocks 2, 3)
+        const bool ru_persist = (e->cfg.flags & SNACB_FLAG_PERSISTENT_RU) != 0;
+        if (ru_tc_supported(B.Cout, ru_persist) && !(e->cfg.flags & SNACB_FLAG_NO_RU_FUSION)) {  // fused dw + 1x1 + residual (blocks 2, 3)
           const bool last = (r == 2) && (b < 3);
           const bool want32 = !last || e->tap_stage == sid + 4 + 2 * r;
           RuTcArgs u{X, cur, B.r[r], B.Cout, kDil[r], B.up_out, R.dw_w, R.dw_b, R.a1, R.i1, R.a2, R.i2, R.pw16, R.pw_b,
                      want32 ? Y : nullptr, last ? Anext : nullptr, last ? W.blk[b + 1].alpha : nullptr,
-                     last ? W.blk[b + 1].inv : nullptr, e->prefetch_ahead * (B.Cout == 64 ? 3 : 2)};
+                     last ? W.blk[b + 1].inv : nullptr, e->prefetch_ahead * (B.Cout == 64 ? 3 : 2), ru_persist};
           if (ce == cudaSuccess) {
             const double el = (double)n * B.r[r].n() * B.Cout;
             ProfScope ps(e, KC_RU, 2.0 * el * B.Cout + el * 24.0,

@@ -98,8 +98,9 @@ struct RuTcArgs {
   const __half* pw16; const float* pw_b;
   float* out32; __half* out16; const float* sn_alpha; const float* sn_inv;
   int prefetch_ahead;
+  bool persistent;   // k_ru_p (persistent, warp-specialised, also C = 256) instead of k_ru_tc
 };
-bool ru_tc_supported(int C);
+bool ru_tc_supported(int C, bool persistent);
 cudaError_t launch_ru_tc(const GroupCtx& g, const RuTcArgs& a);
 void launch_dwconv_half(const GroupCtx& g, const DwArgs& a, __half* out16);  // plain dw k7 -> fp16 (decoder head)
 void launch_to_half(const float* in, __half* out, size_t n, cudaStream_t st);

@@ -1229,6 +1229,245 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
   }
 }
 
+// ============================================================================ persistent fused ResidualUnit
+// Same math as k_ru_tc, restructured so that nothing waits on anything it does not need:
+// one persistent CTA per SM walks tiles (item, 128 rows) round-robin with three kinds of warps running
+// concurrently on different tiles -
+//   warps 0..8   workers : depthwise + Snake -> fp16 operand tile A[ab] in the swizzled K-major layout
+//   warp  9      control : TMA-loads W once; per tile waits for A[ab], issues the tcgen05 MMAs into
+//                          accumulator D[tb] (TMEM double-buffered), commits a_free / t_full
+//   warps 10..17 epilogue: prefetch the residual rows of their tile while the MMAs run, drain D[tb]
+//                          (bias + residual + optional next-block Snake), coalesced stores, release D[tb]
+// so the workers start tile i+1 while tile i is in the tensor core / epilogue, the weight, the TMEM
+// allocation and the barrier setup are paid once per SM instead of once per tile, and C = 256
+// (decoder block 1: W = 128 KB) fits because only one CTA lives on an SM.
+constexpr int kRupThreads = 576;
+template <int C> struct RupSmem {
+  static constexpr int kNA = (C <= 128) ? 2 : 1;            // operand tile buffers
+  static constexpr int kABytes = BM * C * 2;
+  static constexpr int kWBytes = C * C * 2;
+  static constexpr int kStgBytes = 8 * 32 * 16 * 4;
+  static constexpr int kBytes = kWBytes + kNA * kABytes + kStgBytes + 256 + 1024;
+};
+
+template <int C, int DIL>
+__global__ void __launch_bounds__(kRupThreads, 1) k_ru_p(const __grid_constant__ CUtensorMap tmW, const RuDev a,
+                                                         const int tiles_per_item, const int total_tiles) {
+  using S = RupSmem<C>;
+  constexpr int KB = C / BK;
+  constexpr int NA = S::kNA;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_align1024(smem_raw);
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + S::kWBytes;
+  float* sStg = reinterpret_cast<float*>(sA + NA * S::kABytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStg) + S::kStgBytes);
+  // bars: [0] w_full, [1..2] a_full, [3..4] a_free, [5..6] t_full, [7..8] t_empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bars[1 + i]), kRuWorkers);
+      mbar_init(smem_u32(&bars[3 + i]), 1);
+      mbar_init(smem_u32(&bars[5 + i]), 1);
+      mbar_init(smem_u32(&bars[7 + i]), 256);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) tmem_alloc(smem_u32(tmem_slot), 2 * C);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 9) {
+    // ===================================================================== workers
+    constexpr int CP = C / 2;
+    constexpr int U = (DIL == 1) ? 8 : 9;
+    int i = 0;
+    for (int lin = blockIdx.x; lin < total_tiles; lin += gridDim.x, ++i) {
+      const int item = lin / tiles_per_item, row0 = (lin - item * tiles_per_item) * BM;
+      const int ab = i % NA;
+      if (tid == 0) {  // pull the rows of this CTA's next tile into L2 while this one is computed
+        const int nl = lin + gridDim.x;
+        if (nl < total_tiles) {
+          const int nit = nl / tiles_per_item, nrow0 = (nl - nit * tiles_per_item) * BM;
+          const int r_lo = max(a.out_lo + nrow0 - 3 * DIL - a.in_lo, 0);
+          const int r_hi = min(a.out_lo + nrow0 + BM + 3 * DIL - a.in_lo, a.in_rows);
+          if (r_hi > r_lo)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.x + ((size_t)nit * a.in_rows + r_lo) * C),
+                         "r"((uint32_t)(r_hi - r_lo) * C * 4)
+                         : "memory");
+        }
+      }
+      mbar_wait(smem_u32(&bars[3 + ab]), ((i / NA) & 1) ^ 1);  // the MMAs that read A[ab] last time are done
+      const float* xin = a.x + (size_t)item * a.in_rows * C;
+      uint8_t* sAb = sA + ab * S::kABytes;
+#pragma unroll 1
+      for (int idx = tid; idx < CP * U; idx += kRuWorkers) {
+        const int cp = idx % CP, u = idx / CP;
+        int first;
+        if (DIL == 1) first = u * 16;
+        else if (DIL == 3) first = (u % 3) + (u / 3) * 48;
+        else first = u;
+        const int c = cp * 2;
+        DwPairW W;
+        W.load(a.w7, a.dw_b, a.a1, a.i1, a.a2, a.i2, C, c);
+        const int in_first = a.out_lo + row0 + first - 3 * DIL - a.in_lo;
+        uint32_t mlo, mhi;
+        row_mask<DIL>(in_first, a.in_rows, 22, mlo, mhi);
+        uint8_t* a_kb = sAb + (c / BK) * (BM * 128) + ((c % BK) * 2 & 15);
+        const int chunk = ((c % BK) * 2) >> 4;
+        dw_unit<C, DIL, 16>(xin + (long long)in_first * C + c, mlo, mhi, W, [&](int j, float2 v) {
+          const int trow = first + j * DIL;
+          if (trow < BM)
+            *reinterpret_cast<__half2*>(a_kb + trow * 128 + (((chunk ^ trow) & 7) << 4)) = __floats2half2_rn(v.x, v.y);
+        });
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[1 + ab])) : "memory");
+    }
+  } else if (warp == 9) {
+    // ===================================================================== control: W load + MMA issue
+    if (lane == 0) {
+      mbar_arrive_expect_tx(smem_u32(&bars[0]), S::kWBytes);
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(smem_u32(sW + kb * C * 128), &tmW, smem_u32(&bars[0]), kb * BK, 0);
+      mbar_wait(smem_u32(&bars[0]), 0);
+      constexpr uint32_t idesc = umma_idesc_f16(C);
+      int i = 0;
+      for (int lin = blockIdx.x; lin < total_tiles; lin += gridDim.x, ++i) {
+        const int ab = i % NA, tb = i & 1;
+        mbar_wait(smem_u32(&bars[1 + ab]), (i / NA) & 1);          // operand tile written
+        mbar_wait(smem_u32(&bars[7 + tb]), ((i >> 1) & 1) ^ 1);    // accumulator drained
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint64_t da = umma_desc_k_sw128(smem_u32(sA + ab * S::kABytes + kb * (BM * 128)));
+          const uint64_t db = umma_desc_k_sw128(smem_u32(sW + kb * (C * 128)));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_base + tb * C, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&bars[3 + ab]));
+        umma_commit(smem_u32(&bars[5 + tb]));
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 10..17)
+    const int ew = warp - 10;
+    const int q = warp & 3, half = ew >> 2;
+    constexpr int NH = C / 32;                    // 16-column steps per warp
+    constexpr int PD = 2;                        // residual prefetch depth (steps)
+    const int c4 = lane & 3, r8 = lane >> 2;
+    float* stg = sStg + ew * (32 * 16);
+    float* st_p = stg + lane * 16;
+    const int st_x = (lane >> 1) & 3;
+    const float* ld_p = stg + r8 * 16 + ((c4 ^ ((r8 >> 1) & 3)) << 2);
+    const int colb = half * (C / 2) + c4 * 4;
+    int i = 0;
+    for (int lin = blockIdx.x; lin < total_tiles; lin += gridDim.x, ++i) {
+      const int item = lin / tiles_per_item, row0 = (lin - item * tiles_per_item) * BM;
+      const int tb = i & 1;
+      const ItemRef it = get_item(a.items, a.base, item, a.out_len);
+      const int orow_b = row0 + q * 32 + r8;  // first of this lane's four rows (stride 8)
+      const int tabs_b = a.out_lo + orow_b + it.shift0 * a.up;
+      uint32_t vmask = 0, lmask = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (orow_b + 8 * k < a.out_rows) {
+          vmask |= 1u << k;
+          const int t = tabs_b + 8 * k;
+          if (t >= 0 && t < a.T0 * a.up) lmask |= 1u << k;
+        }
+      }
+      const size_t ob = ((size_t)item * a.out_rows + orow_b) * C + colb;
+      const float* rp = a.x + ((size_t)item * a.in_rows + (a.out_lo + orow_b - a.in_lo)) * C + colb;
+      float4 res[PD][4];
+#pragma unroll
+      for (int h = 0; h < PD; ++h)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          res[h][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if ((vmask >> k) & 1u) res[h][k] = __ldg(reinterpret_cast<const float4*>(rp + k * 8 * C + h * 16));
+        }
+      mbar_wait(smem_u32(&bars[5 + tb]), (i >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tb * C + half * (C / 2) + h * 16), r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(st_p + ((j ^ st_x) << 2)) =
+              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                          __uint_as_float(r[4 * j + 3]));
+        __syncwarp();
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const float4*>(ld_p + k * 128);
+        __syncwarp();
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.pw_b + colb + h * 16));
+        float4 al = make_float4(0.f, 0.f, 0.f, 0.f), iv = al;
+        if (a.sn_alpha) {
+          al = __ldg(reinterpret_cast<const float4*>(a.sn_alpha + colb + h * 16));
+          iv = __ldg(reinterpret_cast<const float4*>(a.sn_inv + colb + h * 16));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (!((vmask >> k) & 1u)) continue;
+          float4 x = add4(add4(v[k], b4), res[h % PD][k]);
+          if (!((lmask >> k) & 1u)) x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.out32) *reinterpret_cast<float4*>(a.out32 + ob + k * 8 * C + h * 16) = x;
+          if (a.out16) {
+            if (a.sn_alpha) {
+              const float2 lo = snake2(make_float2(x.x, x.y), make_float2(al.x, al.y), make_float2(iv.x, iv.y));
+              const float2 hi = snake2(make_float2(x.z, x.w), make_float2(al.z, al.w), make_float2(iv.z, iv.w));
+              x = make_float4(lo.x, lo.y, hi.x, hi.y);
+            }
+            store_half4(a.out16 + ob + k * 8 * C + h * 16, x);
+          }
+        }
+        if (h + PD < NH) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            res[h % PD][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((vmask >> k) & 1u) res[h % PD][k] = __ldg(reinterpret_cast<const float4*>(rp + k * 8 * C + (h + PD) * 16));
+          }
+        }
+      }
+      tc_fence_before();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[7 + tb])) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * C);
+  }
+}
+
+template <int C, int DIL>
+cudaError_t launch_rup_t(const CUtensorMap& mw, const RuDev& d, int tiles_per_item, int total_tiles, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_ru_p<C, DIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, RupSmem<C>::kBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int grid = std::min(total_tiles, sm_count());
+  k_ru_p<C, DIL><<<grid, kRupThreads, RupSmem<C>::kBytes, st>>>(mw, d, tiles_per_item, total_tiles);
+  return cudaGetLastError();
+}
+template <int C>
+cudaError_t launch_rup_c(int dil, const CUtensorMap& mw, const RuDev& d, int tpi, int total, cudaStream_t st) {
+  if (dil == 1) return launch_rup_t<C, 1>(mw, d, tpi, total, st);
+  if (dil == 3) return launch_rup_t<C, 3>(mw, d, tpi, total, st);
+  return launch_rup_t<C, 9>(mw, d, tpi, total, st);
+}
+
 template <int C, int DIL>
 cudaError_t launch_ru_t(const CUtensorMap& mw, const RuDev& d, dim3 grid, cudaStream_t st) {
   static bool attr_set = false;
@@ -1249,10 +1488,10 @@ cudaError_t launch_ru_c(int dil, const CUtensorMap& mw, const RuDev& d, dim3 gri
 
 }  // namespace
 
-bool ru_tc_supported(int C) { return C == 64 || C == 128; }
+bool ru_tc_supported(int C, bool persistent) { return C == 64 || C == 128 || (C == 256 && persistent); }
 
 cudaError_t launch_ru_tc(const GroupCtx& g, const RuTcArgs& a) {
-  if (!ru_tc_supported(a.C) || g.n_items <= 0 || a.out_r.n() <= 0) return cudaErrorInvalidValue;
+  if (!ru_tc_supported(a.C, a.persistent) || g.n_items <= 0 || a.out_r.n() <= 0) return cudaErrorInvalidValue;
   CUtensorMap mw;
   if (!get_tmap(a.pw16, a.C, a.C, a.C, &mw)) return cudaErrorNotSupported;
   RuDev d{};
@@ -1261,8 +1500,17 @@ cudaError_t launch_ru_tc(const GroupCtx& g, const RuTcArgs& a) {
   d.w7 = a.w7; d.dw_b = a.dw_b; d.a1 = a.a1; d.i1 = a.i1; d.a2 = a.a2; d.i2 = a.i2; d.pw_b = a.pw_b;
   d.out32 = a.out32; d.out16 = a.out16; d.sn_alpha = a.sn_alpha; d.sn_inv = a.sn_inv;
   d.prefetch_ahead = a.prefetch_ahead;
-  dim3 grid((unsigned)((a.out_r.n() + BM - 1) / BM), (unsigned)g.n_items);
-  cudaError_t e = (a.C == 64) ? launch_ru_c<64>(a.dil, mw, d, grid, g.stream) : launch_ru_c<128>(a.dil, mw, d, grid, g.stream);
+  const int tpi = (a.out_r.n() + BM - 1) / BM;
+  cudaError_t e;
+  if (a.persistent) {
+    const int total = tpi * g.n_items;
+    e = (a.C == 64) ? launch_rup_c<64>(a.dil, mw, d, tpi, total, g.stream)
+        : (a.C == 128) ? launch_rup_c<128>(a.dil, mw, d, tpi, total, g.stream)
+                       : launch_rup_c<256>(a.dil, mw, d, tpi, total, g.stream);
+  } else {
+    dim3 grid((unsigned)tpi, (unsigned)g.n_items);
+    e = (a.C == 64) ? launch_ru_c<64>(a.dil, mw, d, grid, g.stream) : launch_ru_c<128>(a.dil, mw, d, grid, g.stream);
+  }
   ++*g.launches;
   return e;
 }

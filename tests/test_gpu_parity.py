@@ -21,10 +21,10 @@ def engines(state_dict_w1, ensure_lib):
     from project_morpheus_b200.engine import SnacEngine
     made = {}
 
-    def get(precision="fp32", trim=True):
-        key = (precision, trim)
+    def get(precision="fp32", trim=True, **kw):
+        key = (precision, trim, tuple(sorted(kw.items())))
         if key not in made:
-            made[key] = SnacEngine(state_dict_w1, device=0, precision=precision, trim=trim)
+            made[key] = SnacEngine(state_dict_w1, device=0, precision=precision, trim=trim, **kw)
         return made[key]
 
     yield get
@@ -447,3 +447,21 @@ def test_cuda_graph_latency_path_is_bit_identical(engines, precision):
     bad = tok.copy(); bad[2, 5] = 5000
     pcm, st = eng.decode_windows(bad, noise="philox", seed=11, keys=keys)
     assert st.tolist() == [0, 0, _lib.WIN_REJECTED] + [0] * (n - 3) and not pcm[2].any() and np.array_equal(pcm[0], plain[0])
+
+
+@pytest.mark.parametrize("variant", [dict(persistent_ru=True), dict(fuse_ru=False, fuse_convt_noise=False), dict(lanes=3)])
+def test_kernel_variants_match_oracle(engines, oracle_w1, variant):
+    """Alternative kernel selections of the tensor-core recipe (persistent warp-specialised ResidualUnit
+    kernel incl. C = 256; fully unfused layer-per-kernel path; concurrent chunk lanes) meet the same tolerance."""
+    kw = dict(variant)
+    if "lanes" in kw:
+        kw["chunk_items"] = 4
+    eng = engines("fp16", True, **kw)
+    n, frames = 11, 4
+    tok = windows_tokens(n, frames, base_stream=1500)
+    noise = snac_ref.make_noise(n, frames, seed=17)
+    ref = oracle_decode_windows(oracle_w1, tok, noise)[:, 2048:4096]
+    pcm, st = eng.decode_windows(tok, noise=snac_ref.pack_noise(noise))
+    assert (st == _lib.WIN_OK).all()
+    want = pcm_trunc(ref).astype(np.float32) / 32767.0
+    _check_wave(want, pcm.astype(np.float32) / 32767.0, TOL_MAX_ABS, TOL_SNR_DB - 0.5)
