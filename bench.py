@@ -323,24 +323,37 @@ def run_ours(args) -> None:
     e2e_value = windows_total * AUDIO_S_PER_WINDOW / (tot_e2e_ms * 1e-3)
     wps = windows_total / (tot_dev_ms * 1e-3)
 
-    # dominant kernel class and its roofline
+    # dominant kernel class and its roofline.  Which roof applies follows the roofline model: arithmetic
+    # intensity (executed FLOPs / algorithmic bytes of the class) against the ridge point of the measured peaks.
     roof = None
     if stats:
         tot_ms = sum(v["ms"] for v in stats.values()) or 1e-9
         name, top = max(stats.items(), key=lambda kv: kv[1]["ms"])
-        tensor_like = name.startswith("gemm") or name.startswith("block")
-        if tensor_like:
-            ach = top["flops"] / (top["ms"] * 1e-3) / 1e12
-            peak = peaks["tensor_tflops"]
-            roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak}
+        ridge = peaks["tensor_tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+        ai = top["flops"] / max(top["bytes"], 1.0)
+        tflops = top["flops"] / (top["ms"] * 1e-3) / 1e12
+        gbs = top["bytes"] / (top["ms"] * 1e-3) / 1e9
+        if ai >= ridge:
+            roof = {"bound": "tensor", "achieved": tflops, "peak": peaks["tensor_tflops"], "unit": "TFLOP/s",
+                    "frac": tflops / peaks["tensor_tflops"]}
         else:
-            ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9
-            peak = peaks["hbm_gbs"]
-            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}
+            roof = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"]}
+        launches_per_step = top["launches"] / 2
+        traffic = None
+        try:  # DRAM bytes per window of this kernel class from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tj = json.load(f)
+            if name in tj.get("dram_bytes_per_window_per_launch", {}):
+                traffic = tj["dram_bytes_per_window_per_launch"][name] * S
+        except Exception:  # noqa: BLE001
+            traffic = None
         roof.update({
-            "traffic": None, "kernel": name, "launches_per_step": top["launches"] / 2,
+            "traffic": traffic, "kernel": name, "launches_per_step": launches_per_step,
             "avg_launch_ms": top["ms"] / max(1, top["launches"]), "share_of_step": top["ms"] / tot_ms,
-            "peak_source": peaks["source"] + (", bf16 dense sustained" if tensor_like else ", copy"),
+            "arithmetic_intensity_flop_per_byte": ai, "ridge_flop_per_byte": ridge,
+            "tensor_tflops": tflops, "tensor_frac": tflops / peaks["tensor_tflops"], "hbm_gbs": gbs,
+            "hbm_frac": gbs / peaks["hbm_gbs"], "bytes_per_launch": top["bytes"] / max(1, top["launches"]),
+            "peak_source": peaks["source"] + " (bf16 dense sustained / copy)",
             "flops_counted": "executed (2*MAC of the launches, dependency-cone trimmed)",
             "classes": {k: {"ms_per_step": v["ms"] / 2, "launches_per_step": v["launches"] / 2,
                             "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else 0.0,

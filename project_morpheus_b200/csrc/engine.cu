@@ -825,14 +825,12 @@ static int decode_windows_core(snacb_engine* e, const int32_t* d_tokens, int32_t
       if (rc) return rc;
     }
   } else {
-    size_t used = 0;
     std::vector<Item> all;
     std::vector<std::pair<int, std::pair<size_t, int>>> runs;  // F, (offset, count)
     for (auto& kv : groups) {
       runs.push_back({kv.first, {all.size(), (int)kv.second.size()}});
       for (int i : kv.second) all.push_back(Item{i, 0, (int64_t)i * 2048});
     }
-    (void)used;
     if (!all.empty()) {
       rc = upload_items(e, all, d_items, st);
       if (rc) return rc;
