@@ -182,9 +182,11 @@ struct DwPairW {
 };
 template <int C, int DIL, int L, typename Sink>
 __device__ __forceinline__ void dw_unit(const float* p0, uint32_t mask_lo, uint32_t mask_hi, const DwPairW& W, Sink&& sink) {
-  float2 win[7];
-#pragma unroll
-  for (int k = 0; k < 7; ++k) win[k] = make_float2(0.f, 0.f);
+  // Transposed-form FIR: input m, once Snake'd, is scattered into the (up to) seven outputs j = m-6..m it
+  // feeds (tap k = m - j).  The seven FFMA2 of one input are independent of each other and consecutive
+  // updates of one accumulator are seven instructions apart, so the FMA latency is covered inside a single
+  // warp (a sliding-window gather would chain seven dependent FFMA2 per output).
+  float2 acc[7];
 #pragma unroll
   for (int m = 0; m < L + 6; ++m) {
     float2 v = make_float2(0.f, 0.f);
@@ -192,14 +194,11 @@ __device__ __forceinline__ void dw_unit(const float* p0, uint32_t mask_lo, uint3
     if (ok) v = __ldg(reinterpret_cast<const float2*>(p0 + (long long)m * (DIL * C)));
     v = snake2(v, W.al1, W.iv1);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) win[k] = win[k + 1];
-    win[6] = v;
-    if (m >= 6) {
-      float2 acc = W.bias;
-#pragma unroll
-      for (int k = 0; k < 7; ++k) acc = __ffma2_rn(W.w[k], win[k], acc);
-      sink(m - 6, snake2(acc, W.al2, W.iv2));
+    for (int k = 0; k < 7; ++k) {
+      const int j = m - k;  // output fed through tap k
+      if (j >= 0 && j < L) acc[j % 7] = __ffma2_rn(W.w[k], v, (k == 0) ? W.bias : acc[j % 7]);
     }
+    if (m >= 6) sink(m - 6, snake2(acc[(m - 6) % 7], W.al2, W.iv2));
   }
 }
 // bit m set <=> 0 <= r0 + m*DIL < rows, for m in [0, n)
@@ -606,7 +605,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_ws(const __grid_constant
 // the final epilogue combines D1 + b + n*D2 per row and stores fp32 x coalesced.  Saves the fp32 +
 // fp16 round trip of y through HBM (12 B per element) and one launch per block.
 template <int BN>
-__global__ void __launch_bounds__(kTcThreads, 2) k_convt_noise_tc(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(kTcThreads, (BN == 64) ? 3 : 2) k_convt_noise_tc(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmW,
                                                                 const __grid_constant__ CUtensorMap tmN, const TcDev a) {
   using S = TcSmem<BN>;
@@ -909,7 +908,7 @@ cudaError_t launch_convt_noise_tc(const GroupCtx& g, const TcGemmArgs& a, const 
     return cudaErrorNotSupported;
   TcDev d{};
   d.items = g.items; d.base = g.base; d.out_len = g.out_len; d.T0 = g.T0; d.n_items = g.n_items;
-  d.stages = std::min((a.K / BK) * 2, bn == 128 ? TcSmem<128>::kMaxStages : TcSmem<64>::kMaxStages);
+  d.stages = 3;  // stage 0 / 1 / 2 are re-used as y tile / W_n / transposes; 3 stages keep 2-3 CTAs per SM
   d.K = a.K; d.nseg = 2; d.a_rows = a.a_rows; d.a_lo = a.a_lo; d.s = a.s; d.p = a.p; d.Cout = a.Cout;
   d.bias = a.bias; d.out32 = a.out32; d.o_lo = a.o_r.lo; d.o_rows = a.o_r.n(); d.ldo = a.ldo; d.noise = a.noise; d.up = a.up;
   dim3 grid((unsigned)((Mtot + BM - 1) / BM), (unsigned)a.s);
