@@ -201,6 +201,40 @@ __device__ __forceinline__ void dw_unit(const float* p0, uint32_t mask_lo, uint3
     if (m >= 6) sink(m - 6, snake2(acc[(m - 6) % 7], W.al2, W.iv2));
   }
 }
+// Same unit with its L+6 inputs staged through shared memory by cp.async: all loads of the unit are in
+// flight at once without holding a register each (the register-resident version lets the compiler
+// interleave loads and uses, which exposes the global latency at almost every input - ncu: long
+// scoreboard = 74 % of the stalls of k_dw_tc), then the thread waits ONCE and reads its own slots back
+// (stage[m * stride]: the lanes of a warp are contiguous, conflict-free).  No block barrier is needed: a
+// thread only reads what it copied itself.
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = smem_u32(smem_dst);
+  const int n = valid ? 8 : 0;  // src-size 0 -> the 8 destination bytes are zero-filled (conv zero padding)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+template <int C, int DIL, int L, typename Sink>
+__device__ __forceinline__ void dw_unit_staged(const float* p0, uint32_t mask, const DwPairW& W, float2* stage, int stride,
+                                               Sink&& sink) {
+  static_assert(L + 6 <= 32, "mask is 32 bits");
+#pragma unroll
+  for (int m = 0; m < L + 6; ++m) {
+    const bool ok = (mask >> m) & 1u;
+    cp_async_8(stage + m * stride, ok ? (const void*)(p0 + (long long)m * (DIL * C)) : (const void*)p0, ok);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  float2 acc[7];
+#pragma unroll
+  for (int m = 0; m < L + 6; ++m) {
+    const float2 v = snake2(stage[m * stride], W.al1, W.iv1);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const int j = m - k;
+      if (j >= 0 && j < L) acc[j % 7] = __ffma2_rn(W.w[k], v, (k == 0) ? W.bias : acc[j % 7]);
+    }
+    if (m >= 6) sink(m - 6, snake2(acc[(m - 6) % 7], W.al2, W.iv2));
+  }
+}
 // bit m set <=> 0 <= r0 + m*DIL < rows, for m in [0, n)
 template <int DIL>
 __device__ __forceinline__ void row_mask(int r0, int rows, int n, uint32_t& lo, uint32_t& hi) {
@@ -955,8 +989,7 @@ cudaError_t launch_gemm_tc(const GroupCtx& g, const TcGemmArgs& a) {
 
 // ============================================================================ depthwise k=7 -> fp16
 // Each thread owns two adjacent channels and walks one residue class (mod dil) of a 32*dil-row
-// segment: a 7-deep register window slides along time, so every input is loaded and Snake'd once
-// (38 loads for 32 outputs).  Output = Snake(b + sum_k w[k] * Snake(x[t + (k-3)*dil])) as fp16, the
+// segment of 16 outputs (22 inputs, staged through shared memory by cp.async), every input Snake'd once.  Output = Snake(b + sum_k w[k] * Snake(x[t + (k-3)*dil])) as fp16, the
 // K-major operand of the ResidualUnit's 1x1 GEMM.
 template <int C, int DIL>
 __global__ void __launch_bounds__(256) k_dw_tc(const Item* items, int base, int out_len, int T0, DwTcArgs a) {
@@ -966,7 +999,8 @@ __global__ void __launch_bounds__(256) k_dw_tc(const Item* items, int base, int 
   const int cp = idx % CP, rest = idx / CP;
   const int rho = rest % DIL, seg = rest / DIL;
   const int out_rows = a.out_r.n(), in_rows = a.in_r.n();
-  const int row0 = seg * 32 * DIL + rho;
+  __shared__ float2 stage[22 * 256];
+  const int row0 = seg * 16 * DIL + rho;
   if (row0 >= out_rows) return;
   const int c = cp * 2;
   const ItemRef it = get_item(items, base, item, out_len);
@@ -979,8 +1013,8 @@ __global__ void __launch_bounds__(256) k_dw_tc(const Item* items, int base, int 
   const int t_hi = T0 * a.up;
   const int t_abs0 = t_first + it.shift0 * a.up;
   uint32_t mlo, mhi;
-  row_mask<DIL>(in_first, in_rows, 38, mlo, mhi);
-  dw_unit<C, DIL, 32>(x + (long long)in_first * C, mlo, mhi, W, [&](int j, float2 v) {
+  row_mask<DIL>(in_first, in_rows, 22, mlo, mhi);
+  dw_unit_staged<C, DIL, 16>(x + (long long)in_first * C, mlo, W, stage + threadIdx.x, 256, [&](int j, float2 v) {
     const int orow = row0 + j * DIL;
     if (orow < out_rows) {
       const int t_abs = t_abs0 + j * DIL;
@@ -992,7 +1026,7 @@ __global__ void __launch_bounds__(256) k_dw_tc(const Item* items, int base, int 
 
 template <int C>
 void launch_dw_tc_c(const GroupCtx& g, const DwTcArgs& a) {
-  const int nseg = (a.out_r.n() + 32 * a.dil - 1) / (32 * a.dil);
+  const int nseg = (a.out_r.n() + 16 * a.dil - 1) / (16 * a.dil);
   dim3 grid((unsigned)(((long long)nseg * a.dil * (C / 2) + 255) / 256), g.n_items);
   if (a.dil == 1) k_dw_tc<C, 1><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, a);
   else if (a.dil == 3) k_dw_tc<C, 3><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, a);
