@@ -293,6 +293,35 @@ def run_ours(args) -> None:
             extra[name] = {"p50_ms": 1e3 * p50, "p95_ms": 1e3 * sorted(lat)[int(0.95 * (len(lat) - 1))],
                            "audio_s_per_s": n * AUDIO_S_PER_WINDOW / p50, "reps": len(lat)}
 
+        # BASELINE config 5 pattern: ragged ticks (per stream 0/1/2 pending windows, 1 / 4 / 7 frames each)
+        if args.ragged_streams > 0:
+            rng = np.random.default_rng(2024)
+            ns = args.ragged_streams
+            ticks = []
+            for t in range(12):
+                wins, lens = [], []
+                for sidx in range(ns):
+                    for _ in range(int(rng.choice([0, 1, 2], p=[0.2, 0.6, 0.2]))):
+                        fr = int(rng.choice([1, 4, 7], p=[0.05, 0.35, 0.6]))
+                        wins.append(synth_tokens(90000 + sidx * 13 + t, 1, 7)[0][: 7 * fr])
+                        lens.append(7 * fr)
+                tokr = np.zeros((len(wins), 49), dtype=np.int32)
+                for i, w in enumerate(wins):
+                    tokr[i, : len(w)] = w
+                ticks.append((tokr, lens))
+            for tokr, lens in ticks[:3]:
+                eng.decode_windows(tokr, ntok=lens, noise="philox", seed=1, keys=np.arange(len(lens), dtype=np.uint64))
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            emitted = 0
+            for tokr, lens in ticks:
+                pcm_r, st_r = eng.decode_windows(tokr, ntok=lens, noise="philox", seed=2, keys=np.arange(len(lens), dtype=np.uint64))
+                emitted += int((st_r == _lib.WIN_OK).sum())
+            dt = time.perf_counter() - t0
+            extra["cfg5_ragged"] = {"streams": ns, "ticks": len(ticks), "windows": int(sum(len(l) for _, l in ticks)),
+                                    "ms_per_tick": 1e3 * dt / len(ticks), "audio_s_per_s": emitted * AUDIO_S_PER_WINDOW / dt,
+                                    "note": "host API, mixed 1/4/7-frame windows grouped by frame count inside one call"}
+
         # BASELINE config 3 (long_read): one-shot decode of 720-frame utterances, time-tiled; reduced batch by default
         if args.long_read_batch > 0:
             Fl, Bl = 720, args.long_read_batch
@@ -408,6 +437,7 @@ def main() -> None:
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline leg")
     ap.add_argument("--ref-windows", type=int, default=32, help="windows per step of the CPU reference sample")
     ap.add_argument("--latency-reps", type=int, default=200)
+    ap.add_argument("--ragged-streams", type=int, default=512, help="streams of the config-5 ragged-tick side measurement (0 = skip)")
     ap.add_argument("--long-read-batch", type=int, default=8, help="streams of the config-3 long_read side measurement (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -4,7 +4,7 @@ TAG=${1:-sweep2}; PAIRS=$2
 OUT=gpurun_out/$TAG; mkdir -p $OUT
 for pr in $PAIRS; do
   c=${pr%%:*}; l=${pr##*:}
-  timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --latency-reps 3 --long-read-batch 0 --chunk $c --lanes $l > $OUT/b_${c}_$l.json 2> $OUT/b_${c}_$l.err
+  timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --latency-reps 3 --long-read-batch 0 --ragged-streams 0 --chunk $c --lanes $l > $OUT/b_${c}_$l.json 2> $OUT/b_${c}_$l.err
   python - <<PY
 import json
 try:
