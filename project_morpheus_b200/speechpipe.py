@@ -100,10 +100,13 @@ def convert_to_audio_batch(windows: Sequence[Sequence[int]], noise=None) -> List
         return []
     lens = [len(w) for w in windows]
     stride = max(TOKENS_PER_FRAME, max(lens))
-    tokens = np.zeros((n, stride), dtype=np.int32)
-    for i, w in enumerate(windows):
-        if lens[i]:
-            tokens[i, : lens[i]] = np.asarray(w, dtype=np.int64).astype(np.int32)
+    if min(lens) == stride:  # uniform tick (the common case): one vectorised conversion
+        tokens = np.asarray(windows, dtype=np.int64).astype(np.int32).reshape(n, stride)
+    else:
+        tokens = np.zeros((n, stride), dtype=np.int32)
+        for i, w in enumerate(windows):
+            if lens[i]:
+                tokens[i, : lens[i]] = np.asarray(w, dtype=np.int64).astype(np.int32)
     uniform = len(set(lens)) == 1 and lens[0] >= TOKENS_PER_FRAME
     pcm, status = _decode_batch(tokens, None if uniform else lens, noise=noise)
     out: List[Optional[bytes]] = []
