@@ -54,6 +54,7 @@ extern "C" {
 /* snacb_config.flags */
 #define SNACB_FLAG_NO_RU_FUSION 1 /* tensor-core recipe: run every ResidualUnit as dw kernel + GEMM kernel */
 #define SNACB_FLAG_PERSISTENT_RU 4 /* persistent warp-specialised ResidualUnit kernel (also fuses C = 256)   */
+#define SNACB_FLAG_TAIL_FUSION 8 /* fuse the decoder tail into the last ResidualUnit kernel (measured slower: off) */
 #define SNACB_FLAG_NO_CONVT_NOISE_FUSION 2 /* run ConvTranspose1d and NoiseBlock as two GEMM kernels   */
 
 /* fixed geometry of hubertsiuzdak/snac_24khz (the only model the reference loads, speechpipe.py:42) */

@@ -368,6 +368,7 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
     __half* Q16 = bp.take<__half>(S * n);
     if (bp.off > lane_bytes) return fail(e, SNACB_ENOMEM, "workspace overflow in tensor-core pipeline");
     GroupCtx g{d_items ? d_items + start : nullptr, start, n, out_len, P.T0, st, &e->launches};
+    bool tail_done = false;
 
     auto gemm = [&](const TcGemmArgs& a) {
       if (ce != cudaSuccess) return;
@@ -448,6 +449,14 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
           RuTcArgs u{X, cur, B.r[r], B.Cout, kDil[r], B.up_out, R.dw_w, R.dw_b, R.a1, R.i1, R.a2, R.i2, R.pw16, R.pw_b,
                      want32 ? Y : nullptr, last ? Anext : nullptr, last ? W.blk[b + 1].alpha : nullptr,
                      last ? W.blk[b + 1].inv : nullptr, e->prefetch_ahead * (B.Cout == 64 ? 3 : 2), ru_persist};
+          // last ResidualUnit of the decoder: fuse Snake(64) -> conv k7 64->1 -> tanh -> slice -> int16 pack
+          const bool fuse_tail = (b == 3) && (r == 2) && !ru_persist && (e->cfg.flags & SNACB_FLAG_TAIL_FUSION) &&
+                                 e->tap_stage != sid + 4 + 2 * r;
+          if (fuse_tail) {
+            u.out32 = nullptr; u.sn_alpha = W.tail_alpha; u.sn_inv = W.tail_inv;
+            u.tail_w7 = W.tail_w; u.tail_b = W.tail_b; u.tail_out = tail_out; u.status = d_status; u.wav = wav; u.pcm = pcm;
+            tail_done = true;
+          }
           if (ce == cudaSuccess) {
             const double el = (double)n * B.r[r].n() * B.Cout;
             ProfScope ps(e, KC_RU, 2.0 * el * B.Cout + el * 24.0,
@@ -481,7 +490,7 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
       Aother = D16;
     }
     if (ce != cudaSuccess) return fail(e, SNACB_ECUDA, "tensor-core GEMM launch failed: %s", cudaGetErrorString(ce));
-    {
+    if (!tail_done) {
       const double smp = (double)n * tail_out.n();
       ProfScope ps(e, KC_TAIL, smp * (2.0 * 448 + 4.0 * 64), 4.0 * (double)n * P.b[3].r[2].n() * 64 + smp * 2.0, st);
       TailArgs t{X, P.b[3].r[2], tail_out, W.tail_alpha, W.tail_inv, W.tail_w, W.tail_b, d_status, wav, pcm, true};

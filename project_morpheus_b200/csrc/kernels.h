@@ -99,6 +99,8 @@ struct RuTcArgs {
   float* out32; __half* out16; const float* sn_alpha; const float* sn_inv;
   int prefetch_ahead;
   bool persistent;   // k_ru_p (persistent, warp-specialised, also C = 256) instead of k_ru_tc
+  // non-null tail_w7: fuse the decoder tail (Snake = sn_alpha/sn_inv, conv k7 64->1, tanh, slice, int16 pack)
+  const float* tail_w7; const float* tail_b; Rng tail_out; const int32_t* status; float* wav; int16_t* pcm;
 };
 bool ru_tc_supported(int C, bool persistent);
 cudaError_t launch_ru_tc(const GroupCtx& g, const RuTcArgs& a);

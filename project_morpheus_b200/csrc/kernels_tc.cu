@@ -1066,18 +1066,24 @@ struct RuDev {
   const float* pw_b;
   float* out32; __half* out16; const float* sn_alpha; const float* sn_inv;
   int prefetch_ahead;   // CTAs resident on the whole GPU: the tile this far ahead in launch order is prefetched into L2
+  // fused decoder tail (TAIL variant, last ResidualUnit of block 3): Snake(64) -> conv k7 64->1 -> tanh -> pack
+  int tile_stride, row_off;            // tile t covers out rows [t*tile_stride + row_off, +128)
+  int tail_lo, tail_n;                 // emitted samples: relative times [tail_lo, tail_lo + tail_n)
+  const float* tail_w7; const float* tail_b; const int32_t* status; float* wav; int16_t* pcm;
 };
 
+constexpr int kTailPitch = 80;  // floats per row of the Snake'd output tile (conflict-free float4 rows)
 template <int C> struct RuSmem {
   static constexpr int kABytes = BM * C * 2;   // operand tile; the epilogue staging (16 KB) aliases it after the MMAs
   static constexpr int kWBytes = C * C * 2;
   static constexpr int kInBytes = 0;  // (cp.async input staging measured slower here than register loads: 2.22 vs 2.01 ms)
   static constexpr int kMetaBytes = 64;
   static constexpr int kBytes = kABytes + kWBytes + kInBytes + kMetaBytes + 1024;
+  static constexpr int kTailBytes = BM * kTailPitch * 4 + 4 * 64 * 4;  // TAIL variant: output tile + partial sums
   static_assert(kABytes >= 8 * 32 * 16 * 4, "staging aliases the operand tile");
 };
 
-template <int C, int DIL>
+template <int C, int DIL, bool TAIL = false>
 __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const __grid_constant__ CUtensorMap tmW, const RuDev a) {
   using S = RuSmem<C>;
   constexpr int KB = C / BK;  // k-blocks of 64 channels
@@ -1091,8 +1097,11 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int item = blockIdx.y;
-  const int row0 = blockIdx.x * BM;  // first output row (index into the item's out rows) of this tile
+  // first output row (index into the item's out rows) of this tile; TAIL tiles overlap by 6 rows and may start
+  // before row 0 / run past the last row (those rows are the final conv's zero padding)
+  const int row0 = TAIL ? (int)blockIdx.x * a.tile_stride + a.row_off : (int)blockIdx.x * BM;
   const ItemRef it = get_item(a.items, a.base, item, a.out_len);
+  float* sTail = reinterpret_cast<float*>(smem + S::kABytes + S::kWBytes + S::kInBytes + S::kMetaBytes);  // TAIL only
 
   if (tid == 0) {
     mbar_init(smem_u32(&bars[0]), 1);
@@ -1106,8 +1115,9 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
     const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + a.prefetch_ahead;
     const int pit = (int)(lin / gridDim.x), ptile = (int)(lin - (long long)pit * gridDim.x);
     if (pit < (int)gridDim.y) {
-      const int r_lo = max(a.out_lo + ptile * BM - 3 * DIL - a.in_lo, 0);
-      const int r_hi = min(a.out_lo + ptile * BM + BM + 3 * DIL - a.in_lo, a.in_rows);
+      const int prow0 = TAIL ? ptile * a.tile_stride + a.row_off : ptile * BM;
+      const int r_lo = max(a.out_lo + prow0 - 3 * DIL - a.in_lo, 0);
+      const int r_hi = min(a.out_lo + prow0 + BM + 3 * DIL - a.in_lo, a.in_rows);
       const char* p = reinterpret_cast<const char*>(a.x + ((size_t)pit * a.in_rows + r_lo) * C);
       const uint32_t bytes = (uint32_t)(r_hi - r_lo) * C * 4;  // rows are contiguous: one bulk prefetch covers the tile
       if (r_hi > r_lo) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
@@ -1185,7 +1195,7 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
     uint32_t vmask = 0, lmask = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      if (orow_b + 8 * i < a.out_rows) {
+      if (orow_b + 8 * i >= 0 && orow_b + 8 * i < a.out_rows) {
         vmask |= 1u << i;
         const int t = tabs_b + 8 * i;
         if (t >= 0 && t < a.T0 * a.up) lmask |= 1u << i;
@@ -1227,9 +1237,18 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        if (!((vmask >> i) & 1u)) continue;
+        if (!((vmask >> i) & 1u)) {
+          if (TAIL) *reinterpret_cast<float4*>(sTail + (q * 32 + r8 + 8 * i) * kTailPitch + colb + h * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+          continue;
+        }
         float4 x = add4(add4(v[i], b4), res[i]);
         if (!((lmask >> i) & 1u)) x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (TAIL) {  // Snake of the decoder tail, kept on chip for the final conv
+          const float2 lo = snake2(make_float2(x.x, x.y), make_float2(al.x, al.y), make_float2(iv.x, iv.y));
+          const float2 hi = snake2(make_float2(x.z, x.w), make_float2(al.z, al.w), make_float2(iv.z, iv.w));
+          *reinterpret_cast<float4*>(sTail + (q * 32 + r8 + 8 * i) * kTailPitch + colb + h * 16) = make_float4(lo.x, lo.y, hi.x, hi.y);
+          continue;
+        }
         if (a.out32) *reinterpret_cast<float4*>(a.out32 + ob + i * 8 * C + h * 16) = x;
         if (a.out16) {
           if (a.sn_alpha) {
@@ -1243,6 +1262,41 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
       if (h + 1 < NH) load_res(h + 1);
     }
     tc_fence_before();
+    if (TAIL) {
+      // ---- decoder tail on the tile: y[o] = tanh(b + sum_{k,c} w[k][c] * s[o + k][c]), o = 0..121 (rows o..o+6)
+      asm volatile("bar.sync 2, 256;" ::: "memory");  // the eight epilogue warps: tile complete in shared memory
+      float* part = sTail + BM * kTailPitch;           // [4][64]
+      const int etid = tid;                            // 0..255
+      const int sx = etid & 63, qc = etid >> 6;
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        const int o = pass * 64 + sx;
+        float acc = 0.0f;
+        if (o < a.tile_stride) {
+#pragma unroll
+          for (int k = 0; k < 7; ++k)
+#pragma unroll
+            for (int c = 0; c < 16; c += 4) {
+              const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.tail_w7 + k * 64 + qc * 16 + c));
+              const float4 x4 = *reinterpret_cast<const float4*>(sTail + (o + k) * kTailPitch + qc * 16 + c);
+              acc = fmaf(w4.x, x4.x, acc); acc = fmaf(w4.y, x4.y, acc); acc = fmaf(w4.z, x4.z, acc); acc = fmaf(w4.w, x4.w, acc);
+            }
+        }
+        part[qc * 64 + sx] = acc;
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (qc == 0 && o < a.tile_stride) {
+          const int oi = (int)blockIdx.x * a.tile_stride + o;  // emitted sample index inside [0, tail_n)
+          const int t_abs = a.tail_lo + oi + it.shift0 * 512;
+          if (oi < a.tail_n && t_abs >= 0 && t_abs < a.T0 * 512 && !(a.status && a.status[it.code_row] != SNACB_WIN_OK)) {
+            const float y = tanhf(((part[sx] + part[64 + sx]) + (part[128 + sx] + part[192 + sx])) + a.tail_b[0]);
+            const long long d = it.dst + oi;
+            if (a.wav) a.wav[d] = y;
+            if (a.pcm) a.pcm[d] = (int16_t)(y * 32767.0f);
+          }
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+      }
+    }
   }
   __syncthreads();
   if (warp == 9) {
@@ -1501,6 +1555,17 @@ cudaError_t launch_ru_t(const CUtensorMap& mw, const RuDev& d, dim3 grid, cudaSt
   k_ru_tc<C, DIL><<<grid, kRuThreads, RuSmem<C>::kBytes, st>>>(mw, d);
   return cudaGetLastError();
 }
+cudaError_t launch_ru_tail(const CUtensorMap& mw, const RuDev& d, dim3 grid, cudaStream_t st) {
+  constexpr int bytes = RuSmem<64>::kBytes + RuSmem<64>::kTailBytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_ru_tc<64, 9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  k_ru_tc<64, 9, true><<<grid, kRuThreads, bytes, st>>>(mw, d);
+  return cudaGetLastError();
+}
 template <int C>
 cudaError_t launch_ru_c(int dil, const CUtensorMap& mw, const RuDev& d, dim3 grid, cudaStream_t st) {
   if (dil == 1) return launch_ru_t<C, 1>(mw, d, grid, st);
@@ -1524,6 +1589,15 @@ cudaError_t launch_ru_tc(const GroupCtx& g, const RuTcArgs& a) {
   d.prefetch_ahead = a.prefetch_ahead;
   const int tpi = (a.out_r.n() + BM - 1) / BM;
   cudaError_t e;
+  if (a.tail_w7) {  // last ResidualUnit of block 3 + decoder tail + PCM pack in one kernel
+    if (a.C != 64 || a.dil != 9) return cudaErrorInvalidValue;
+    d.tile_stride = BM - 6; d.row_off = a.tail_out.lo - 3 - a.out_r.lo; d.tail_lo = a.tail_out.lo; d.tail_n = a.tail_out.n();
+    d.tail_w7 = a.tail_w7; d.tail_b = a.tail_b; d.status = a.status; d.wav = a.wav; d.pcm = a.pcm;
+    dim3 grid((unsigned)((a.tail_out.n() + d.tile_stride - 1) / d.tile_stride), (unsigned)g.n_items);
+    e = launch_ru_tail(mw, d, grid, g.stream);
+    ++*g.launches;
+    return e;
+  }
   if (a.persistent) {
     const int total = tpi * g.n_items;
     e = (a.C == 64) ? launch_rup_c<64>(a.dil, mw, d, tpi, total, g.stream)

@@ -449,7 +449,8 @@ def test_cuda_graph_latency_path_is_bit_identical(engines, precision):
     assert st.tolist() == [0, 0, _lib.WIN_REJECTED] + [0] * (n - 3) and not pcm[2].any() and np.array_equal(pcm[0], plain[0])
 
 
-@pytest.mark.parametrize("variant", [dict(persistent_ru=True), dict(fuse_ru=False, fuse_convt_noise=False), dict(lanes=3)])
+@pytest.mark.parametrize("variant", [dict(persistent_ru=True), dict(fuse_ru=False, fuse_convt_noise=False), dict(lanes=3),
+                                     dict(fuse_tail=True)])
 def test_kernel_variants_match_oracle(engines, oracle_w1, variant):
     """Alternative kernel selections of the tensor-core recipe (persistent warp-specialised ResidualUnit
     kernel incl. C = 256; fully unfused layer-per-kernel path; concurrent chunk lanes) meet the same tolerance."""
