@@ -466,3 +466,36 @@ def test_kernel_variants_match_oracle(engines, oracle_w1, variant):
     assert (st == _lib.WIN_OK).all()
     want = pcm_trunc(ref).astype(np.float32) / 32767.0
     _check_wave(want, pcm.astype(np.float32) / 32767.0, TOL_MAX_ABS, TOL_SNR_DB - 0.5)
+
+
+def test_c_abi_error_paths(engines):
+    """Misuse returns negative codes with a message; nothing is thrown across the C boundary and the engine
+    stays usable afterwards."""
+    eng = engines("fp16")
+    lib, h = eng._lib, eng._h
+    tok = torch.from_numpy(windows_tokens(2, 4, 1)).cuda()
+    pcm = torch.empty((2, 2048), dtype=torch.int16, device="cuda")
+    st = torch.empty((2,), dtype=torch.int32, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    assert lib.snacb_decode_windows(h, None, 28, None, 28, 2, 0, None, 0, 0, None, pcm.data_ptr(), st.data_ptr(), s) == -1
+    assert b"bad argument" in lib.snacb_last_error(h)
+    assert lib.snacb_decode_windows(h, tok.data_ptr(), 28, None, 29, 2, 0, None, 0, 0, None, pcm.data_ptr(), st.data_ptr(), s) == -1
+    assert lib.snacb_decode_windows(h, tok.data_ptr(), 28, None, 28, 2, 1, None, 0, 0, None, pcm.data_ptr(), st.data_ptr(), s) == -1
+    nz = torch.zeros((2, 100), device="cuda")
+    assert lib.snacb_decode_windows(h, tok.data_ptr(), 28, None, 28, 2, 1, nz.data_ptr(), 100, 0, None, pcm.data_ptr(), st.data_ptr(), s) == -1
+    assert b"noise_stride" in lib.snacb_last_error(h)
+    assert lib.snacb_decode_windows(h, tok.data_ptr(), 28, None, 28, 0, 0, None, 0, 0, None, pcm.data_ptr(), st.data_ptr(), s) == 0
+    bad = (C.c_int32 * 2)(28, 99)
+    assert lib.snacb_decode_windows(h, tok.data_ptr(), 28, bad, 28, 2, 0, None, 0, 0, None, pcm.data_ptr(), st.data_ptr(), s) == -1
+    assert lib.snacb_decode_codes(h, None, None, None, 1, 4, 0, None, 0, None, None, s) == -1
+    # unloaded engine refuses to decode
+    h2 = C.c_void_p()
+    cfg = _lib.Config(abi_version=_lib.ABI_VERSION, device=0, precision=_lib.PREC_FP16, chunk_items=0, trim=1)
+    assert lib.snacb_create(C.byref(h2), C.byref(cfg)) == 0
+    assert lib.snacb_decode_windows(h2, tok.data_ptr(), 28, None, 28, 2, 0, None, 0, 0, None, pcm.data_ptr(), st.data_ptr(), s) == -3
+    lib.snacb_destroy(h2)
+    bad_cfg = _lib.Config(abi_version=99, device=0, precision=_lib.PREC_FP16, chunk_items=0, trim=1)
+    assert lib.snacb_create(C.byref(h2), C.byref(bad_cfg)) == -1
+    # still healthy
+    out, status = eng.decode_windows(windows_tokens(2, 4, 1), noise="off")
+    assert (status == _lib.WIN_OK).all() and out.any()
