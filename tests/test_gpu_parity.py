@@ -499,3 +499,32 @@ def test_c_abi_error_paths(engines):
     # still healthy
     out, status = eng.decode_windows(windows_tokens(2, 4, 1), noise="off")
     assert (status == _lib.WIN_OK).all() and out.any()
+
+
+def test_orpheus_snac_path_checkpoint_dir(tmp_path, state_dict_w1, monkeypatch, engines):
+    """The reference's offline knob (speechpipe.py:38-43): ORPHEUS_SNAC_PATH names a directory with config.json +
+    pytorch_model.bin; the module loads it at import and decodes exactly like an engine built from the same weights
+    (here written with the NEW weight-norm key spelling, parametrizations.weight.original0/1)."""
+    from project_morpheus_b200 import weights
+    renamed = {}
+    for k, v in state_dict_w1.items():
+        if k.endswith(".weight_g"):
+            k = k[:-9] + ".parametrizations.weight.original0"
+        elif k.endswith(".weight_v"):
+            k = k[:-9] + ".parametrizations.weight.original1"
+        renamed[k] = v
+    weights.save_checkpoint(str(tmp_path), renamed)
+    monkeypatch.setenv("ORPHEUS_SNAC_PATH", str(tmp_path))
+    monkeypatch.setenv("SNACB_NOISE", "off")
+    monkeypatch.setenv("SNACB_PRECISION", "fp16")
+    monkeypatch.delenv("SNACB_RANDOM_INIT", raising=False)
+    import importlib
+    import sys
+    sys.modules.pop("project_morpheus_b200.speechpipe", None)
+    speechpipe = importlib.import_module("project_morpheus_b200.speechpipe")
+    assert speechpipe.model_source == str(tmp_path) and speechpipe.snac_device == "cuda"
+    win = windows_tokens(1, 4, 321)[0].tolist()
+    got = speechpipe.convert_to_audio(win, 0)
+    want, st = engines("fp16").decode_windows(np.asarray([win], dtype=np.int32), noise="off")
+    assert st[0] == _lib.WIN_OK and got == want[0].tobytes()
+    sys.modules.pop("project_morpheus_b200.speechpipe", None)
