@@ -12,6 +12,9 @@ PyPI package ``snac`` (``requirements.txt:8`` -> ``snac>=1.2.1,<2``; model id
 stub it out (``tests/conftest.py:16-30``) and hold no golden vector for
 ``convert_to_audio`` / ``tokens_decoder``.  The oracle is therefore
 
+(``tests/test_oracle_vs_dac.py`` additionally checks the shared building blocks - Snake1d and the whole
+DecoderBlock - against the independent DAC implementation shipped in the ``transformers`` wheel.)
+
 * ``snac_ref``        - a restatement of the published SNAC-24k decode algorithm
                         (quantizer ``from_codes`` + decoder), anchored on the
                         reference's single call site
