@@ -33,6 +33,9 @@ constexpr int BK = 64;   // fp16 per k-block = one 128-byte swizzle span
 constexpr int kTcThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr uint32_t kLiveFlag = 0x40000000u;
 const bool g_no_ws = [] { const char* v = getenv("SNACB_NO_WS"); return v && v[0] == '1'; }();
+// cluster + TMA multicast of the A stream (opt-in: measured 1.47 vs 1.42 ms per tick - the layers are HBM-bound on the
+// fp32 residual stream, not on the L2 -> SM operand traffic)
+const bool g_ws_cluster = [] { const char* v = getenv("SNACB_WS_CLUSTER"); return v && v[0] == '1'; }();
 
 // ------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -71,6 +74,27 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+// Multicast variants (thread-block clusters): the tile lands at the same shared-memory offset of every CTA in
+// `mask` and completes the transaction on each destination CTA's own mbarrier at that offset.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
@@ -449,10 +473,14 @@ struct WsSmem {
   static constexpr int bytes(int K) { return K * 128 * 2 + kABytes + kStgBytes + kMetaBytes + 1024; }
 };
 
-template <int EPI>
+// CL > 1: the CL CTAs that own the CL output-channel slices of the same M tiles form a thread-block cluster and
+// share the operand stream - every k-block tile of A is fetched from L2 once (by CTA kb % CL) and multicast into
+// all CL shared memories, instead of CL times (the C = 512 layers are otherwise bound by that L2 -> SM traffic).
+template <int EPI, int CL>
 __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_ws(const __grid_constant__ CUtensorMap tmA,
                                                          const __grid_constant__ CUtensorMap tmW, const TcDev a) {
   constexpr int BN = 128;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
   const int KB = a.K / BK;
@@ -473,15 +501,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_ws(const __grid_constant
 
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&bars[0]), 1);
-    for (int i = 0; i < kWsStages; ++i) { mbar_init(smem_u32(&bars[1 + i]), 1); mbar_init(smem_u32(&bars[5 + i]), 1); }
+    for (int i = 0; i < kWsStages; ++i) { mbar_init(smem_u32(&bars[1 + i]), 1); mbar_init(smem_u32(&bars[5 + i]), CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars[9 + i]), 1); mbar_init(smem_u32(&bars[11 + i]), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * BN);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -494,7 +524,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_ws(const __grid_constant
           const int st = it % kWsStages;
           mbar_wait(smem_u32(&bars[5 + st]), ((it / kWsStages) & 1) ^ 1);
           mbar_arrive_expect_tx(smem_u32(&bars[1 + st]), BM * BK * 2);
-          tma_load_2d(smem_u32(sA + st * (BM * 128)), &tmA, smem_u32(&bars[1 + st]), kb * BK, mt * BM);
+          if (CL == 1) tma_load_2d(smem_u32(sA + st * (BM * 128)), &tmA, smem_u32(&bars[1 + st]), kb * BK, mt * BM);
+          else if ((uint32_t)(it % CL) == crank)
+            tma_load_2d_mc(smem_u32(sA + st * (BM * 128)), &tmA, smem_u32(&bars[1 + st]), kb * BK, mt * BM, kMask);
         }
       }
     }
@@ -516,7 +548,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_ws(const __grid_constant
           const uint64_t db = umma_desc_k_sw128(smem_u32(sW + kb * (BN * 128)));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_base + buf * BN, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
-          umma_commit(smem_u32(&bars[5 + st]));
+          if (CL == 1) umma_commit(smem_u32(&bars[5 + st]));
+          else umma_commit_mc(smem_u32(&bars[5 + st]), kMask);  // the stage is free once ALL CTAs of the cluster consumed it
         }
         umma_commit(smem_u32(&bars[9 + buf]));
       }
@@ -627,6 +660,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_ws(const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // nobody leaves while a peer may still write into its shared memory / barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * BN);
@@ -893,18 +927,6 @@ cudaError_t launch_tc_bn(int epi, const CUtensorMap& ma, const CUtensorMap& mw, 
   }
 }
 
-template <int EPI>
-cudaError_t launch_ws_t(const CUtensorMap& ma, const CUtensorMap& mw, const TcDev& d, int grid, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_ws<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsSmem::bytes(512));
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  k_gemm_ws<EPI><<<grid, kTcThreads, WsSmem::bytes(d.K), st>>>(ma, mw, d);
-  return cudaGetLastError();
-}
-
 int sm_count() {
   static int n = [] {
     int dev = 0, v = 148;
@@ -913,6 +935,47 @@ int sm_count() {
     return v;
   }();
   return n;
+}
+
+template <int EPI, int CL>
+cudaError_t launch_ws_t(const CUtensorMap& ma, const CUtensorMap& mw, const TcDev& d, int n_slices, cudaStream_t st) {
+  static int max_p = 0;  // co-resident clusters (CL > 1) / CTAs per slice (CL == 1)
+  if (!max_p) {
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_ws<EPI, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsSmem::bytes(512));
+    if (e != cudaSuccess) return e;
+    if (CL > 1) {
+      cudaLaunchConfig_t q{};
+      q.gridDim = dim3(CL * 64); q.blockDim = dim3(kTcThreads); q.dynamicSmemBytes = WsSmem::bytes(512);
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      q.attrs = at; q.numAttrs = 1;
+      int n = 0;
+      e = cudaOccupancyMaxActiveClusters(&n, k_gemm_ws<EPI, CL>, &q);
+      if (e != cudaSuccess || n < 1) { cudaGetLastError(); return cudaErrorNotSupported; }
+      max_p = n;
+    } else {
+      max_p = std::max(1, sm_count() / std::max(1, n_slices));
+    }
+  }
+  const int P = (CL > 1) ? max_p : std::max(1, sm_count() / n_slices);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(n_slices * P)); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = WsSmem::bytes(d.K); cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = (CL > 1) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k_gemm_ws<EPI, CL>, ma, mw, d);
+}
+template <int EPI>
+cudaError_t launch_ws_e(const CUtensorMap& ma, const CUtensorMap& mw, const TcDev& d, int n_slices, cudaStream_t st) {
+  if (g_ws_cluster && n_slices == 4) {
+    cudaError_t e = launch_ws_t<EPI, 4>(ma, mw, d, n_slices, st);
+    if (e != cudaErrorNotSupported) return e;
+  }
+  if (g_ws_cluster && n_slices == 2) {
+    cudaError_t e = launch_ws_t<EPI, 2>(ma, mw, d, n_slices, st);
+    if (e != cudaErrorNotSupported) return e;
+  }
+  return launch_ws_t<EPI, 1>(ma, mw, d, n_slices, st);
 }
 
 template <int BN>
@@ -977,9 +1040,9 @@ cudaError_t launch_gemm_tc(const GroupCtx& g, const TcGemmArgs& a) {
   d.sn_alpha = a.sn_alpha; d.sn_inv = a.sn_inv; d.R = a.R; d.r_lo = a.r_r.lo; d.r_rows = a.r_r.n(); d.ldr = a.ldr;
   d.noise = a.noise; d.up = a.up;
   if (ws) {
-    const int n_slices = a.N / 128, P = std::max(1, sm_count() / n_slices);
-    cudaError_t e = (a.epi == EPI_RESID) ? launch_ws_t<EPI_RESID>(ma, mw, d, n_slices * P, g.stream)
-                                         : launch_ws_t<EPI_NOISE>(ma, mw, d, n_slices * P, g.stream);
+    const int n_slices = a.N / 128;
+    cudaError_t e = (a.epi == EPI_RESID) ? launch_ws_e<EPI_RESID>(ma, mw, d, n_slices, g.stream)
+                                         : launch_ws_e<EPI_NOISE>(ma, mw, d, n_slices, g.stream);
     ++*g.launches;
     return e;
   }
