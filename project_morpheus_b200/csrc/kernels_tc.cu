@@ -595,15 +595,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_ws(const __grid_constant
       int oi4[4], ri4[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { oi4[i] = m_out[q * 32 + r8 + 8 * i]; ri4[i] = m_res[q * 32 + r8 + 8 * i]; }
-      float4 res[4];
-      auto load_res = [&](int h) {
+      // the whole residual / carrier block of this warp (4 column steps x 4 rows per lane) is requested before the
+      // accumulator is waited for: one DRAM latency per tile instead of one per column step
+      float4 res[NH][4];
+#pragma unroll
+      for (int h = 0; h < NH; ++h)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (oi4[i] >= 0) res[i] = __ldg(reinterpret_cast<const float4*>(a.R + (size_t)ri4[i] * a.ldr + ocol0 + h * 16));
+          res[h][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (oi4[i] >= 0) res[h][i] = __ldg(reinterpret_cast<const float4*>(a.R + (size_t)ri4[i] * a.ldr + ocol0 + h * 16));
         }
-      };
-      load_res(0);
       mbar_wait(smem_u32(&bars[9 + buf]), (ti >> 1) & 1);
       tc_fence_after();
 #pragma unroll
@@ -634,11 +635,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_ws(const __grid_constant
           if (EPI == EPI_NOISE) {
             const float nz = m_nz[q * 32 + r8 + 8 * i];
             const float2 n2 = make_float2(nz, nz);
-            const float2 lo = __ffma2_rn(n2, make_float2(x.x, x.y), make_float2(res[i].x, res[i].y));
-            const float2 hi = __ffma2_rn(n2, make_float2(x.z, x.w), make_float2(res[i].z, res[i].w));
+            const float2 lo = __ffma2_rn(n2, make_float2(x.x, x.y), make_float2(res[h][i].x, res[h][i].y));
+            const float2 hi = __ffma2_rn(n2, make_float2(x.z, x.w), make_float2(res[h][i].z, res[h][i].w));
             x = make_float4(lo.x, lo.y, hi.x, hi.y);
           } else {
-            x = add4(x, res[i]);
+            x = add4(x, res[h][i]);
           }
           if (!live) x = make_float4(0.f, 0.f, 0.f, 0.f);
           const size_t o = (size_t)oi * a.ldo + ocol;
@@ -652,7 +653,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_gemm_ws(const __grid_constant
             store_half4(a.out16 + o, x);
           }
         }
-        if (h + 1 < NH) load_res(h + 1);
       }
       tc_fence_before();
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[11 + buf])) : "memory");  // accumulator free
