@@ -379,12 +379,17 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
       ProfScope ps(e, a.epi == EPI_CONVT ? KC_CONVT : KC_GEMM1, flops, by, st);
       ce = launch_gemm_tc(g, a);
     };
-    {
-      ProfScope ps(e, KC_CODES, 2.0 * 24 * kLatent * n * P.z.n(), 4.0 * kLatent * n * P.z.n(), st);
-      launch_from_codes(g, W.q, c0, c1, c2, pitch0, P.z, Z);
-    }
-    tap(e, 0, Z, P.z, kLatent, n, first, st);
-    {  // decoder.model.0: depthwise k7 -> fp16 operand of the 1x1
+    if (codes_head_supported(P.z) && e->tap_stage != 0) {  // from_codes + decoder.model.0 fused, z stays on chip
+      const double el = (double)n * P.h.n() * kLatent;
+      ProfScope ps(e, KC_CODES, 2.0 * 24 * kLatent * n * P.z.n() + el * 14.0, 2.0 * el + 28.0 * n * P.z.n(), st);
+      launch_codes_head(g, W.q, c0, c1, c2, pitch0, P.z, P.h, W.head_dw_w, W.head_dw_b, P16);
+    } else {
+      {
+        ProfScope ps(e, KC_CODES, 2.0 * 24 * kLatent * n * P.z.n(), 4.0 * kLatent * n * P.z.n(), st);
+        launch_from_codes(g, W.q, c0, c1, c2, pitch0, P.z, Z);
+      }
+      tap(e, 0, Z, P.z, kLatent, n, first, st);
+      // decoder.model.0: depthwise k7 -> fp16 operand of the 1x1
       DwArgs d{Z, P.z, nullptr, P.h, kLatent, 1, 1, W.head_dw_w, W.head_dw_b, nullptr, nullptr, nullptr, nullptr};
       const double el = (double)n * P.h.n() * kLatent;
       ProfScope ps(e, KC_DW, el * 14.0, 4.0 * (double)n * P.z.n() * kLatent + 2.0 * el, st);

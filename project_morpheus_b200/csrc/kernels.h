@@ -104,6 +104,10 @@ struct RuTcArgs {
 };
 bool ru_tc_supported(int C, bool persistent);
 cudaError_t launch_ru_tc(const GroupCtx& g, const RuTcArgs& a);
+// from_codes + decoder.model.0 (depthwise k7) -> fp16 operand of the 768->1024 GEMM, z never leaves the SM
+bool codes_head_supported(Rng z);
+void launch_codes_head(const GroupCtx& g, const QuantW& q, const int32_t* c0, const int32_t* c1, const int32_t* c2, int pitch0,
+                       Rng z, Rng h, const float* w7, const float* dw_b, __half* out);
 void launch_dwconv_half(const GroupCtx& g, const DwArgs& a, __half* out16);  // plain dw k7 -> fp16 (decoder head)
 void launch_to_half(const float* in, __half* out, size_t n, cudaStream_t st);
 

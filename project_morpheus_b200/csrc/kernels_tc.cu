@@ -1267,15 +1267,18 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
     const int colb = half * (C / 2) + c4 * 4;
     const size_t ob = ((size_t)item * a.out_rows + orow_b) * C + colb;
     const float* rp = a.x + ((size_t)item * a.in_rows + (a.out_lo + orow_b - a.in_lo)) * C + colb;
-    float4 res[4];
+    // residual rows of this lane, requested one column step ahead (two steps ahead measured slower: register spills)
+    constexpr int PD = 1;
+    float4 res[PD][4];
     auto load_res = [&](int h) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if ((vmask >> i) & 1u) res[i] = __ldg(reinterpret_cast<const float4*>(rp + i * 8 * C + h * 16));
+        res[h % PD][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((vmask >> i) & 1u) res[h % PD][i] = __ldg(reinterpret_cast<const float4*>(rp + i * 8 * C + h * 16));
       }
     };
-    load_res(0);
+#pragma unroll
+    for (int h = 0; h < PD && h < NH; ++h) load_res(h);
     mbar_wait(smem_u32(&bars[1]), 0);
     tc_fence_after();
 #pragma unroll
@@ -1304,7 +1307,7 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
           if (TAIL) *reinterpret_cast<float4*>(sTail + (q * 32 + r8 + 8 * i) * kTailPitch + colb + h * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
           continue;
         }
-        float4 x = add4(add4(v[i], b4), res[i]);
+        float4 x = add4(add4(v[i], b4), res[h % PD][i]);
         if (!((lmask >> i) & 1u)) x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (TAIL) {  // Snake of the decoder tail, kept on chip for the final conv
           const float2 lo = snake2(make_float2(x.x, x.y), make_float2(al.x, al.y), make_float2(iv.x, iv.y));
@@ -1322,7 +1325,7 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
           store_half4(a.out16 + ob + i * 8 * C + h * 16, x);
         }
       }
-      if (h + 1 < NH) load_res(h + 1);
+      if (h + PD < NH) load_res(h + PD);
     }
     tc_fence_before();
     if (TAIL) {
@@ -1672,6 +1675,95 @@ cudaError_t launch_ru_tc(const GroupCtx& g, const RuTcArgs& a) {
   }
   ++*g.launches;
   return e;
+}
+
+namespace {
+// ============================================================================ from_codes + decoder head depthwise
+// z = sum_l outproj_l(codebook_l[code_l]) (strides 4/2/1) for the latent rows of one item, kept in shared memory,
+// then decoder.model.0 (depthwise k7) straight to the fp16 operand of the 768->1024 GEMM.  One CTA per item, a
+// thread owns 3 channels and keeps their 3 x 8 out-projection weights in registers across all rows (the standalone
+// k_from_codes re-reads them for every row and writes z to HBM only for k_dwconv to read it back).
+__global__ void __launch_bounds__(256) k_codes_head(const Item* items, int base, int out_len, int T0, QuantW q,
+                                                    const int32_t* __restrict__ c0, const int32_t* __restrict__ c1,
+                                                    const int32_t* __restrict__ c2, int pitch0, Rng z, Rng h,
+                                                    const float* __restrict__ w7, const float* __restrict__ dw_b,
+                                                    __half* __restrict__ out) {
+  extern __shared__ float zs[];          // [z rows][768] then [z rows][24] embeddings
+  const int zr = z.n(), hr = h.n();
+  float* es = zs + (size_t)zr * kLatent;
+  const int i = blockIdx.x, tid = threadIdx.x;
+  const ItemRef it = get_item(items, base, i, out_len);
+  for (int e = tid; e < zr * 24; e += 256) {
+    const int j = e / 24, r = e - j * 24, l = r >> 3, d = r & 7;
+    const int u = z.lo + j + it.shift0;
+    float v = 0.0f;
+    if (u >= 0 && u < T0) {
+      int k = (l == 0) ? c0[(size_t)it.code_row * pitch0 + (u >> 2)]
+              : (l == 1) ? c1[(size_t)it.code_row * 2 * pitch0 + (u >> 1)] : c2[(size_t)it.code_row * 4 * pitch0 + u];
+      k = min(max(k, 0), SNACB_CODEBOOK_SIZE - 1);  // rejected windows stay memory-safe
+      v = q.codebook[l][(size_t)k * 8 + d];
+    }
+    es[e] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int cc = 0; cc < 3; ++cc) {
+    const int c = tid + cc * 256;
+    float w[24], bsum = 0.0f;
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+      const float4 a = *reinterpret_cast<const float4*>(q.w[l] + (size_t)c * 8), b = *reinterpret_cast<const float4*>(q.w[l] + (size_t)c * 8 + 4);
+      w[8 * l] = a.x; w[8 * l + 1] = a.y; w[8 * l + 2] = a.z; w[8 * l + 3] = a.w;
+      w[8 * l + 4] = b.x; w[8 * l + 5] = b.y; w[8 * l + 6] = b.z; w[8 * l + 7] = b.w;
+    }
+    for (int j = 0; j < zr; ++j) {
+      const int u = z.lo + j + it.shift0;
+      float acc = 0.0f;
+      if (u >= 0 && u < T0) {
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {  // same association as k_from_codes: per level dot product + bias, summed over levels
+          float d = w[8 * l] * es[j * 24 + 8 * l];
+#pragma unroll
+          for (int t = 1; t < 8; ++t) d = fmaf(w[8 * l + t], es[j * 24 + 8 * l + t], d);
+          acc += d + q.b[l][c];
+        }
+      }
+      zs[(size_t)j * kLatent + c] = acc;
+    }
+    (void)bsum;
+  }
+  __syncthreads();
+  for (int e = tid; e < hr * kLatent; e += 256) {
+    const int j = e / kLatent, c = e - j * kLatent;
+    const int t_rel = h.lo + j, t_abs = t_rel + it.shift0;
+    float acc = 0.0f;
+    if (t_abs >= 0 && t_abs < T0) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        const int r = t_rel + k - 3 - z.lo;
+        const float v = (r >= 0 && r < zr) ? zs[(size_t)r * kLatent + c] : 0.0f;
+        acc = fmaf(w7[k * kLatent + c], v, acc);
+      }
+      acc += dw_b[c];
+    }
+    out[((size_t)i * hr + j) * kLatent + c] = __float2half_rn(acc);
+  }
+}
+
+}  // namespace
+
+bool codes_head_supported(Rng z) { return (size_t)z.n() * (kLatent + 24) * sizeof(float) <= 200 * 1024; }
+
+void launch_codes_head(const GroupCtx& g, const QuantW& q, const int32_t* c0, const int32_t* c1, const int32_t* c2, int pitch0,
+                       Rng z, Rng h, const float* w7, const float* dw_b, __half* out) {
+  const size_t smem = (size_t)z.n() * (kLatent + 24) * sizeof(float);
+  static size_t max_set = 48 * 1024;
+  if (smem > max_set) {
+    cudaFuncSetAttribute(k_codes_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    max_set = smem;
+  }
+  k_codes_head<<<g.n_items, 256, smem, g.stream>>>(g.items, g.base, g.out_len, g.T0, q, c0, c1, c2, pitch0, z, h, w7, dw_b, out);
+  ++*g.launches;
 }
 
 namespace {
