@@ -293,6 +293,27 @@ def run_ours(args) -> None:
             extra[name] = {"p50_ms": 1e3 * p50, "p95_ms": 1e3 * sorted(lat)[int(0.95 * (len(lat) - 1))],
                            "audio_s_per_s": n * AUDIO_S_PER_WINDOW / p50, "reps": len(lat)}
 
+        # p50 of the reference-shaped Python call itself: speechpipe.convert_to_audio(28 tokens) -> bytes
+        try:
+            os.environ.setdefault("SNACB_RANDOM_INIT", "0:w1")
+            os.environ.setdefault("SNACB_PRECISION", args.precision)
+            import importlib
+            sp_mod = importlib.import_module("project_morpheus_b200.speechpipe")
+            win = tok_host[0].tolist()
+            for i in range(10):
+                sp_mod.convert_to_audio(win, i)
+            lat = []
+            for i in range(args.latency_reps * 5):
+                t0 = time.perf_counter()
+                out_b = sp_mod.convert_to_audio(win, i)
+                lat.append(time.perf_counter() - t0)
+            assert out_b is not None and len(out_b) == 4096
+            extra["convert_to_audio_call"] = {"p50_ms": 1e3 * statistics.median(lat),
+                                              "p95_ms": 1e3 * sorted(lat)[int(0.95 * (len(lat) - 1))], "reps": len(lat),
+                                              "note": "project_morpheus_b200.speechpipe.convert_to_audio, Python list in -> bytes out"}
+        except Exception as exc:  # noqa: BLE001
+            extra["convert_to_audio_call"] = {"error": repr(exc)}
+
         # BASELINE config 5 pattern: ragged ticks (per stream 0/1/2 pending windows, 1 / 4 / 7 frames each)
         if args.ragged_streams > 0:
             rng = np.random.default_rng(2024)
@@ -390,6 +411,42 @@ def run_ours(args) -> None:
                         for k, v in stats.items() if v["launches"]},
         })
 
+    gpu_torch = None
+    if world == 1 and not args.no_cpu_baseline:
+        # second baseline: the same restated reference algorithm run by stock PyTorch/cuDNN on this B200,
+        # the way the reference drives it (one B=1 decode per window) and, for information, as one B=64 batch
+        try:
+            from oracle import snac_ref
+            torch.set_grad_enabled(False)
+            ref_model = snac_ref.SNAC.from_state_dict(weights.random_state_dict(0, "w1")).eval().to(dev)
+            ref_model.set_noise("randn")
+            tk = torch.from_numpy(tok_host[:64].astype(np.int64)).to(dev).reshape(64, F, 7)
+            cs = [tk[:, :, 0], tk[:, :, [1, 4]].reshape(64, 2 * F), tk[:, :, [2, 3, 5, 6]].reshape(64, 4 * F)]
+            def one(b0, b1):
+                y = ref_model.decode([c[b0:b1] for c in cs])[:, :, 2048:4096]
+                return (y * 32767).to(torch.int16).cpu()
+            for _ in range(3):
+                one(0, 1)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            nrep = 32
+            for i in range(nrep):
+                one(i, i + 1)
+            dt1 = (time.perf_counter() - t0) / nrep
+            one(0, 64)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                one(0, 64)
+            dt64 = (time.perf_counter() - t0) / 3
+            gpu_torch = {"kind": "oracle port on stock PyTorch CUDA (cuDNN/ATen), not this repo's kernels",
+                         "b1_ms_per_window": 1e3 * dt1, "b1_audio_s_per_s": AUDIO_S_PER_WINDOW / dt1,
+                         "b64_ms_per_tick": 1e3 * dt64, "b64_audio_s_per_s": 64 * AUDIO_S_PER_WINDOW / dt64}
+            del ref_model
+            torch.cuda.empty_cache()
+        except Exception as exc:  # noqa: BLE001
+            gpu_torch = {"error": repr(exc)}
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cw, ctimes, cores = cpu_reference_run(args.ref_windows, F, steps=50, warmup=1, budget_s=args.cpu_budget)
@@ -413,7 +470,7 @@ def run_ours(args) -> None:
                 "d2h_bytes_per_step": int(S * 2048 * 2 + S * 4), "ms_per_step": tot_e2e_ms / K,
                 "api": "snacb_decode_windows_host via SnacEngine.decode_windows (pinned host tokens -> PCM on host)"},
         "gpu_launches": int(launches), "wall_s_device_region": wall_dev, "clocks": clocks,
-        "roofline": roof, "cpu_baseline": cpu, "latency": extra, "checksum": checksum,
+        "roofline": roof, "cpu_baseline": cpu, "gpu_torch_baseline": gpu_torch, "latency": extra, "checksum": checksum,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
