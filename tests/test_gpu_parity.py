@@ -528,3 +528,34 @@ def test_orpheus_snac_path_checkpoint_dir(tmp_path, state_dict_w1, monkeypatch, 
     want, st = engines("fp16").decode_windows(np.asarray([win], dtype=np.int32), noise="off")
     assert st[0] == _lib.WIN_OK and got == want[0].tobytes()
     sys.modules.pop("project_morpheus_b200.speechpipe", None)
+
+
+def test_soak_varying_shapes_graph_cache_and_regrowth(state_dict_w1):
+    """Many host-API ticks of changing size and raggedness on ONE engine (staging / workspace re-allocation
+    invalidates captured CUDA graphs; shapes recur so graphs are captured, replayed and re-captured) must give
+    the same bytes as a fresh engine decoding each tick in isolation through the never-graphed device API."""
+    from project_morpheus_b200.engine import SnacEngine
+    eng = SnacEngine(state_dict_w1, device=0, precision="fp16")
+    ref = SnacEngine(state_dict_w1, device=0, precision="fp16")
+    rng = np.random.default_rng(42)
+    sizes = [3, 17, 3, 64, 17, 3, 300, 64, 17, 3, 5, 300, 64, 1, 1, 1, 17, 129, 129, 3]
+    try:
+        for step, n in enumerate(sizes):
+            frames = int(rng.choice([4, 7]))
+            tok = windows_tokens(n, frames, base_stream=3000 + 7 * step)
+            keys = (np.arange(n) + 11 * step).astype(np.uint64)
+            ragged = (step % 4 == 3)
+            if ragged:
+                lens = rng.choice([7, 28, 49, 6, 7 * frames], size=n).astype(np.int32)
+                lens = np.minimum(lens, tok.shape[1])
+                pcm, st = eng.decode_windows(tok, ntok=lens.tolist(), noise="philox", seed=step, keys=keys)
+                want, wst = ref.decode_windows_device(torch.from_numpy(tok).cuda(), ntok=lens.tolist(), noise="philox", seed=step, keys=keys)
+            else:
+                pcm, st = eng.decode_windows(tok, noise="philox", seed=step, keys=keys)
+                want, wst = ref.decode_windows_device(torch.from_numpy(tok).cuda(), noise="philox", seed=step, keys=keys)
+            assert np.array_equal(st, wst.cpu().numpy()), step
+            assert np.array_equal(pcm, want.cpu().numpy()), step
+        assert eng.graph_launch_count > 0
+    finally:
+        eng.close()
+        ref.close()

@@ -175,3 +175,30 @@ def test_adapter_registers_like_reference_registry():
     assert isinstance(ad, SnacB200Adapter) and ad.voice == "leo" and ad.use_batching
     with pytest.raises(RuntimeError):
         asyncio.run(ad.pull(8))  # no token source configured: fails loudly
+
+
+def test_planner_and_scheduler_property_random_streams():
+    """Property test (hypothesis): for arbitrary streams of valid / zero / negative / out-of-range / malformed /
+    multi-token strings the product's WindowPlanner (per stream) and TickScheduler (batched) emit exactly the chunk
+    sequence of the oracle's restatement of tokens_decoder (itself proven identical to the verbatim reference)."""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as stx
+
+    token = stx.one_of(
+        stx.integers(min_value=0, max_value=7 * 4096 + 30).map(lambda n: f"<custom_token_{n}>"),
+        stx.sampled_from(["", "junk", "<custom_token_", "<custom_token_x>", "<custom_token_10>", "<custom_token_11><custom_token_4107>",
+                          " <custom_token_20000> ", "<custom_token_99999>"]),
+    )
+
+    @settings(max_examples=60, deadline=None)
+    @given(stx.lists(token, min_size=0, max_size=140))
+    def check(strings):
+        want = list(sp.decode_stream(strings, fake_convert))
+        sched = TickScheduler(fake_batch)
+        sched.add_stream("s")
+        sched.push_many("s", strings)
+        sched.finish("s")
+        sched.drain()
+        assert sched.pop_audio("s") == want
+
+    check()
