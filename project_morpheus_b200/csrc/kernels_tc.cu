@@ -33,6 +33,7 @@ constexpr int BK = 64;   // fp16 per k-block = one 128-byte swizzle span
 constexpr int kTcThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr uint32_t kLiveFlag = 0x40000000u;
 const bool g_no_ws = [] { const char* v = getenv("SNACB_NO_WS"); return v && v[0] == '1'; }();
+const bool g_convt_p = [] { const char* v = getenv("SNACB_CONVT_PERSISTENT"); return !(v && v[0] == '0'); }();
 // cluster + TMA multicast of the A stream (opt-in: measured 1.47 vs 1.42 ms per tick - the layers are HBM-bound on the
 // fp32 residual stream, not on the L2 -> SM operand traffic)
 const bool g_ws_cluster = [] { const char* v = getenv("SNACB_WS_CLUSTER"); return v && v[0] == '1'; }();
@@ -927,6 +928,165 @@ cudaError_t launch_tc_bn(int epi, const CUtensorMap& ma, const CUtensorMap& mw, 
   }
 }
 
+// ============================================================================ persistent ConvTranspose1d GEMM
+// The wide transposed convs (decoder blocks 0 / 1: K = 2*Cin = 2048 / 1024, N = s*Cout = 4096 / 2048) are the
+// tensor-bound layers.  Persistent variant of k_gemm_tc<128, EPI_CONVT>: one CTA per SM walks (m tile, phase/n
+// tile) pairs round-robin, A and W stream through a 4-stage TMA ring that never drains between tiles, and two
+// TMEM accumulators let the 8 epilogue warps (bias, fp32 + fp16 stores) work on tile i while the MMAs of tile
+// i+1 run.
+struct CtpSmem {
+  static constexpr int kStages = 4;
+  static constexpr int kStageBytes = BM * BK * 2 + 128 * BK * 2;
+  static constexpr int kStgBytes = 8 * 32 * 16 * 4;
+  static constexpr int kBytes = kStages * kStageBytes + kStgBytes + 2 * BM * 4 + 256 + 1024;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1) k_convt_p(const __grid_constant__ CUtensorMap tmA,
+                                                         const __grid_constant__ CUtensorMap tmW, const TcDev a,
+                                                         const int n_tiles, const int total_tiles) {
+  constexpr int BN = 128;
+  using S = CtpSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_align1024(smem_raw);
+  float* sStg = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes);
+  int* meta = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(sStg) + S::kStgBytes);  // [2][BM] output row of each tile row
+  uint64_t* bars = reinterpret_cast<uint64_t*>(meta + 2 * BM);
+  // bars: [0..3] full, [4..7] empty, [8..9] t_full, [10..11] t_empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long Mtot = (long long)a.n_items * a.a_rows;
+  const int kb_per_seg = a.K / BK, num_kb = 2 * kb_per_seg;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S::kStages; ++i) { mbar_init(smem_u32(&bars[i]), 1); mbar_init(smem_u32(&bars[4 + i]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars[8 + i]), 1); mbar_init(smem_u32(&bars[10 + i]), 256); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t % n_tiles, mt = t / n_tiles;
+        const int n0 = nt * BN, m0 = mt * BM;
+        const int phase = n0 / a.Cout, delta = (phase < a.s - a.p) ? -1 : 1;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int st = it % S::kStages;
+          mbar_wait(smem_u32(&bars[4 + st]), ((it / S::kStages) & 1) ^ 1);
+          const uint32_t full = smem_u32(&bars[st]);
+          const uint32_t sa = smem_u32(smem + st * S::kStageBytes), sb = sa + BM * BK * 2;
+          const int seg = kb / kb_per_seg, kk = (kb - seg * kb_per_seg) * BK;
+          mbar_arrive_expect_tx(full, S::kStageBytes);
+          tma_load_2d(sa, &tmA, full, kk, m0 + (seg ? delta : 0));
+          tma_load_2d(sb, &tmW, full, seg * a.K + kk, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BN);
+      int it = 0, ti = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+        const int buf = ti & 1;
+        mbar_wait(smem_u32(&bars[10 + buf]), ((ti >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int st = it % S::kStages;
+          mbar_wait(smem_u32(&bars[st]), (it / S::kStages) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + st * S::kStageBytes), sb = sa + BM * BK * 2;
+          const uint64_t da = umma_desc_k_sw128(sa), db = umma_desc_k_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_base + buf * BN, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          umma_commit(smem_u32(&bars[4 + st]));
+        }
+        umma_commit(smem_u32(&bars[8 + buf]));
+      }
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int c4 = lane & 3, r8 = lane >> 2;
+    float* stg = sStg + (warp - 2) * (32 * 16);
+    float* st_p = stg + lane * 16;
+    const int st_x = (lane >> 1) & 3;
+    const float* ld_p = stg + r8 * 16 + ((c4 ^ ((r8 >> 1) & 3)) << 2);
+    constexpr int NH = BN / 32;
+    int ti = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+      const int nt = t % n_tiles, mt = t / n_tiles;
+      const int n0 = nt * BN, phase = n0 / a.Cout;
+      const int buf = ti & 1;
+      int* m_out = meta + buf * BM;
+      if (half == 0) {
+        const int trow = q * 32 + lane;
+        const long long gm = (long long)mt * BM + trow;
+        int oi = -1;
+        if (gm < Mtot) {
+          const int item = (int)(gm / a.a_rows), j = (int)(gm - (long long)item * a.a_rows);
+          const ItemRef itr = get_item(a.items, a.base, item, a.out_len);
+          const int t_rel = (a.a_lo + j) * a.s + phase;
+          const int orow = t_rel - a.o_lo;
+          if (orow >= 0 && orow < a.o_rows) {
+            const int t_abs = t_rel + itr.shift0 * a.up;
+            oi = item * a.o_rows + orow;
+            if (!((t_abs >= 0) && (t_abs < a.T0 * a.up))) oi |= (int)kLiveFlag;
+          }
+        }
+        m_out[trow] = oi;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      int oi4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) oi4[i] = m_out[q * 32 + r8 + 8 * i];
+      const int ocol0 = n0 - phase * a.Cout + half * (BN / 2) + c4 * 4;
+      mbar_wait(smem_u32(&bars[8 + buf]), (ti >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * (BN / 2) + h * 16), r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(st_p + ((j ^ st_x) << 2)) =
+              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                          __uint_as_float(r[4 * j + 3]));
+        __syncwarp();
+        float4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(ld_p + i * 128);
+        __syncwarp();
+        const int ocol = ocol0 + h * 16;
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + ocol));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int oi = oi4[i];
+          if (oi < 0) continue;
+          const bool live = !(oi & (int)kLiveFlag);
+          oi &= (int)(kLiveFlag - 1);
+          float4 x = add4(v[i], b4);
+          if (!live) x = make_float4(0.f, 0.f, 0.f, 0.f);
+          const size_t o = (size_t)oi * a.ldo + ocol;
+          if (a.out32) *reinterpret_cast<float4*>(a.out32 + o) = x;
+          if (a.out16) store_half4(a.out16 + o, x);
+        }
+      }
+      tc_fence_before();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[10 + buf])) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
 int sm_count() {
   static int n = [] {
     int dev = 0, v = 148;
@@ -1045,6 +1205,21 @@ cudaError_t launch_gemm_tc(const GroupCtx& g, const TcGemmArgs& a) {
                                          : launch_ws_e<EPI_NOISE>(ma, mw, d, n_slices, g.stream);
     ++*g.launches;
     return e;
+  }
+  if (g_convt_p && a.epi == EPI_CONVT && bn == 128 && !a.sn_alpha) {
+    const int n_tiles = a.N / 128, m_tiles = (int)((Mtot + BM - 1) / BM);
+    const long long total = (long long)n_tiles * m_tiles;
+    if (total >= 4LL * sm_count()) {
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaError_t e0 = cudaFuncSetAttribute(k_convt_p, cudaFuncAttributeMaxDynamicSharedMemorySize, CtpSmem::kBytes);
+        if (e0 != cudaSuccess) return e0;
+        attr_set = true;
+      }
+      k_convt_p<<<sm_count(), kTcThreads, CtpSmem::kBytes, g.stream>>>(ma, mw, d, n_tiles, (int)total);
+      ++*g.launches;
+      return cudaGetLastError();
+    }
   }
   dim3 grid((unsigned)((Mtot + BM - 1) / BM), (unsigned)(a.N / bn));
   cudaError_t e = (bn == 128) ? launch_tc_bn<128>(a.epi, ma, mw, d, grid, g.stream) : launch_tc_bn<64>(a.epi, ma, mw, d, grid, g.stream);
