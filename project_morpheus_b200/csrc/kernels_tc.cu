@@ -934,18 +934,18 @@ cudaError_t launch_tc_bn(int epi, const CUtensorMap& ma, const CUtensorMap& mw, 
 // tile) pairs round-robin, A and W stream through a 4-stage TMA ring that never drains between tiles, and two
 // TMEM accumulators let the 8 epilogue warps (bias, fp32 + fp16 stores) work on tile i while the MMAs of tile
 // i+1 run.
-struct CtpSmem {
+template <int BN> struct CtpSmem {
   static constexpr int kStages = 4;
-  static constexpr int kStageBytes = BM * BK * 2 + 128 * BK * 2;
+  static constexpr int kStageBytes = BM * BK * 2 + BN * BK * 2;
   static constexpr int kStgBytes = 8 * 32 * 16 * 4;
   static constexpr int kBytes = kStages * kStageBytes + kStgBytes + 2 * BM * 4 + 256 + 1024;
 };
 
+template <int BN>
 __global__ void __launch_bounds__(kTcThreads, 1) k_convt_p(const __grid_constant__ CUtensorMap tmA,
                                                          const __grid_constant__ CUtensorMap tmW, const TcDev a,
                                                          const int n_tiles, const int total_tiles) {
-  constexpr int BN = 128;
-  using S = CtpSmem;
+  using S = CtpSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
   float* sStg = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes);
@@ -1206,17 +1206,20 @@ cudaError_t launch_gemm_tc(const GroupCtx& g, const TcGemmArgs& a) {
     ++*g.launches;
     return e;
   }
-  if (g_convt_p && a.epi == EPI_CONVT && bn == 128 && !a.sn_alpha) {
-    const int n_tiles = a.N / 128, m_tiles = (int)((Mtot + BM - 1) / BM);
+  if (g_convt_p && a.epi == EPI_CONVT && a.Cout % 256 == 0 && !a.sn_alpha) {
+    // wide transposed convs: persistent kernel with 128 x 256 tiles (87 FLOP per byte of L2 -> SM operand traffic
+    // instead of 65 at 128 x 128, which caps those layers near 770 TFLOP/s)
+    const int n_tiles = a.N / 256, m_tiles = (int)((Mtot + BM - 1) / BM);
     const long long total = (long long)n_tiles * m_tiles;
-    if (total >= 4LL * sm_count()) {
+    CUtensorMap mw256;
+    if (total >= 2LL * sm_count() && get_tmap(a.W, a.N, nseg * a.K, 256, &mw256)) {
       static bool attr_set = false;
       if (!attr_set) {
-        cudaError_t e0 = cudaFuncSetAttribute(k_convt_p, cudaFuncAttributeMaxDynamicSharedMemorySize, CtpSmem::kBytes);
+        cudaError_t e0 = cudaFuncSetAttribute(k_convt_p<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, CtpSmem<256>::kBytes);
         if (e0 != cudaSuccess) return e0;
         attr_set = true;
       }
-      k_convt_p<<<sm_count(), kTcThreads, CtpSmem::kBytes, g.stream>>>(ma, mw, d, n_tiles, (int)total);
+      k_convt_p<256><<<sm_count(), kTcThreads, CtpSmem<256>::kBytes, g.stream>>>(ma, mw256, d, n_tiles, (int)total);
       ++*g.launches;
       return cudaGetLastError();
     }
