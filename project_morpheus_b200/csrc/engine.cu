@@ -74,6 +74,7 @@ struct snacb_engine {
   cudaEvent_t items_ev = nullptr;
   int64_t launches = 0;
   int prefetch_ahead = 0;  // SM count when L2 prefetch-ahead is on (SNACB_PREFETCH env, default on)
+  bool ru256 = false;      // decoder block 1 (C = 256) ResidualUnits through the persistent fused kernel (SNACB_RU256 env)
   // CUDA graphs of small host-API ticks (latency mode): key -> instantiated graph
   struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t gen = 0; int calls = 0; bool disabled = false; };
   std::map<std::vector<long long>, GraphEntry> graphs;
@@ -447,7 +448,7 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
       Rng cur = B.ct;
       for (int r = 0; r < 3 && ce == cudaSuccess; ++r) {
         const RuDev& R = Wb.ru[r];
-        const bool ru_persist = (e->cfg.flags & SNACB_FLAG_PERSISTENT_RU) != 0;
+        const bool ru_persist = (e->cfg.flags & SNACB_FLAG_PERSISTENT_RU) != 0 || (B.Cout == 256 && e->ru256);
         if (ru_tc_supported(B.Cout, ru_persist) && !(e->cfg.flags & SNACB_FLAG_NO_RU_FUSION)) {  // fused dw + 1x1 + residual (blocks 2, 3)
           const bool last = (r == 2) && (b < 3);
           const bool want32 = !last || e->tap_stage == sid + 4 + 2 * r;
@@ -592,6 +593,8 @@ int snacb_create(snacb_engine** out, const snacb_config* cfg) {
   {
     const char* pf = getenv("SNACB_PREFETCH");
     e->prefetch_ahead = (pf && pf[0] == '0') ? 0 : prop.multiProcessorCount;
+    const char* r2 = getenv("SNACB_RU256");
+    e->ru256 = r2 && r2[0] == '1';
     const char* gr = getenv("SNACB_GRAPHS");
     if (gr) e->graph_max_win = atoi(gr);  // 0 disables the CUDA-graph path
   }

@@ -33,6 +33,7 @@ constexpr int BK = 64;   // fp16 per k-block = one 128-byte swizzle span
 constexpr int kTcThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr uint32_t kLiveFlag = 0x40000000u;
 const bool g_no_ws = [] { const char* v = getenv("SNACB_NO_WS"); return v && v[0] == '1'; }();
+const bool g_cn_p = [] { const char* v = getenv("SNACB_CN_PERSISTENT"); return !(v && v[0] == '0'); }();
 const bool g_convt_p = [] { const char* v = getenv("SNACB_CONVT_PERSISTENT"); return !(v && v[0] == '0'); }();
 // cluster + TMA multicast of the A stream (opt-in: measured 1.47 vs 1.42 ms per tick - the layers are HBM-bound on the
 // fp32 residual stream, not on the L2 -> SM operand traffic)
@@ -53,6 +54,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Non-blocking probe (try_wait may suspend the thread for a while before it reports failure).
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
@@ -286,6 +301,7 @@ struct TcDev {
   const float* R; int r_lo, r_rows, ldr;
   NoiseSrc noise;
   int up;
+  int n_tiles;              // k_gemm_tc: N tiles per M tile (linear grid, N tile fastest)
 };
 
 template <int BN> struct TcSmem {
@@ -312,7 +328,8 @@ __global__ void __launch_bounds__(kTcThreads, 3) k_gemm_tc(const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kMaxStages + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  // N tile fastest: the CTAs sharing an operand tile run back to back (one HBM read, the rest L2 hits)
+  const int m0 = (blockIdx.x / a.n_tiles) * BM, n0 = (blockIdx.x % a.n_tiles) * BN;
   const long long Mtot = (long long)a.n_items * a.a_rows;
   int phase = 0, delta = 0;
   if (EPI == EPI_CONVT) { phase = n0 / a.Cout; delta = (phase < a.s - a.p) ? -1 : 1; }
@@ -692,8 +709,10 @@ __global__ void __launch_bounds__(kTcThreads, (BN == 64) ? 3 : 2) k_convt_noise_
   const uint32_t bar_y = smem_u32(&bars[2 * S::kMaxStages + 2]), bar_acc2 = smem_u32(&bars[2 * S::kMaxStages + 3]);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM;
-  const int phase = blockIdx.y;  // one N tile per polyphase component (BN == Cout)
+  // phase fastest: the s CTAs that read the same operand rows are launched back to back, so the tile comes
+  // from HBM once and from L2 s - 1 times (m-tile-fastest order re-read it from HBM for every phase)
+  const int phase = blockIdx.x % a.s;  // one N tile per polyphase component (BN == Cout)
+  const int m0 = (blockIdx.x / a.s) * BM;
   const int delta = (phase < a.s - a.p) ? -1 : 1;
   const long long Mtot = (long long)a.n_items * a.a_rows;
   const int kb_per_seg = a.K / BK;
@@ -1087,6 +1106,233 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_convt_p(const __grid_constant
   }
 }
 
+// ============================================================================ persistent ConvT + NoiseBlock
+// Same math as k_convt_noise_tc, one CTA per SM walking (m tile, phase) pairs (phase fastest: the s CTAs
+// working on one m tile at a time share its operand rows through L2).  The per-tile latencies of the
+// one-shot kernel - launch, barrier / TMEM setup, pipeline fill, the W_n load between the two chains -
+// are paid once per SM, and the accumulator pair (D1 conv, D2 noise GEMM) is double-buffered in TMEM so
+// the conv MMAs of tile i+1 run under the two epilogue phases of tile i.
+template <int BN> struct CnpSmem {
+  static constexpr int kStages = (BN == 64) ? 6 : 4;
+  static constexpr int kStageBytes = BM * BK * 2 + BN * BK * 2;
+  static constexpr int kWnBytes = BN * BN * 2;
+  static constexpr int kYBytes = BM * BN * 2;
+  static constexpr int kStgBytes = 8 * 32 * 16 * 4;
+  static constexpr int kMetaBytes = 2 * BM * 4;
+  static constexpr int kBytes = kStages * kStageBytes + kWnBytes + kYBytes + kStgBytes + kMetaBytes + 256 + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kTcThreads, 1) k_convt_noise_p(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmW,
+                                                               const __grid_constant__ CUtensorMap tmN, const TcDev a,
+                                                               const int total_tiles) {
+  using S = CnpSmem<BN>;
+  constexpr int NS = S::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_align1024(smem_raw);
+  uint8_t* sWn = smem + NS * S::kStageBytes;          // [KB2][BN rows][128 B]
+  uint8_t* sY = sWn + S::kWnBytes;                    // [KB2][128 rows][128 B]
+  float* sStg = reinterpret_cast<float*>(sY + S::kYBytes);
+  int* meta = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(sStg) + S::kStgBytes);  // [2][BM] output row of each tile row
+  uint64_t* bars = reinterpret_cast<uint64_t*>(meta + 2 * BM);
+  // bars: [0..NS) full, [NS..2NS) empty, then c1_full[2], c2_full[2], acc_empty[2], y_ready, wn_full
+  uint64_t* bx = bars + 2 * NS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bx + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long Mtot = (long long)a.n_items * a.a_rows;
+  const int kb_per_seg = a.K / BK, num_kb = 2 * kb_per_seg;
+  constexpr int KB2 = BN / BK;  // k-blocks of the noise GEMM (K = Cout)
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(smem_u32(&bars[i]), 1); mbar_init(smem_u32(&bars[NS + i]), 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bx[i]), 1); mbar_init(smem_u32(&bx[2 + i]), 1); mbar_init(smem_u32(&bx[4 + i]), 256);
+    }
+    mbar_init(smem_u32(&bx[6]), 1); mbar_init(smem_u32(&bx[7]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 4 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(smem_u32(&bx[7]), S::kWnBytes);
+#pragma unroll
+      for (int kb = 0; kb < KB2; ++kb) tma_load_2d(smem_u32(sWn + kb * BN * 128), &tmN, smem_u32(&bx[7]), kb * BK, 0);
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int phase = t % a.s, m0 = (t / a.s) * BM;
+        const int delta = (phase < a.s - a.p) ? -1 : 1;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int st = it % NS;
+          mbar_wait(smem_u32(&bars[NS + st]), ((it / NS) & 1) ^ 1);
+          const uint32_t full = smem_u32(&bars[st]);
+          const uint32_t sa = smem_u32(smem + st * S::kStageBytes), sb = sa + BM * BK * 2;
+          const int seg = kb / kb_per_seg, kk = (kb - seg * kb_per_seg) * BK;
+          mbar_arrive_expect_tx(full, S::kStageBytes);
+          tma_load_2d(sa, &tmA, full, kk, m0 + (seg ? delta : 0));
+          tma_load_2d(sb, &tmW, full, seg * a.K + kk, phase * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BN);
+      int it = 0;
+      const int n_my = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      // The noise GEMM of tile i is two to eight MMAs that the epilogue warps are waiting for, the conv chain of
+      // tile i+1 is long and paced by TMA: the short chain is issued the moment its operand tile is ready, between
+      // two k-blocks of the long one, instead of queueing behind it.
+      int c2_next = 0;  // next tile whose noise GEMM has not been issued
+      auto noise_chain = [&](bool block) -> bool {
+        const uint32_t bar_y = smem_u32(&bx[6]);
+        if (block) mbar_wait(bar_y, c2_next & 1);
+        else if (!mbar_test(bar_y, c2_next & 1)) return false;
+        tc_fence_after();
+        const int buf = c2_next & 1;
+#pragma unroll
+        for (int kb = 0; kb < KB2; ++kb) {
+          const uint64_t da = umma_desc_k_sw128(smem_u32(sY + kb * BM * 128));
+          const uint64_t db = umma_desc_k_sw128(smem_u32(sWn + kb * BN * 128));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_base + buf * 2 * BN + BN, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&bx[2 + buf]));
+        ++c2_next;
+        return true;
+      };
+      mbar_wait(smem_u32(&bx[7]), 0);
+      for (int ti = 0; ti < n_my; ++ti) {
+        const int buf = ti & 1;
+        while (c2_next + 2 <= ti) noise_chain(true);  // the accumulators of this buffer are drained only after tile ti-2 finished
+        mbar_wait(smem_u32(&bx[4 + buf]), ((ti >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int st = it % NS;
+          uint32_t spins = 0;
+          while (!mbar_test(smem_u32(&bars[st]), (it / NS) & 1)) {
+            if (c2_next < ti) noise_chain(false);
+            if (++spins > (1u << 26)) { printf("snacb: k_convt_noise_p ring timeout\n"); __trap(); }
+          }
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + st * S::kStageBytes), sb = sa + BM * BK * 2;
+          const uint64_t da = umma_desc_k_sw128(sa), db = umma_desc_k_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_base + buf * 2 * BN, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          umma_commit(smem_u32(&bars[NS + st]));
+          if (c2_next < ti) noise_chain(false);
+        }
+        umma_commit(smem_u32(&bx[buf]));
+      }
+      while (c2_next < n_my) noise_chain(true);
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int trow = q * 32 + lane;  // TMEM lane == tile row owned by this thread in the row-per-lane phases
+    const int c4 = lane & 3, r8 = lane >> 2;
+    constexpr int NH = BN / 32;  // 16-column steps per warp
+    const int colbase = half * (BN / 2);
+    float* stg = sStg + (warp - 2) * (32 * 16);
+    int ti = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+      const int phase = t % a.s, m0 = (t / a.s) * BM;
+      const int buf = ti & 1;
+      int* m_out = meta + buf * BM;
+      int my_oi = -1;
+      float my_nz = 0.0f;
+      {
+        const long long gm = (long long)m0 + trow;
+        if (gm < Mtot) {
+          const int item = (int)(gm / a.a_rows), j = (int)(gm - (long long)item * a.a_rows);
+          const ItemRef itr = get_item(a.items, a.base, item, a.out_len);
+          const int t_rel = (a.a_lo + j) * a.s + phase;
+          const int orow = t_rel - a.o_lo;
+          if (orow >= 0 && orow < a.o_rows) {
+            const int t_abs = t_rel + itr.shift0 * a.up;
+            const bool live = (t_abs >= 0) && (t_abs < a.T0 * a.up);
+            my_oi = item * a.o_rows + orow;
+            if (live) my_nz = noise_at(a.noise, itr.code_row, t_abs);
+            else my_oi |= (int)kLiveFlag;
+          }
+        }
+        if (half == 0) m_out[trow] = my_oi;
+      }
+      const uint32_t d1_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN + colbase);
+      mbar_wait(smem_u32(&bx[buf]), (ti >> 1) & 1);
+      tc_fence_after();
+      // ---- phase 1: y = D1 + b -> fp16 -> operand tile of the noise GEMM (row per lane is exactly the K-major layout)
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        const int col = colbase + h * 16;
+        uint32_t r[16];
+        tmem_ld16(d1_addr + (uint32_t)(h * 16), r);
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + col + 4 * j));
+          const __half2 h0 = __floats2half2_rn(__uint_as_float(r[4 * j]) + b4.x, __uint_as_float(r[4 * j + 1]) + b4.y);
+          const __half2 h1 = __floats2half2_rn(__uint_as_float(r[4 * j + 2]) + b4.z, __uint_as_float(r[4 * j + 3]) + b4.w);
+          pk[2 * j] = *reinterpret_cast<const uint32_t*>(&h0);
+          pk[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+        }
+        uint8_t* rowp = sY + (col / BK) * (BM * 128) + trow * 128;
+        const int ch = ((col % BK) * 2) >> 4;  // first of the two 16-byte chunks
+        *reinterpret_cast<uint4*>(rowp + (((ch) ^ (trow & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(rowp + (((ch + 1) ^ (trow & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp == 2 && lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bx[6])) : "memory");
+      // ---- phase 2: x = (D1 + b) + n * D2, transposed through the staging tile, stored coalesced
+      int oi4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) oi4[i] = m_out[q * 32 + r8 + 8 * i];
+      const bool live = my_oi >= 0 && !(my_oi & (int)kLiveFlag);
+      mbar_wait(smem_u32(&bx[2 + buf]), (ti >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        const int col = colbase + h * 16;
+        uint32_t d1[16], d2[16];
+        tmem_ld16(d1_addr + (uint32_t)(h * 16), d1);
+        tmem_ld16(d1_addr + (uint32_t)(BN + h * 16), d2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + col + 4 * j));
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float y = __uint_as_float(d1[4 * j + e]) + bb[e];
+            const float x = fmaf(my_nz, __uint_as_float(d2[4 * j + e]), y);
+            d1[4 * j + e] = __float_as_uint(live ? x : 0.0f);
+          }
+        }
+        float4 v[4];
+        epi_transpose16(stg, lane, d1, v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (oi4[i] < 0) continue;
+          const size_t o = (size_t)(oi4[i] & (int)(kLiveFlag - 1)) * a.ldo + col + c4 * 4;
+          *reinterpret_cast<float4*>(a.out32 + o) = v[i];
+        }
+      }
+      tc_fence_before();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bx[4 + buf])) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 4 * BN);
+  }
+}
+
 int sm_count() {
   static int n = [] {
     int dev = 0, v = 148;
@@ -1139,6 +1385,19 @@ cudaError_t launch_ws_e(const CUtensorMap& ma, const CUtensorMap& mw, const TcDe
 }
 
 template <int BN>
+cudaError_t launch_cnp_t(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mn, const TcDev& d, int total,
+                         cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_convt_noise_p<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, CnpSmem<BN>::kBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  k_convt_noise_p<BN><<<std::min(total, sm_count()), kTcThreads, CnpSmem<BN>::kBytes, st>>>(ma, mw, mn, d, total);
+  return cudaGetLastError();
+}
+
+template <int BN>
 cudaError_t launch_cn_t(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mn, const TcDev& d, dim3 grid,
                         cudaStream_t st) {
   static bool attr_set = false;
@@ -1170,8 +1429,14 @@ cudaError_t launch_convt_noise_tc(const GroupCtx& g, const TcGemmArgs& a, const 
   d.stages = 3;  // stage 0 / 1 / 2 are re-used as y tile / W_n / transposes; 3 stages keep 2-3 CTAs per SM
   d.K = a.K; d.nseg = 2; d.a_rows = a.a_rows; d.a_lo = a.a_lo; d.s = a.s; d.p = a.p; d.Cout = a.Cout;
   d.bias = a.bias; d.out32 = a.out32; d.o_lo = a.o_r.lo; d.o_rows = a.o_r.n(); d.ldo = a.ldo; d.noise = a.noise; d.up = a.up;
-  dim3 grid((unsigned)((Mtot + BM - 1) / BM), (unsigned)a.s);
-  cudaError_t e = (bn == 128) ? launch_cn_t<128>(ma, mw, mn, d, grid, g.stream) : launch_cn_t<64>(ma, mw, mn, d, grid, g.stream);
+  const long long total = ((Mtot + BM - 1) / BM) * a.s;
+  cudaError_t e;
+  if (g_cn_p && total >= 2LL * sm_count() && total < (1LL << 30)) {
+    e = (bn == 128) ? launch_cnp_t<128>(ma, mw, mn, d, (int)total, g.stream) : launch_cnp_t<64>(ma, mw, mn, d, (int)total, g.stream);
+  } else {
+    dim3 grid((unsigned)total);
+    e = (bn == 128) ? launch_cn_t<128>(ma, mw, mn, d, grid, g.stream) : launch_cn_t<64>(ma, mw, mn, d, grid, g.stream);
+  }
   ++*g.launches;
   return e;
 }
@@ -1224,7 +1489,8 @@ cudaError_t launch_gemm_tc(const GroupCtx& g, const TcGemmArgs& a) {
       return cudaGetLastError();
     }
   }
-  dim3 grid((unsigned)((Mtot + BM - 1) / BM), (unsigned)(a.N / bn));
+  d.n_tiles = a.N / bn;
+  dim3 grid((unsigned)(((Mtot + BM - 1) / BM) * d.n_tiles));
   cudaError_t e = (bn == 128) ? launch_tc_bn<128>(a.epi, ma, mw, d, grid, g.stream) : launch_tc_bn<64>(a.epi, ma, mw, d, grid, g.stream);
   ++*g.launches;
   return e;
