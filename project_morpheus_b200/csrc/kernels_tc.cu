@@ -143,6 +143,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // Epilogue transpose: a warp holds a 32-row x 16-column fp32 block one row per lane (tcgen05.ld
 // 32x32b.x16); after the trip through its private 2 KB of swizzled shared memory lane l holds, for
 // i = 0..3, the float4 of row (l/4 + 8i), columns 4*(l%4)..+3 - so global accesses are 64-byte row
@@ -1119,7 +1128,7 @@ template <int BN> struct CnpSmem {
   static constexpr int kYBytes = BM * BN * 2;
   static constexpr int kStgBytes = 8 * 32 * 16 * 4;
   static constexpr int kMetaBytes = 2 * BM * 4;
-  static constexpr int kBytes = kStages * kStageBytes + kWnBytes + kYBytes + kStgBytes + kMetaBytes + 256 + 1024;
+  static constexpr int kBytes = kStages * kStageBytes + kWnBytes + kYBytes + kStgBytes + kMetaBytes + BN * 4 + 256 + 1024;
 };
 
 template <int BN>
@@ -1135,7 +1144,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_convt_noise_p(const __grid_co
   uint8_t* sY = sWn + S::kWnBytes;                    // [KB2][128 rows][128 B]
   float* sStg = reinterpret_cast<float*>(sY + S::kYBytes);
   int* meta = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(sStg) + S::kStgBytes);  // [2][BM] output row of each tile row
-  uint64_t* bars = reinterpret_cast<uint64_t*>(meta + 2 * BM);
+  float* sBias = reinterpret_cast<float*>(meta + 2 * BM);                                // [BN] conv bias (same for every phase)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + BN);
   // bars: [0..NS) full, [NS..2NS) empty, then c1_full[2], c2_full[2], acc_empty[2], y_ready, wn_full
   uint64_t* bx = bars + 2 * NS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bx + 8);
@@ -1153,6 +1163,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_convt_noise_p(const __grid_co
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 4 * BN);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + BN) sBias[threadIdx.x - 64] = a.bias[threadIdx.x - 64];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1273,9 +1284,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_convt_noise_p(const __grid_co
         uint32_t pk[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + col + 4 * j));
-          const __half2 h0 = __floats2half2_rn(__uint_as_float(r[4 * j]) + b4.x, __uint_as_float(r[4 * j + 1]) + b4.y);
-          const __half2 h1 = __floats2half2_rn(__uint_as_float(r[4 * j + 2]) + b4.z, __uint_as_float(r[4 * j + 3]) + b4.w);
+          const float4 b4 = *reinterpret_cast<const float4*>(sBias + col + 4 * j);
+          const float2 lo = __fadd2_rn(make_float2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), make_float2(b4.x, b4.y));
+          const float2 hi = __fadd2_rn(make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), make_float2(b4.z, b4.w));
+          const __half2 h0 = __floats2half2_rn(lo.x, lo.y), h1 = __floats2half2_rn(hi.x, hi.y);
           pk[2 * j] = *reinterpret_cast<const uint32_t*>(&h0);
           pk[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1);
         }
@@ -1292,33 +1304,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_convt_noise_p(const __grid_co
       int oi4[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) oi4[i] = m_out[q * 32 + r8 + 8 * i];
-      const bool live = my_oi >= 0 && !(my_oi & (int)kLiveFlag);
+      const bool dead = (my_oi >= 0) && (my_oi & (int)kLiveFlag);  // row exists but lies outside the stream: stored as zeros
+      const bool any_dead = __any_sync(0xffffffffu, dead);
+      const bool all_rows = __all_sync(0xffffffffu, (oi4[0] | oi4[1] | oi4[2] | oi4[3]) >= 0);
+      const float2 nz2 = make_float2(my_nz, my_nz);
       mbar_wait(smem_u32(&bx[2 + buf]), (ti >> 1) & 1);
       tc_fence_after();
 #pragma unroll
       for (int h = 0; h < NH; ++h) {
         const int col = colbase + h * 16;
         uint32_t d1[16], d2[16];
-        tmem_ld16(d1_addr + (uint32_t)(h * 16), d1);
-        tmem_ld16(d1_addr + (uint32_t)(BN + h * 16), d2);
+        tmem_ld16_nowait(d1_addr + (uint32_t)(h * 16), d1);
+        tmem_ld16_nowait(d1_addr + (uint32_t)(BN + h * 16), d2);
+        tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + col + 4 * j));
-          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+          const float4 b4 = *reinterpret_cast<const float4*>(sBias + col + 4 * j);
+          float2 lo = __fadd2_rn(make_float2(__uint_as_float(d1[4 * j]), __uint_as_float(d1[4 * j + 1])), make_float2(b4.x, b4.y));
+          float2 hi = __fadd2_rn(make_float2(__uint_as_float(d1[4 * j + 2]), __uint_as_float(d1[4 * j + 3])), make_float2(b4.z, b4.w));
+          lo = __ffma2_rn(nz2, make_float2(__uint_as_float(d2[4 * j]), __uint_as_float(d2[4 * j + 1])), lo);
+          hi = __ffma2_rn(nz2, make_float2(__uint_as_float(d2[4 * j + 2]), __uint_as_float(d2[4 * j + 3])), hi);
+          d1[4 * j] = __float_as_uint(lo.x); d1[4 * j + 1] = __float_as_uint(lo.y);
+          d1[4 * j + 2] = __float_as_uint(hi.x); d1[4 * j + 3] = __float_as_uint(hi.y);
+        }
+        if (any_dead) {
+          if (dead) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float y = __uint_as_float(d1[4 * j + e]) + bb[e];
-            const float x = fmaf(my_nz, __uint_as_float(d2[4 * j + e]), y);
-            d1[4 * j + e] = __float_as_uint(live ? x : 0.0f);
+            for (int e = 0; e < 16; ++e) d1[e] = 0u;
           }
         }
         float4 v[4];
         epi_transpose16(stg, lane, d1, v);
+        float* op = a.out32 + col + c4 * 4;
+        if (all_rows) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (oi4[i] < 0) continue;
-          const size_t o = (size_t)(oi4[i] & (int)(kLiveFlag - 1)) * a.ldo + col + c4 * 4;
-          *reinterpret_cast<float4*>(a.out32 + o) = v[i];
+          for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(op + (size_t)(oi4[i] & (int)(kLiveFlag - 1)) * a.ldo) = v[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (oi4[i] < 0) continue;
+            *reinterpret_cast<float4*>(op + (size_t)(oi4[i] & (int)(kLiveFlag - 1)) * a.ldo) = v[i];
+          }
         }
       }
       tc_fence_before();
