@@ -1127,12 +1127,13 @@ template <int BN> struct CnpSmem {
   static constexpr int kWnBytes = BN * BN * 2;
   static constexpr int kYBytes = BM * BN * 2;
   static constexpr int kStgBytes = 8 * 32 * 16 * 4;
-  static constexpr int kMetaBytes = 2 * BM * 4;
+  static constexpr int kMetaBytes = 4 * BM * 4;         // [2][BM] output row + [2][BM] noise sample of each tile row
   static constexpr int kBytes = kStages * kStageBytes + kWnBytes + kYBytes + kStgBytes + kMetaBytes + BN * 4 + 256 + 1024;
 };
+constexpr int kCnpThreads = kTcThreads + 128;  // + warps 10..13: output row / Philox noise of the NEXT tile, one row per thread
 
 template <int BN>
-__global__ void __launch_bounds__(kTcThreads, 1) k_convt_noise_p(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(kCnpThreads, 1) k_convt_noise_p(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmW,
                                                                const __grid_constant__ CUtensorMap tmN, const TcDev a,
                                                                const int total_tiles) {
@@ -1144,11 +1145,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_convt_noise_p(const __grid_co
   uint8_t* sY = sWn + S::kWnBytes;                    // [KB2][128 rows][128 B]
   float* sStg = reinterpret_cast<float*>(sY + S::kYBytes);
   int* meta = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(sStg) + S::kStgBytes);  // [2][BM] output row of each tile row
-  float* sBias = reinterpret_cast<float*>(meta + 2 * BM);                                // [BN] conv bias (same for every phase)
+  float* meta_nz = reinterpret_cast<float*>(meta + 2 * BM);                              // [2][BM] noise sample of each tile row
+  float* sBias = meta_nz + 2 * BM;                                                       // [BN] conv bias (same for every phase)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + BN);
-  // bars: [0..NS) full, [NS..2NS) empty, then c1_full[2], c2_full[2], acc_empty[2], y_ready, wn_full
+  // bars: [0..NS) full, [NS..2NS) empty, then c1_full[2], c2_full[2], acc_empty[2], y_ready, wn_full, meta_full[2], meta_empty[2]
   uint64_t* bx = bars + 2 * NS;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bx + 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bx + 12);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long Mtot = (long long)a.n_items * a.a_rows;
   const int kb_per_seg = a.K / BK, num_kb = 2 * kb_per_seg;
@@ -1160,6 +1162,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_convt_noise_p(const __grid_co
       mbar_init(smem_u32(&bx[i]), 1); mbar_init(smem_u32(&bx[2 + i]), 1); mbar_init(smem_u32(&bx[4 + i]), 256);
     }
     mbar_init(smem_u32(&bx[6]), 1); mbar_init(smem_u32(&bx[7]), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bx[8 + i]), 128); mbar_init(smem_u32(&bx[10 + i]), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 4 * BN);
@@ -1241,6 +1244,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_convt_noise_p(const __grid_co
       }
       while (c2_next < n_my) noise_chain(true);
     }
+  } else if (warp >= 10) {
+    // ---- row bookkeeping one tile ahead of the epilogue: output row, live flag and the Philox noise sample
+    const int trow = (warp - 10) * 32 + lane;
+    int ti = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+      const int phase = t % a.s, m0 = (t / a.s) * BM;
+      const int buf = ti & 1;
+      int my_oi = -1;
+      float my_nz = 0.0f;
+      const long long gm = (long long)m0 + trow;
+      if (gm < Mtot) {
+        const int item = (int)(gm / a.a_rows), j = (int)(gm - (long long)item * a.a_rows);
+        const ItemRef itr = get_item(a.items, a.base, item, a.out_len);
+        const int t_rel = (a.a_lo + j) * a.s + phase;
+        const int orow = t_rel - a.o_lo;
+        if (orow >= 0 && orow < a.o_rows) {
+          const int t_abs = t_rel + itr.shift0 * a.up;
+          const bool live = (t_abs >= 0) && (t_abs < a.T0 * a.up);
+          my_oi = item * a.o_rows + orow;
+          if (live) my_nz = noise_at(a.noise, itr.code_row, t_abs);
+          else my_oi |= (int)kLiveFlag;
+        }
+      }
+      mbar_wait(smem_u32(&bx[10 + buf]), ((ti >> 1) & 1) ^ 1);  // the epilogue has read this buffer's previous tile
+      meta[buf * BM + trow] = my_oi;
+      meta_nz[buf * BM + trow] = my_nz;
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bx[8 + buf])) : "memory");
+    }
   } else {
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int trow = q * 32 + lane;  // TMEM lane == tile row owned by this thread in the row-per-lane phases
@@ -1250,28 +1281,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_convt_noise_p(const __grid_co
     float* stg = sStg + (warp - 2) * (32 * 16);
     int ti = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
-      const int phase = t % a.s, m0 = (t / a.s) * BM;
       const int buf = ti & 1;
-      int* m_out = meta + buf * BM;
-      int my_oi = -1;
-      float my_nz = 0.0f;
-      {
-        const long long gm = (long long)m0 + trow;
-        if (gm < Mtot) {
-          const int item = (int)(gm / a.a_rows), j = (int)(gm - (long long)item * a.a_rows);
-          const ItemRef itr = get_item(a.items, a.base, item, a.out_len);
-          const int t_rel = (a.a_lo + j) * a.s + phase;
-          const int orow = t_rel - a.o_lo;
-          if (orow >= 0 && orow < a.o_rows) {
-            const int t_abs = t_rel + itr.shift0 * a.up;
-            const bool live = (t_abs >= 0) && (t_abs < a.T0 * a.up);
-            my_oi = item * a.o_rows + orow;
-            if (live) my_nz = noise_at(a.noise, itr.code_row, t_abs);
-            else my_oi |= (int)kLiveFlag;
-          }
-        }
-        if (half == 0) m_out[trow] = my_oi;
-      }
+      const int* m_out = meta + buf * BM;
+      mbar_wait(smem_u32(&bx[8 + buf]), (ti >> 1) & 1);
+      const int my_oi = m_out[trow];
+      const float my_nz = meta_nz[buf * BM + trow];
       const uint32_t d1_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN + colbase);
       mbar_wait(smem_u32(&bx[buf]), (ti >> 1) & 1);
       tc_fence_after();
@@ -1304,6 +1318,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_convt_noise_p(const __grid_co
       int oi4[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) oi4[i] = m_out[q * 32 + r8 + 8 * i];
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bx[10 + buf])) : "memory");
       const bool dead = (my_oi >= 0) && (my_oi & (int)kLiveFlag);  // row exists but lies outside the stream: stored as zeros
       const bool any_dead = __any_sync(0xffffffffu, dead);
       const bool all_rows = __all_sync(0xffffffffu, (oi4[0] | oi4[1] | oi4[2] | oi4[3]) >= 0);
@@ -1419,7 +1434,7 @@ cudaError_t launch_cnp_t(const CUtensorMap& ma, const CUtensorMap& mw, const CUt
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  k_convt_noise_p<BN><<<std::min(total, sm_count()), kTcThreads, CnpSmem<BN>::kBytes, st>>>(ma, mw, mn, d, total);
+  k_convt_noise_p<BN><<<std::min(total, sm_count()), kCnpThreads, CnpSmem<BN>::kBytes, st>>>(ma, mw, mn, d, total);
   return cudaGetLastError();
 }
 
