@@ -1122,15 +1122,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_convt_p(const __grid_constant
 // are paid once per SM, and the accumulator pair (D1 conv, D2 noise GEMM) is double-buffered in TMEM so
 // the conv MMAs of tile i+1 run under the two epilogue phases of tile i.
 template <int BN> struct CnpSmem {
-  static constexpr int kStages = (BN == 64) ? 6 : 4;
+  static constexpr int kStages = (BN == 64) ? 6 : 3;
   static constexpr int kStageBytes = BM * BK * 2 + BN * BK * 2;
   static constexpr int kWnBytes = BN * BN * 2;
-  static constexpr int kYBytes = BM * BN * 2;
+  static constexpr int kYBytes = BM * BN * 2;           // fp16 y tile, one per epilogue set; the set's phase-2 transposes alias it
   static constexpr int kStgBytes = 8 * 32 * 16 * 4;
   static constexpr int kMetaBytes = 4 * BM * 4;         // [2][BM] output row + [2][BM] noise sample of each tile row
-  static constexpr int kBytes = kStages * kStageBytes + kWnBytes + kYBytes + kStgBytes + kMetaBytes + BN * 4 + 256 + 1024;
+  static constexpr int kBytes = kStages * kStageBytes + kWnBytes + 2 * kYBytes + kMetaBytes + BN * 4 + 256 + 1024;
+  static_assert(kYBytes >= kStgBytes, "staging aliases the y tile");
 };
-constexpr int kCnpThreads = kTcThreads + 128;  // + warps 10..13: output row / Philox noise of the NEXT tile, one row per thread
+// warp 0 TMA, warp 1 MMA, warps 2..9 / 10..17 two epilogue sets (even / odd tiles of this CTA, one TMEM accumulator
+// pair each), warps 18..21 output row + Philox noise of upcoming tiles, one row per thread
+constexpr int kCnpThreads = 64 + 2 * 256 + 128;
 
 template <int BN>
 __global__ void __launch_bounds__(kCnpThreads, 1) k_convt_noise_p(const __grid_constant__ CUtensorMap tmA,
@@ -1142,15 +1145,15 @@ __global__ void __launch_bounds__(kCnpThreads, 1) k_convt_noise_p(const __grid_c
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sWn = smem + NS * S::kStageBytes;          // [KB2][BN rows][128 B]
-  uint8_t* sY = sWn + S::kWnBytes;                    // [KB2][128 rows][128 B]
-  float* sStg = reinterpret_cast<float*>(sY + S::kYBytes);
-  int* meta = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(sStg) + S::kStgBytes);  // [2][BM] output row of each tile row
+  uint8_t* sY = sWn + S::kWnBytes;                    // [2 sets][KB2][128 rows][128 B]
+  int* meta = reinterpret_cast<int*>(sY + 2 * S::kYBytes);  // [2][BM] output row of each tile row
   float* meta_nz = reinterpret_cast<float*>(meta + 2 * BM);                              // [2][BM] noise sample of each tile row
   float* sBias = meta_nz + 2 * BM;                                                       // [BN] conv bias (same for every phase)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + BN);
-  // bars: [0..NS) full, [NS..2NS) empty, then c1_full[2], c2_full[2], acc_empty[2], y_ready, wn_full, meta_full[2], meta_empty[2]
+  // bars: [0..NS) full, [NS..2NS) empty, then c1_full[2], c2_full[2], acc_empty[2], y_ready[2], wn_full, meta_full[2], meta_empty[2]
   uint64_t* bx = bars + 2 * NS;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bx + 12);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bx + 13);
+  const int n_my = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long Mtot = (long long)a.n_items * a.a_rows;
   const int kb_per_seg = a.K / BK, num_kb = 2 * kb_per_seg;
@@ -1161,8 +1164,8 @@ __global__ void __launch_bounds__(kCnpThreads, 1) k_convt_noise_p(const __grid_c
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bx[i]), 1); mbar_init(smem_u32(&bx[2 + i]), 1); mbar_init(smem_u32(&bx[4 + i]), 256);
     }
-    mbar_init(smem_u32(&bx[6]), 1); mbar_init(smem_u32(&bx[7]), 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bx[8 + i]), 128); mbar_init(smem_u32(&bx[10 + i]), 256); }
+    mbar_init(smem_u32(&bx[6]), 1); mbar_init(smem_u32(&bx[7]), 1); mbar_init(smem_u32(&bx[8]), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bx[9 + i]), 128); mbar_init(smem_u32(&bx[11 + i]), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 4 * BN);
@@ -1174,9 +1177,9 @@ __global__ void __launch_bounds__(kCnpThreads, 1) k_convt_noise_p(const __grid_c
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(smem_u32(&bx[7]), S::kWnBytes);
+      mbar_arrive_expect_tx(smem_u32(&bx[8]), S::kWnBytes);
 #pragma unroll
-      for (int kb = 0; kb < KB2; ++kb) tma_load_2d(smem_u32(sWn + kb * BN * 128), &tmN, smem_u32(&bx[7]), kb * BK, 0);
+      for (int kb = 0; kb < KB2; ++kb) tma_load_2d(smem_u32(sWn + kb * BN * 128), &tmN, smem_u32(&bx[8]), kb * BK, 0);
       int it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int phase = t % a.s, m0 = (t / a.s) * BM;
@@ -1197,20 +1200,19 @@ __global__ void __launch_bounds__(kCnpThreads, 1) k_convt_noise_p(const __grid_c
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(BN);
       int it = 0;
-      const int n_my = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
       // The noise GEMM of tile i is two to eight MMAs that the epilogue warps are waiting for, the conv chain of
       // tile i+1 is long and paced by TMA: the short chain is issued the moment its operand tile is ready, between
       // two k-blocks of the long one, instead of queueing behind it.
       int c2_next = 0;  // next tile whose noise GEMM has not been issued
       auto noise_chain = [&](bool block) -> bool {
-        const uint32_t bar_y = smem_u32(&bx[6]);
-        if (block) mbar_wait(bar_y, c2_next & 1);
-        else if (!mbar_test(bar_y, c2_next & 1)) return false;
-        tc_fence_after();
         const int buf = c2_next & 1;
+        const uint32_t bar_y = smem_u32(&bx[6 + buf]), par = (uint32_t)(c2_next >> 1) & 1u;
+        if (block) mbar_wait(bar_y, par);
+        else if (!mbar_test(bar_y, par)) return false;
+        tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < KB2; ++kb) {
-          const uint64_t da = umma_desc_k_sw128(smem_u32(sY + kb * BM * 128));
+          const uint64_t da = umma_desc_k_sw128(smem_u32(sY + buf * S::kYBytes + kb * BM * 128));
           const uint64_t db = umma_desc_k_sw128(smem_u32(sWn + kb * BN * 128));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_base + buf * 2 * BN + BN, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
@@ -1219,7 +1221,7 @@ __global__ void __launch_bounds__(kCnpThreads, 1) k_convt_noise_p(const __grid_c
         ++c2_next;
         return true;
       };
-      mbar_wait(smem_u32(&bx[7]), 0);
+      mbar_wait(smem_u32(&bx[8]), 0);
       for (int ti = 0; ti < n_my; ++ti) {
         const int buf = ti & 1;
         while (c2_next + 2 <= ti) noise_chain(true);  // the accumulators of this buffer are drained only after tile ti-2 finished
@@ -1244,9 +1246,9 @@ __global__ void __launch_bounds__(kCnpThreads, 1) k_convt_noise_p(const __grid_c
       }
       while (c2_next < n_my) noise_chain(true);
     }
-  } else if (warp >= 10) {
-    // ---- row bookkeeping one tile ahead of the epilogue: output row, live flag and the Philox noise sample
-    const int trow = (warp - 10) * 32 + lane;
+  } else if (warp >= 18) {
+    // ---- row bookkeeping ahead of the epilogue: output row, live flag and the Philox noise sample
+    const int trow = (warp - 18) * 32 + lane;
     int ti = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
       const int phase = t % a.s, m0 = (t / a.s) * BM;
@@ -1267,28 +1269,32 @@ __global__ void __launch_bounds__(kCnpThreads, 1) k_convt_noise_p(const __grid_c
           else my_oi |= (int)kLiveFlag;
         }
       }
-      mbar_wait(smem_u32(&bx[10 + buf]), ((ti >> 1) & 1) ^ 1);  // the epilogue has read this buffer's previous tile
+      mbar_wait(smem_u32(&bx[11 + buf]), ((ti >> 1) & 1) ^ 1);  // the epilogue has read this buffer's previous tile
       meta[buf * BM + trow] = my_oi;
       meta_nz[buf * BM + trow] = my_nz;
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bx[8 + buf])) : "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bx[9 + buf])) : "memory");
     }
   } else {
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    // set 0 (warps 2..9) takes this CTA's even tiles, set 1 (warps 10..17) the odd ones: tile i+1 goes through its
+    // two epilogue phases while tile i is still in its own, each set on its own accumulator pair and y tile
+    const int set = (warp - 2) >> 3, ew = (warp - 2) & 7;
+    const int q = warp & 3, half = ew >> 2;
     const int trow = q * 32 + lane;  // TMEM lane == tile row owned by this thread in the row-per-lane phases
     const int c4 = lane & 3, r8 = lane >> 2;
     constexpr int NH = BN / 32;  // 16-column steps per warp
     const int colbase = half * (BN / 2);
-    float* stg = sStg + (warp - 2) * (32 * 16);
-    int ti = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
-      const int buf = ti & 1;
-      const int* m_out = meta + buf * BM;
-      mbar_wait(smem_u32(&bx[8 + buf]), (ti >> 1) & 1);
+    const int buf = set;
+    uint8_t* sYs = sY + set * S::kYBytes;
+    float* stg = reinterpret_cast<float*>(sYs) + ew * (32 * 16);
+    const int* m_out = meta + buf * BM;
+    for (int ti = set; ti < n_my; ti += 2) {
+      mbar_wait(smem_u32(&bx[9 + buf]), (ti >> 1) & 1);
       const int my_oi = m_out[trow];
       const float my_nz = meta_nz[buf * BM + trow];
       const uint32_t d1_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN + colbase);
       mbar_wait(smem_u32(&bx[buf]), (ti >> 1) & 1);
       tc_fence_after();
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + set) : "memory");  // the set is done with its transposes (they alias the y tile)
       // ---- phase 1: y = D1 + b -> fp16 -> operand tile of the noise GEMM (row per lane is exactly the K-major layout)
 #pragma unroll
       for (int h = 0; h < NH; ++h) {
@@ -1305,20 +1311,20 @@ __global__ void __launch_bounds__(kCnpThreads, 1) k_convt_noise_p(const __grid_c
           pk[2 * j] = *reinterpret_cast<const uint32_t*>(&h0);
           pk[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1);
         }
-        uint8_t* rowp = sY + (col / BK) * (BM * 128) + trow * 128;
+        uint8_t* rowp = sYs + (col / BK) * (BM * 128) + trow * 128;
         const int ch = ((col % BK) * 2) >> 4;  // first of the two 16-byte chunks
         *reinterpret_cast<uint4*>(rowp + (((ch) ^ (trow & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         *reinterpret_cast<uint4*>(rowp + (((ch + 1) ^ (trow & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tc_fence_before();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (warp == 2 && lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bx[6])) : "memory");
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + set) : "memory");
+      if (ew == 0 && lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bx[6 + buf])) : "memory");
       // ---- phase 2: x = (D1 + b) + n * D2, transposed through the staging tile, stored coalesced
       int oi4[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) oi4[i] = m_out[q * 32 + r8 + 8 * i];
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bx[10 + buf])) : "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bx[11 + buf])) : "memory");
       const bool dead = (my_oi >= 0) && (my_oi & (int)kLiveFlag);  // row exists but lies outside the stream: stored as zeros
       const bool any_dead = __any_sync(0xffffffffu, dead);
       const bool all_rows = __all_sync(0xffffffffu, (oi4[0] | oi4[1] | oi4[2] | oi4[3]) >= 0);
