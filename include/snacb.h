@@ -56,6 +56,8 @@ extern "C" {
 #define SNACB_FLAG_PERSISTENT_RU 4 /* persistent warp-specialised ResidualUnit kernel (also fuses C = 256)   */
 #define SNACB_FLAG_TAIL_FUSION 8 /* fuse the decoder tail into the last ResidualUnit kernel (measured slower: off) */
 #define SNACB_FLAG_NO_CONVT_NOISE_FUSION 2 /* run ConvTranspose1d and NoiseBlock as two GEMM kernels   */
+#define SNACB_FLAG_NO_PERSISTENT_CONVT 16 /* transposed convs through the one-shot (one tile per CTA) kernels  */
+#define SNACB_FLAG_FUSE_RU256 32 /* decoder block 1 ResidualUnits through the persistent fused kernel (measured on par: off) */
 
 /* fixed geometry of hubertsiuzdak/snac_24khz (the only model the reference loads, speechpipe.py:42) */
 #define SNACB_LATENT 768

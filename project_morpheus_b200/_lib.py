@@ -17,6 +17,8 @@ FLAG_NO_RU_FUSION = 1
 FLAG_NO_CONVT_NOISE_FUSION = 2
 FLAG_PERSISTENT_RU = 4
 FLAG_TAIL_FUSION = 8
+FLAG_NO_PERSISTENT_CONVT = 16
+FLAG_FUSE_RU256 = 32
 NOISE_PER_FRAME = 3360
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsnacb.so")

@@ -241,7 +241,7 @@ int run_group_f32(snacb_engine* e, const Plan& P, const Item* d_items, int n_tot
     float* X = bp.take<float>(S * n);
     float* Y = bp.take<float>(S * n);
     float* A = bp.take<float>(S * n);
-    GroupCtx g{d_items ? d_items + start : nullptr, start, n, out_len, P.T0, st, &e->launches};
+    GroupCtx g{d_items ? d_items + start : nullptr, start, n, out_len, P.T0, st, &e->launches, e->cfg.flags};
 
     auto gemm = [&](const GemmArgs& a) {
       const double M = (double)n * a.m_r.n(), segs = a.epi == EPI_CONVT ? 2.0 : 1.0;
@@ -368,7 +368,7 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
     __half* P16 = bp.take<__half>(S * n);
     __half* Q16 = bp.take<__half>(S * n);
     if (bp.off > lane_bytes) return fail(e, SNACB_ENOMEM, "workspace overflow in tensor-core pipeline");
-    GroupCtx g{d_items ? d_items + start : nullptr, start, n, out_len, P.T0, st, &e->launches};
+    GroupCtx g{d_items ? d_items + start : nullptr, start, n, out_len, P.T0, st, &e->launches, e->cfg.flags};
     bool tail_done = false;
 
     auto gemm = [&](const TcGemmArgs& a) {
@@ -448,7 +448,7 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
       Rng cur = B.ct;
       for (int r = 0; r < 3 && ce == cudaSuccess; ++r) {
         const RuDev& R = Wb.ru[r];
-        const bool ru_persist = (e->cfg.flags & SNACB_FLAG_PERSISTENT_RU) != 0 || (B.Cout == 256 && e->ru256);
+        const bool ru_persist = (e->cfg.flags & SNACB_FLAG_PERSISTENT_RU) != 0 || (B.Cout == 256 && (e->ru256 || (e->cfg.flags & SNACB_FLAG_FUSE_RU256)));
         if (ru_tc_supported(B.Cout, ru_persist) && !(e->cfg.flags & SNACB_FLAG_NO_RU_FUSION)) {  // fused dw + 1x1 + residual (blocks 2, 3)
           const bool last = (r == 2) && (b < 3);
           const bool want32 = !last || e->tap_stage == sid + 4 + 2 * r;

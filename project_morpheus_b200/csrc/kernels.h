@@ -15,6 +15,7 @@ struct GroupCtx {
   int T0;             // latent steps of the whole sequence
   cudaStream_t stream;
   int64_t* launches;  // launch counter
+  int flags = 0;      // snacb_config.flags (kernel selection switches)
 };
 
 // ---- integer kernel ------------------------------------------------------------------------

@@ -1478,7 +1478,7 @@ cudaError_t launch_convt_noise_tc(const GroupCtx& g, const TcGemmArgs& a, const 
   d.bias = a.bias; d.out32 = a.out32; d.o_lo = a.o_r.lo; d.o_rows = a.o_r.n(); d.ldo = a.ldo; d.noise = a.noise; d.up = a.up;
   const long long total = ((Mtot + BM - 1) / BM) * a.s;
   cudaError_t e;
-  if (g_cn_p && total >= 2LL * sm_count() && total < (1LL << 30)) {
+  if (g_cn_p && !(g.flags & SNACB_FLAG_NO_PERSISTENT_CONVT) && total >= 2LL * sm_count() && total < (1LL << 30)) {
     e = (bn == 128) ? launch_cnp_t<128>(ma, mw, mn, d, (int)total, g.stream) : launch_cnp_t<64>(ma, mw, mn, d, (int)total, g.stream);
   } else {
     dim3 grid((unsigned)total);
@@ -1518,7 +1518,7 @@ cudaError_t launch_gemm_tc(const GroupCtx& g, const TcGemmArgs& a) {
     ++*g.launches;
     return e;
   }
-  if (g_convt_p && a.epi == EPI_CONVT && a.Cout % 256 == 0 && !a.sn_alpha) {
+  if (g_convt_p && !(g.flags & SNACB_FLAG_NO_PERSISTENT_CONVT) && a.epi == EPI_CONVT && a.Cout % 256 == 0 && !a.sn_alpha) {
     // wide transposed convs: persistent kernel with 128 x 256 tiles (87 FLOP per byte of L2 -> SM operand traffic
     // instead of 65 at 128 x 128, which caps those layers near 770 TFLOP/s)
     const int n_tiles = a.N / 256, m_tiles = (int)((Mtot + BM - 1) / BM);
@@ -1874,7 +1874,12 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
 // so the workers start tile i+1 while tile i is in the tensor core / epilogue, the weight, the TMEM
 // allocation and the barrier setup are paid once per SM instead of once per tile, and C = 256
 // (decoder block 1: W = 128 KB) fits because only one CTA lives on an SM.
-constexpr int kRupThreads = 576;
+// NW worker warps, one control warp, NE (4 or 8) epilogue warps
+template <int C> struct RupCfg {
+  static constexpr int NW = (C == 256) ? 11 : 9, NE = 8;  // 20 warps: registers are allocated per 4 warps, 96 each
+  static constexpr int PD = (C == 256) ? 4 : 2;  // residual prefetch depth of the epilogue (16-column steps)
+  static constexpr int kThreads = (NW + 1 + NE) * 32;
+};
 template <int C> struct RupSmem {
   static constexpr int kNA = (C <= 128) ? 2 : 1;            // operand tile buffers
   static constexpr int kABytes = BM * C * 2;
@@ -1884,11 +1889,12 @@ template <int C> struct RupSmem {
 };
 
 template <int C, int DIL>
-__global__ void __launch_bounds__(kRupThreads, 1) k_ru_p(const __grid_constant__ CUtensorMap tmW, const RuDev a,
+__global__ void __launch_bounds__(RupCfg<C>::kThreads, 1) k_ru_p(const __grid_constant__ CUtensorMap tmW, const RuDev a,
                                                          const int tiles_per_item, const int total_tiles) {
   using S = RupSmem<C>;
   constexpr int KB = C / BK;
   constexpr int NA = S::kNA;
+  constexpr int NW = RupCfg<C>::NW, NE = RupCfg<C>::NE;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sW = smem;
@@ -1902,20 +1908,20 @@ __global__ void __launch_bounds__(kRupThreads, 1) k_ru_p(const __grid_constant__
   if (tid == 0) {
     mbar_init(smem_u32(&bars[0]), 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&bars[1 + i]), kRuWorkers);
+      mbar_init(smem_u32(&bars[1 + i]), NW * 32);
       mbar_init(smem_u32(&bars[3 + i]), 1);
       mbar_init(smem_u32(&bars[5 + i]), 1);
-      mbar_init(smem_u32(&bars[7 + i]), 256);
+      mbar_init(smem_u32(&bars[7 + i]), NE * 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) tmem_alloc(smem_u32(tmem_slot), 2 * C);
+  if (warp == NW) tmem_alloc(smem_u32(tmem_slot), 2 * C);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 9) {
+  if (warp < NW) {
     // ===================================================================== workers
     constexpr int CP = C / 2;
     constexpr int U = (DIL == 1) ? 8 : 9;
@@ -1939,7 +1945,7 @@ __global__ void __launch_bounds__(kRupThreads, 1) k_ru_p(const __grid_constant__
       const float* xin = a.x + (size_t)item * a.in_rows * C;
       uint8_t* sAb = sA + ab * S::kABytes;
 #pragma unroll 1
-      for (int idx = tid; idx < CP * U; idx += kRuWorkers) {
+      for (int idx = tid; idx < CP * U; idx += NW * 32) {
         const int cp = idx % CP, u = idx / CP;
         int first;
         if (DIL == 1) first = u * 16;
@@ -1962,7 +1968,7 @@ __global__ void __launch_bounds__(kRupThreads, 1) k_ru_p(const __grid_constant__
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[1 + ab])) : "memory");
     }
-  } else if (warp == 9) {
+  } else if (warp == NW) {
     // ===================================================================== control: W load + MMA issue
     if (lane == 0) {
       mbar_arrive_expect_tx(smem_u32(&bars[0]), S::kWBytes);
@@ -1989,16 +1995,15 @@ __global__ void __launch_bounds__(kRupThreads, 1) k_ru_p(const __grid_constant__
     }
   } else {
     // ===================================================================== epilogue (warps 10..17)
-    const int ew = warp - 10;
-    const int q = warp & 3, half = ew >> 2;
-    constexpr int NH = C / 32;                    // 16-column steps per warp
-    constexpr int PD = 2;                        // residual prefetch depth (steps)
+    const int ew = warp - NW - 1;
+    const int q = warp & 3;
+    constexpr int NH = C / 32;                    // 16-column steps per warp and column half
+    constexpr int PD = RupCfg<C>::PD;            // residual prefetch depth (steps)
     const int c4 = lane & 3, r8 = lane >> 2;
     float* stg = sStg + ew * (32 * 16);
     float* st_p = stg + lane * 16;
     const int st_x = (lane >> 1) & 3;
     const float* ld_p = stg + r8 * 16 + ((c4 ^ ((r8 >> 1) & 3)) << 2);
-    const int colb = half * (C / 2) + c4 * 4;
     int i = 0;
     for (int lin = blockIdx.x; lin < total_tiles; lin += gridDim.x, ++i) {
       const int item = lin / tiles_per_item, row0 = (lin - item * tiles_per_item) * BM;
@@ -2015,6 +2020,10 @@ __global__ void __launch_bounds__(kRupThreads, 1) k_ru_p(const __grid_constant__
           if (t >= 0 && t < a.T0 * a.up) lmask |= 1u << k;
         }
       }
+      bool waited = false;
+#pragma unroll 1
+      for (int half = (NE == 8) ? (ew >> 2) : 0; half < ((NE == 8) ? (ew >> 2) + 1 : 2); ++half) {
+      const int colb = half * (C / 2) + c4 * 4;
       const size_t ob = ((size_t)item * a.out_rows + orow_b) * C + colb;
       const float* rp = a.x + ((size_t)item * a.in_rows + (a.out_lo + orow_b - a.in_lo)) * C + colb;
       float4 res[PD][4];
@@ -2025,8 +2034,11 @@ __global__ void __launch_bounds__(kRupThreads, 1) k_ru_p(const __grid_constant__
           res[h][k] = make_float4(0.f, 0.f, 0.f, 0.f);
           if ((vmask >> k) & 1u) res[h][k] = __ldg(reinterpret_cast<const float4*>(rp + k * 8 * C + h * 16));
         }
-      mbar_wait(smem_u32(&bars[5 + tb]), (i >> 1) & 1);
-      tc_fence_after();
+      if (!waited) {
+        mbar_wait(smem_u32(&bars[5 + tb]), (i >> 1) & 1);
+        tc_fence_after();
+        waited = true;
+      }
 #pragma unroll
       for (int h = 0; h < NH; ++h) {
         uint32_t r[16];
@@ -2070,13 +2082,14 @@ __global__ void __launch_bounds__(kRupThreads, 1) k_ru_p(const __grid_constant__
           }
         }
       }
+      }
       tc_fence_before();
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[7 + tb])) : "memory");
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == NW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * C);
   }
@@ -2091,7 +2104,7 @@ cudaError_t launch_rup_t(const CUtensorMap& mw, const RuDev& d, int tiles_per_it
     attr_set = true;
   }
   const int grid = std::min(total_tiles, sm_count());
-  k_ru_p<C, DIL><<<grid, kRupThreads, RupSmem<C>::kBytes, st>>>(mw, d, tiles_per_item, total_tiles);
+  k_ru_p<C, DIL><<<grid, RupCfg<C>::kThreads, RupSmem<C>::kBytes, st>>>(mw, d, tiles_per_item, total_tiles);
   return cudaGetLastError();
 }
 template <int C>

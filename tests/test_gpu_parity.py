@@ -449,8 +449,28 @@ def test_cuda_graph_latency_path_is_bit_identical(engines, precision):
     assert st.tolist() == [0, 0, _lib.WIN_REJECTED] + [0] * (n - 3) and not pcm[2].any() and np.array_equal(pcm[0], plain[0])
 
 
+@pytest.mark.parametrize("persistent_convt", [True, False])
+def test_large_tick_persistent_kernels_match_oracle(engines, oracle_w1, persistent_convt):
+    """A tick big enough (320 windows) that every layer takes its persistent kernel (transposed convs with 128 x 256
+    tiles, fused ConvT + NoiseBlock with two epilogue sets, weight-stationary 1x1 GEMMs) - small ticks use the
+    one-tile-per-CTA kernels.  A spread of its windows is checked against the oracle with the same injected noise,
+    and the persistent and one-shot transposed-conv kernels must agree to the last bit."""
+    n, frames = 320, 4
+    tok = windows_tokens(n, frames, base_stream=4100)
+    noise = snac_ref.make_noise(n, frames, seed=23)
+    eng = engines("fp16", True, persistent_convt=persistent_convt)
+    pcm, st = eng.decode_windows(tok, noise=snac_ref.pack_noise(noise))
+    assert (st == _lib.WIN_OK).all()
+    idx = [0, 1, 2, 37, 38, 63, 64, 127, 128, 129, 200, 255, 256, 300, 318, 319]
+    ref = oracle_decode_windows(oracle_w1, tok[idx], [z[idx] for z in noise])[:, 2048:4096]
+    want = pcm_trunc(ref).astype(np.float32) / 32767.0
+    _check_wave(want, pcm[idx].astype(np.float32) / 32767.0, TOL_MAX_ABS, TOL_SNR_DB)
+    other, _ = engines("fp16", True, persistent_convt=not persistent_convt).decode_windows(tok, noise=snac_ref.pack_noise(noise))
+    assert np.array_equal(other, pcm)
+
+
 @pytest.mark.parametrize("variant", [dict(persistent_ru=True), dict(fuse_ru=False, fuse_convt_noise=False), dict(lanes=3),
-                                     dict(fuse_tail=True)])
+                                     dict(fuse_tail=True), dict(fuse_ru256=True), dict(persistent_convt=False)])
 def test_kernel_variants_match_oracle(engines, oracle_w1, variant):
     """Alternative kernel selections of the tensor-core recipe (persistent warp-specialised ResidualUnit
     kernel incl. C = 256; fully unfused layer-per-kernel path; concurrent chunk lanes) meet the same tolerance."""
