@@ -1876,8 +1876,8 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
 // (decoder block 1: W = 128 KB) fits because only one CTA lives on an SM.
 // NW worker warps, one control warp, NE (4 or 8) epilogue warps
 template <int C> struct RupCfg {
-  static constexpr int NW = (C == 256) ? 11 : 9, NE = 8;  // 20 warps: registers are allocated per 4 warps, 96 each
-  static constexpr int PD = (C == 256) ? 4 : 2;  // residual prefetch depth of the epilogue (16-column steps)
+  static constexpr int NW = 11, NE = 8;  // 20 warps: registers are allocated per 4 warps, 96 each
+  static constexpr int PD = (C >= 128) ? 4 : 2;  // residual prefetch depth of the epilogue (16-column steps)
   static constexpr int kThreads = (NW + 1 + NE) * 32;
 };
 template <int C> struct RupSmem {
