@@ -469,6 +469,20 @@ def test_large_tick_persistent_kernels_match_oracle(engines, oracle_w1, persiste
     assert np.array_equal(other, pcm)
 
 
+@pytest.mark.parametrize("n,frames", [(97, 4), (333, 4), (1301, 4), (150, 7), (2100, 1)])
+def test_persistent_and_one_shot_convt_kernels_agree_bitwise(engines, n, frames):
+    """Tile counts below / above / not a multiple of the persistent grids (148 CTAs), 7-frame windows, more windows
+    than one chunk: the persistent transposed-conv kernels and the one-tile-per-CTA kernels produce identical PCM."""
+    tok = windows_tokens(n, frames, base_stream=5200)
+    keys = list(range(n))
+    a, sa = engines("fp16", True, persistent_convt=True).decode_windows(tok, noise="philox", seed=3, keys=keys)
+    a = a.copy()
+    b, sb = engines("fp16", True, persistent_convt=False).decode_windows(tok, noise="philox", seed=3, keys=keys)
+    assert np.array_equal(sa, sb) and np.array_equal(a, b)
+    if frames > 1:
+        assert a.any(axis=1).all()
+
+
 @pytest.mark.parametrize("variant", [dict(persistent_ru=True), dict(fuse_ru=False, fuse_convt_noise=False), dict(lanes=3),
                                      dict(fuse_tail=True), dict(fuse_ru256=True), dict(persistent_convt=False)])
 def test_kernel_variants_match_oracle(engines, oracle_w1, variant):
