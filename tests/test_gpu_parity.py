@@ -222,6 +222,56 @@ def test_ragged_tick_statuses_and_isolation(engines, oracle_w1):
         assert np.abs(pcm[i].astype(np.int32) - pcm_trunc(ref)[0].astype(np.int32)).max() <= 1
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_ragged_tick_fuzz_against_reference_semantics(engines, oracle_w1, seed):
+    """Seeded random ticks: window lengths 0..49 tokens (whole frames used, `len // 7`), ids mostly valid with a few
+    -1 / 4096 / 4097 / huge values: every window's outcome (None / b'' / IndexError / 4096 bytes) and its bytes match
+    the restated reference (`oracle.speechpipe_ref.window_to_pcm` over the fp32 oracle decode, noise off)."""
+    rng = np.random.default_rng(1000 + seed)
+    eng = engines("fp32")
+    n = 40
+    wins = []
+    for i in range(n):
+        L = int(rng.choice([0, 3, 6, 7, 8, 13, 14, 20, 21, 27, 28, 29, 34, 35, 41, 42, 48, 49]))
+        w = rng.integers(0, 4096, size=L).astype(np.int64)
+        r = rng.random()
+        if L and r < 0.10:
+            w[int(rng.integers(0, L))] = int(rng.choice([-1, 4097, 2**31 - 1, -4096]))
+        elif L and r < 0.16:
+            w[int(rng.integers(0, L))] = 4096
+        wins.append(w.tolist())
+    stride = 49
+    tok = np.zeros((n, stride), dtype=np.int32)
+    for i, w in enumerate(wins):
+        tok[i, : len(w)] = np.asarray(w, dtype=np.int64).astype(np.int32)
+    pcm, st = eng.decode_windows(tok, ntok=[len(w) for w in wins], noise="off")
+
+    def decode(c0, c1, c2):
+        codes = [torch.from_numpy(np.asarray(c, dtype=np.int64))[None] for c in (c0, c1, c2)]
+        oracle_w1.set_noise("off")
+        with torch.no_grad():
+            return oracle_w1.decode(codes)[0, 0].numpy()
+
+    kinds = set()
+    for i, w in enumerate(wins):
+        try:
+            want = sp.window_to_pcm(w, decode)
+        except IndexError:
+            want = IndexError
+        if want is IndexError:
+            assert st[i] == _lib.WIN_CODE4096 and not pcm[i].any(), i
+        elif want is None:
+            assert st[i] == _lib.WIN_REJECTED and not pcm[i].any(), i
+        elif want == b"":
+            assert st[i] == _lib.WIN_EMPTY and not pcm[i].any(), i
+        else:
+            assert st[i] == _lib.WIN_OK, i
+            got = pcm[i].astype(np.int32)
+            assert np.abs(got - np.frombuffer(want, dtype="<i2").astype(np.int32)).max() <= 1, i
+        kinds.add(int(st[i]))
+    assert _lib.WIN_OK in kinds and _lib.WIN_REJECTED in kinds and _lib.WIN_EMPTY in kinds
+
+
 def test_philox_noise_replays_through_oracle(engines, oracle_w1):
     """Mode C: in-kernel Philox noise, dumped and replayed through the oracle."""
     eng = engines("fp32")
