@@ -26,6 +26,22 @@ def test_every_declared_symbol_is_exported_and_bound(ensure_lib):
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
 
 
+def test_header_constants_match_the_ctypes_binding():
+    """Every SNACB_FLAG_* / status / precision / noise constant of include/snacb.h has the same value in _lib.py."""
+    src = open(os.path.join(ROOT, "include", "snacb.h")).read()
+    defs = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"^#define\s+SNACB_(\w+)\s+(-?(?:0x)?[0-9a-fA-F]+)\b", src, flags=re.M)}
+    assert len(defs) >= 15
+    checked = 0
+    for name, val in defs.items():
+        if hasattr(_lib, name):
+            assert getattr(_lib, name) == val, name
+            checked += 1
+    for flag in ("FLAG_NO_RU_FUSION", "FLAG_NO_CONVT_NOISE_FUSION", "FLAG_PERSISTENT_RU", "FLAG_TAIL_FUSION",
+                 "FLAG_NO_PERSISTENT_CONVT", "FLAG_FUSE_RU256"):
+        assert flag in defs and getattr(_lib, flag) == defs[flag]
+    assert checked >= 10
+
+
 def test_plan_matches_dependency_cone(ensure_lib):
     """rows needed for samples [2048,4096) of a 4-frame and a 7-frame window."""
     lib = _lib.load()
