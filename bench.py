@@ -343,6 +343,69 @@ def run_ours(args) -> None:
                                     "ms_per_tick": 1e3 * dt / len(ticks), "audio_s_per_s": emitted * AUDIO_S_PER_WINDOW / dt,
                                     "note": "host API, mixed 1/4/7-frame windows grouped by frame count inside one call"}
 
+        # Next row N2: token strings -> PCM chunks for every stream of a tick, through the Python tick scheduler
+        # (per-token Python like the reference's tokens_decoder, one batched decode) and through the native ingress
+        # (csrc/ingest.cpp).  Steady state: 7 new token strings per stream per tick -> one 28-token window per stream.
+        if args.ingest_streams > 0:
+            from oracle import speechpipe_ref as sp_ref
+            from project_morpheus_b200.ingest import NativeTickScheduler, decode_arrays_with
+            from project_morpheus_b200.scheduler import TickScheduler
+            ns, warm_f, timed_ticks = args.ingest_streams, 5, 6
+            strings = [sp_ref.synth_token_strings(70000 + i, warm_f + timed_ticks) for i in range(ns)]
+            kk = np.arange(ns, dtype=np.uint64)
+
+            def dec_arrays(tok, ntok_or_none):
+                return eng.decode_windows(tok, ntok=ntok_or_none, noise="philox", seed=3, keys=kk[: tok.shape[0]])
+
+            def dec_lists(windows):
+                tok = np.asarray(windows, dtype=np.int64).astype(np.int32)
+                pcm_l, st_l = dec_arrays(tok, None)
+                return [pcm_l[i].tobytes() if st_l[i] == _lib.WIN_OK else (b"" if st_l[i] == _lib.WIN_EMPTY else None)
+                        for i in range(len(windows))]
+
+            def null_arrays(tok, ntok):
+                return np.zeros((tok.shape[0], 2048), dtype=np.int16), np.where(ntok >= 14, _lib.WIN_OK, _lib.WIN_EMPTY).astype(np.int32)
+
+            def null_lists(windows):
+                return [b"\0" * 4096 if len(w) >= 14 else b"" for w in windows]
+
+            def drive(sched):
+                for i in range(ns):
+                    sched.add_stream(i)
+                    sched.push_many(i, strings[i][: 7 * warm_f])
+                while sched.tick():
+                    pass
+                for i in range(ns):
+                    sched.pop_audio(i)
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                got = 0
+                for t in range(timed_ticks):
+                    lo = 7 * (warm_f + t)
+                    for i in range(ns):
+                        sched.push_many(i, strings[i][lo: lo + 7])
+                    sched.tick()
+                    for i in range(ns):
+                        got += len(sched.pop_audio(i))
+                dt = (time.perf_counter() - t0) / timed_ticks
+                assert got == ns * timed_ticks, (got, ns, timed_ticks)
+                return dt
+
+            res = {}
+            for name, mk in (("python_scheduler", lambda: TickScheduler(dec_lists, max_windows_per_tick=ns)),
+                             ("native_ingest", lambda: NativeTickScheduler(max_streams=ns, max_windows_per_tick=ns,
+                                                                           decode_arrays=lambda a, b: decode_arrays_with(dec_arrays, a, b))),
+                             ("python_scheduler_host_only", lambda: TickScheduler(null_lists, max_windows_per_tick=ns)),
+                             ("native_ingest_host_only", lambda: NativeTickScheduler(max_streams=ns, max_windows_per_tick=ns,
+                                                                                     decode_arrays=null_arrays))):
+                dt = drive(mk())
+                res[name] = {"ms_per_tick": 1e3 * dt, "token_strings_per_s": 7 * ns / dt,
+                             "audio_s_per_s": ns * AUDIO_S_PER_WINDOW / dt}
+            res["streams"] = ns
+            res["note"] = ("token strings in -> PCM chunks out for every stream, 7 new strings per stream per tick; "
+                           "*_host_only replaces the decode by a no-op to isolate parsing + window planning + egress")
+            extra["n2_token_ingress"] = res
+
         # BASELINE config 3 (long_read): one-shot decode of 720-frame utterances, time-tiled; reduced batch by default
         if args.long_read_batch > 0:
             Fl, Bl = 720, args.long_read_batch
@@ -494,6 +557,7 @@ def main() -> None:
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline leg")
     ap.add_argument("--ref-windows", type=int, default=32, help="windows per step of the CPU reference sample")
     ap.add_argument("--latency-reps", type=int, default=200)
+    ap.add_argument("--ingest-streams", type=int, default=1024, help="streams of the token-ingress measurement (0 = skip)")
     ap.add_argument("--ragged-streams", type=int, default=512, help="streams of the config-5 ragged-tick side measurement (0 = skip)")
     ap.add_argument("--long-read-batch", type=int, default=8, help="streams of the config-3 long_read side measurement (0 = skip)")
     args = ap.parse_args()

@@ -231,6 +231,36 @@ int snacb_get_tap_shape(const snacb_engine* e, int32_t* rows, int32_t* channels,
  * (lo, hi) pairs: z, head, then per decoder block: in, q, convT, ru0, ru1, ru2. Needs no GPU. */
 int snacb_plan(int32_t frames, int32_t out_lo, int32_t out_hi, int32_t clip, int32_t* ranges);
 
+/* ---- N2: token ingress for many streams (host only, no GPU) ---------------------------------- */
+
+/* Replaces, batched over streams, the per-token Python of speechpipe.py:146-189 (turn_token_into_id: the last
+ * "<custom_token_N>" of the stripped string -> N - 10 - 4096 * (accepted_count % 7), None on any parse failure)
+ * and the window control flow of tokens_decoder, speechpipe.py:191-293 (ids <= 0 dropped without advancing the
+ * slot, first chunk after 7 accepted tokens until one decode returned non-None, then the last 28 / last 49 ids
+ * every 7 accepted tokens, end-of-stream flush padded to 28 with the last id).  Streams are slots 0..n-1. */
+typedef struct snacb_ingest snacb_ingest;
+/* turn_token_into_id(text, index), speechpipe.py:146-189: returns 1 and *id, or 0 where the reference returns None. */
+int snacb_parse_token(const char* text, int32_t len, int32_t index, int64_t* id);
+int snacb_ingest_create(snacb_ingest** out, int32_t n_streams);
+void snacb_ingest_destroy(snacb_ingest* g);
+/* A new request in this slot (barge-in, swap): drops everything queued for it. */
+int snacb_ingest_reset(snacb_ingest* g, int32_t stream);
+/* n token strings (one generator item each): string i is blob[offsets[i] .. offsets[i+1]) for streams[i]. */
+int snacb_ingest_push(snacb_ingest* g, int32_t n, const int32_t* streams, const char* blob, const int64_t* offsets);
+/* The producer of this stream is exhausted (the flush rule applies once its queue is consumed). */
+int snacb_ingest_finish(snacb_ingest* g, int32_t stream);
+/* The next ready window of every stream (at most one per stream, slot order, at most max_win): row w of
+ * tokens[max_win][tokens_stride >= 49] gets ntok[w] ids (7, 28 or 49; zero-filled beyond), stream_of[w] its slot.
+ * Returns the number of windows (>= 0) or a negative status.  The rows are what snacb_decode_windows_host takes. */
+int32_t snacb_ingest_tick(snacb_ingest* g, int32_t max_win, int32_t* tokens, int32_t tokens_stride, int32_t* ntok,
+                          int32_t* stream_of);
+/* Per-window statuses (SNACB_WIN_*) of the windows the last tick returned: latches the first-chunk rule. */
+int snacb_ingest_result(snacb_ingest* g, int32_t n, const int32_t* stream_of, const int32_t* status);
+/* 1 when the stream is finished, flushed and has nothing queued. */
+int snacb_ingest_done(const snacb_ingest* g, int32_t stream);
+/* which: 0 accepted tokens, 1 rejected token strings, 2 windows emitted. */
+int64_t snacb_ingest_stat(const snacb_ingest* g, int32_t which);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,17 @@ SIGNATURES = {
     "snacb_set_tap": (_i32, [_vp, _i32, _vp, _sz]),
     "snacb_plan": (_i32, [_i32, _i32, _i32, _i32, C.POINTER(_i32)]),
     "snacb_get_tap_shape": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
+    # N2: token ingress (host only)
+    "snacb_parse_token": (_i32, [C.c_char_p, _i32, _i32, C.POINTER(_i64)]),
+    "snacb_ingest_create": (_i32, [C.POINTER(_vp), _i32]),
+    "snacb_ingest_destroy": (None, [_vp]),
+    "snacb_ingest_reset": (_i32, [_vp, _i32]),
+    "snacb_ingest_push": (_i32, [_vp, _i32, _vp, _vp, _vp]),
+    "snacb_ingest_finish": (_i32, [_vp, _i32]),
+    "snacb_ingest_tick": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp]),
+    "snacb_ingest_result": (_i32, [_vp, _i32, _vp, _vp]),
+    "snacb_ingest_done": (_i32, [_vp, _i32]),
+    "snacb_ingest_stat": (_i64, [_vp, _i32]),
 }
 
 _lib = None

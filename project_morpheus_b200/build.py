@@ -26,7 +26,7 @@ def _nvcc() -> str:
 
 
 def sources():
-    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cpp")))
 
 
 def _stale() -> bool:

@@ -3,7 +3,7 @@
 TAG=$1; VAR=$2; VALS=$3
 OUT=gpurun_out/$TAG; mkdir -p $OUT
 for v in $VALS; do
-  env $VAR=$v timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --latency-reps 3 > $OUT/bench_$v.json 2> $OUT/bench_$v.err
+  env $VAR=$v timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --latency-reps 3 --long-read-batch 0 --ragged-streams 0 --ingest-streams 0 > $OUT/bench_$v.json 2> $OUT/bench_$v.err
   python - <<PY
 import json
 try:

@@ -4,7 +4,7 @@ TAG=$1; shift
 OUT=gpurun_out/$TAG; mkdir -p $OUT
 i=0
 for A in "$@"; do
-  timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --latency-reps 3 --long-read-batch 0 --ragged-streams 0 $A > $OUT/bench_$i.json 2> $OUT/bench_$i.err
+  timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --latency-reps 3 --long-read-batch 0 --ragged-streams 0 --ingest-streams 0 $A > $OUT/bench_$i.json 2> $OUT/bench_$i.err
   python - <<PY
 import json
 try:

@@ -3,7 +3,7 @@
 # Usage: gpurun -- bash scripts/gpu_profile_final.sh <tag>
 TAG=${1:-final}
 OUT=gpurun_out/$TAG; mkdir -p $OUT
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --latency-reps 1 --long-read-batch 0 --ragged-streams 0"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --latency-reps 1 --long-read-batch 0 --ragged-streams 0 --ingest-streams 0"
 $CMD > $OUT/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s 170 -c 120 --csv --log-file $OUT/launches.csv $CMD > $OUT/ncu_list.log 2>&1
 echo "list rc=$?"

@@ -3,7 +3,7 @@
 TAG=${1:-sweep}; CHUNKS=${2:-"32 128 512 1024"}
 OUT=gpurun_out/$TAG; mkdir -p $OUT
 for c in $CHUNKS; do
-  timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --latency-reps 3 --long-read-batch 0 --ragged-streams 0 --chunk $c > $OUT/bench_c$c.json 2> $OUT/bench_c$c.err
+  timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --latency-reps 3 --long-read-batch 0 --ragged-streams 0 --ingest-streams 0 --chunk $c > $OUT/bench_c$c.json 2> $OUT/bench_c$c.err
   python - <<PY
 import json
 try:

@@ -1,0 +1,165 @@
+"""N2 (native token ingress, csrc/ingest.cpp) without a GPU: the C++ parser against the golden token-id vectors and
+the Python restatement, the native tick scheduler against the Python one and the oracle's per-stream semantics."""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from oracle import speechpipe_ref as sp
+from project_morpheus_b200 import _lib, tokens
+from project_morpheus_b200.ingest import NativeIngest, NativeTickScheduler
+from project_morpheus_b200.scheduler import TickScheduler
+from helpers import load_golden
+
+
+def parse_native(text: str, index: int):
+    lib = _lib.load()
+    b = text.encode("utf-8", "surrogatepass")
+    out = C.c_int64()
+    rc = lib.snacb_parse_token(b, len(b), index, C.byref(out))
+    assert rc in (0, 1)
+    return int(out.value) if rc == 1 else None
+
+
+def fake_convert(window):
+    if len(window) < 7:
+        return None
+    f = len(window) // 7
+    toks = list(window[: 7 * f])
+    if any(t < 0 or t > 4096 for t in toks):
+        return None
+    if f == 1:
+        return b""
+    h = hashlib.sha256(np.asarray(toks, dtype=np.int32).tobytes()).digest()
+    return (h * 128)[:4096]
+
+
+def fake_batch(windows):
+    return [fake_convert(w) for w in windows]
+
+
+def test_parser_matches_golden_token_ids(ensure_lib):
+    for row in load_golden()["g2_token_ids"]:
+        assert parse_native(row["text"], row["index"]) == row["id"], row
+
+
+ASCII_PIECES = ["<custom_token_", ">", " ", "\t", "\n", "-", "+", "_", "0", "1", "7", "42", "4106", "28681", "x", "<", "custom",
+                "<custom_token_12>", "\x1c", "\r"]
+
+
+@settings(max_examples=400, deadline=None)
+@given(st.lists(st.sampled_from(ASCII_PIECES), min_size=0, max_size=8), st.integers(min_value=0, max_value=60))
+def test_parser_matches_python_restatement_on_ascii(pieces, index):
+    text = "".join(pieces)
+    tokens.token_id_cache.clear()
+    want = tokens.turn_token_into_id(text, index)
+    if want is not None and abs(want) > (1 << 61):
+        return  # beyond the documented clamp
+    assert parse_native(text, index) == want, repr(text)
+
+
+def dirty_stream(seed, frames):
+    rng = np.random.default_rng(seed)
+    s = sp.synth_token_strings(seed, frames)
+    for pos in sorted(rng.integers(0, len(s), frames).tolist(), reverse=True):
+        s.insert(pos, rng.choice(["<custom_token_10>", "junk", "<custom_token_3>", "", " <custom_token_4200> ", "<custom_token_99"]))
+    return s
+
+
+def run_scheduler(sched, streams, seed, evict=None):
+    for i in streams:
+        sched.add_stream(i)
+    cursors = {i: 0 for i in streams}
+    got = {i: [] for i in streams}
+    rng = np.random.default_rng(seed)
+    gone = set()
+    while any(cursors[i] < len(streams[i]) for i in streams if i not in gone):
+        for i in streams:
+            if i in gone:
+                continue
+            n = int(rng.integers(0, 12))
+            chunk = streams[i][cursors[i]: cursors[i] + n]
+            cursors[i] += len(chunk)
+            sched.push_many(i, chunk)
+        sched.tick()
+        for i in streams:
+            if i not in gone:
+                got[i] += sched.pop_audio(i)
+        if evict is not None and evict not in gone and cursors[evict] >= 21:
+            sched.evict(evict)
+            gone.add(evict)
+    for i in streams:
+        if i not in gone:
+            sched.finish(i)
+    sched.drain()
+    for i in streams:
+        if i not in gone:
+            got[i] += sched.pop_audio(i)
+            assert sched.done(i)
+    return got
+
+
+def test_native_scheduler_matches_python_scheduler_and_oracle(ensure_lib):
+    streams = {i: (dirty_stream(i, f) if i % 2 else sp.synth_token_strings(i, f))
+               for i, f in enumerate([1, 2, 3, 4, 5, 8, 10, 13, 7, 9, 0, 21])}
+    want = {i: list(sp.decode_stream(s, fake_convert)) for i, s in streams.items()}
+    py = run_scheduler(TickScheduler(fake_batch), streams, 0)
+    nat = run_scheduler(NativeTickScheduler(fake_batch, max_streams=16), streams, 0)
+    for i in streams:
+        assert nat[i] == py[i] == want[i], i
+
+
+def test_native_scheduler_golden_chunk_sizes(ensure_lib):
+    for row in load_golden()["g3_chunk_sizes"]:
+        if not isinstance(row["frames"], int):
+            continue
+        sched = NativeTickScheduler(fake_batch, max_streams=2)
+        got = run_scheduler(sched, {0: sp.synth_token_strings(3, row["frames"])}, 1)[0]
+        assert [len(c) for c in got] == row["sizes"], row
+
+
+def test_native_scheduler_evict_and_slot_reuse(ensure_lib):
+    streams = {i: sp.synth_token_strings(40 + i, f) for i, f in enumerate([6, 9, 5, 12])}
+    want = {i: list(sp.decode_stream(s, fake_convert)) for i, s in streams.items()}
+    sched = NativeTickScheduler(fake_batch, max_streams=4)
+    got = run_scheduler(sched, streams, 3, evict=2)
+    for i in (0, 1, 3):
+        assert got[i] == want[i]
+    assert len(got[2]) < len(want[2]) and got[2] == want[2][: len(got[2])]
+    sched.add_stream("again")  # the evicted slot starts clean
+    sched.push_many("again", streams[0])
+    sched.finish("again")
+    sched.drain()
+    assert sched.pop_audio("again") == want[0]
+
+
+def test_first_chunk_latch_follows_decode_result(ensure_lib):
+    """A rejected first chunk keeps the stream in first-chunk mode: the next accepted token probes again."""
+    calls = []
+
+    def decode(windows):
+        calls.append([list(w) for w in windows])
+        return [None if len(calls) == 1 else fake_convert(w) for w in windows]
+
+    sched = NativeTickScheduler(decode, max_streams=1)
+    sched.add_stream(0)
+    s = sp.synth_token_strings(5, 2)
+    sched.push_many(0, s[:9])
+    assert sched.tick() == 1 and len(calls[0][0]) == 7
+    assert sched.tick() == 1 and len(calls[1][0]) == 7 and calls[1][0] != calls[0][0]
+    assert sched.tick() == 0  # latched; the ninth token does not complete a frame
+
+
+def test_ingest_argument_checks(ensure_lib):
+    ing = NativeIngest(2)
+    with pytest.raises(_lib.SnacbError):
+        ing.push([5], ["<custom_token_11>"])
+    ing.finish(1)
+    with pytest.raises(_lib.SnacbError):
+        ing.push([1], ["<custom_token_11>"])
+    tok, ntok, owner = ing.tick()
+    assert len(ntok) == 0 and ing.done(1) and not ing.done(0)
+    assert ing.stats() == {"accepted": 0, "rejected": 0, "windows": 0}
+    ing.close()
