@@ -345,12 +345,12 @@ def run_ours(args) -> None:
 
         # Next row N2: token strings -> PCM chunks for every stream of a tick, through the Python tick scheduler
         # (per-token Python like the reference's tokens_decoder, one batched decode) and through the native ingress
-        # (csrc/ingest.cpp).  Steady state: 7 new token strings per stream per tick -> one 28-token window per stream.
+        # (csrc/ingest.cpp).  Steady state: 7 new token strings per stream per tick -> one 49-token (7-frame) window per stream.
         if args.ingest_streams > 0:
             from oracle import speechpipe_ref as sp_ref
             from project_morpheus_b200.ingest import NativeTickScheduler, decode_arrays_with
             from project_morpheus_b200.scheduler import TickScheduler
-            ns, warm_f, timed_ticks = args.ingest_streams, 5, 6
+            ns, warm_f, timed_ticks = args.ingest_streams, 8, 6  # warm-up reaches the 49-token steady state (workspace sized)
             strings = [sp_ref.synth_token_strings(70000 + i, warm_f + timed_ticks) for i in range(ns)]
             kk = np.arange(ns, dtype=np.uint64)
 

@@ -469,6 +469,54 @@ def test_long_read_full_size_properties(engines):
     assert np.abs(tail - full[:, -2048 * 8:]).max() <= 2e-3
 
 
+def test_native_ingest_scheduler_on_gpu_matches_per_stream_decoder(monkeypatch):
+    """Row N2 end to end: token strings -> native parser / planner (csrc/ingest.cpp) -> batched CUDA decode; every
+    stream's chunks equal what the per-stream ``tokens_decoder`` yields (same CUDA path, noise off)."""
+    monkeypatch.setenv("SNACB_NOISE", "off")
+    monkeypatch.setenv("SNACB_PRECISION", "fp16")
+    monkeypatch.setenv("SNACB_RANDOM_INIT", "0:w1")
+    monkeypatch.delenv("ORPHEUS_SNAC_PATH", raising=False)
+    import importlib
+    import sys
+    sys.modules.pop("project_morpheus_b200.speechpipe", None)
+    speechpipe = importlib.import_module("project_morpheus_b200.speechpipe")
+    from project_morpheus_b200.ingest import NativeTickScheduler
+
+    lifetimes = {0: 2, 1: 10, 2: 5, 3: 6, 4: 9, 5: 12, 6: 3, 7: 8, 8: 1}
+    streams = {i: sp.synth_token_strings(900 + i, f) for i, f in lifetimes.items()}
+    streams[3] = streams[3][:10] + ["junk", "<custom_token_10>", " <custom_token_5> "] + streams[3][10:]
+
+    async def per_stream(strings):
+        async def gen():
+            for s in strings:
+                yield s
+        return [c async for c in speechpipe.tokens_decoder(gen())]
+
+    want = {i: asyncio.run(per_stream(s)) for i, s in streams.items()}
+    sched = NativeTickScheduler(max_streams=16)
+    got = {i: [] for i in streams}
+    for i in streams:
+        sched.add_stream(i)
+    cur = {i: 0 for i in streams}
+    rng = np.random.default_rng(4)
+    while any(cur[i] < len(streams[i]) for i in streams):
+        for i in streams:
+            part = streams[i][cur[i]: cur[i] + int(rng.integers(0, 15))]
+            cur[i] += len(part)
+            sched.push_many(i, part)
+        sched.tick()
+        for i in streams:
+            got[i] += sched.pop_audio(i)
+    for i in streams:
+        sched.finish(i)
+    sched.drain()
+    for i in streams:
+        got[i] += sched.pop_audio(i)
+        assert sched.done(i)
+        assert got[i] == want[i], i
+    sched.close()
+
+
 @pytest.mark.parametrize("precision", PRECISIONS)
 def test_cuda_graph_latency_path_is_bit_identical(engines, precision):
     """Small uniform ticks through the host API are captured into a CUDA graph on their second call and
