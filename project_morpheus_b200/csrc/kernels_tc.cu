@@ -91,6 +91,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 // Multicast variants (thread-block clusters): the tile lands at the same shared-memory offset of every CTA in
 // `mask` and completes the transaction on each destination CTA's own mbarrier at that offset.
 __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
@@ -240,6 +246,22 @@ __device__ __forceinline__ void dw_unit(const float* p0, uint32_t mask_lo, uint3
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
       const int j = m - k;  // output fed through tap k
+      if (j >= 0 && j < L) acc[j % 7] = __ffma2_rn(W.w[k], v, (k == 0) ? W.bias : acc[j % 7]);
+    }
+    if (m >= 6) sink(m - 6, snake2(acc[(m - 6) % 7], W.al2, W.iv2));
+  }
+}
+// Same unit with its inputs already in shared memory (a TMA-loaded fp32 tile, row pitch C floats): plain LDS.64
+// with immediate offsets, no predicates (rows outside the sequence are zeros in the tile), no global-load latency.
+template <int C, int DIL, int L, typename Sink>
+__device__ __forceinline__ void dw_unit_smem(const float* p0, const DwPairW& W, Sink&& sink) {
+  float2 acc[7];
+#pragma unroll
+  for (int m = 0; m < L + 6; ++m) {
+    const float2 v = snake2(*reinterpret_cast<const float2*>(p0 + m * (DIL * C)), W.al1, W.iv1);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const int j = m - k;
       if (j >= 0 && j < L) acc[j % 7] = __ffma2_rn(W.w[k], v, (k == 0) ? W.bias : acc[j % 7]);
     }
     if (m >= 6) sink(m - 6, snake2(acc[(m - 6) % 7], W.al2, W.iv2));
@@ -925,6 +947,32 @@ bool get_tmap(const void* ptr, long long rows, int cols, int box_rows, CUtensorM
   CUtensorMap m;
   CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, m);
+  *out = m;
+  return true;
+}
+
+// fp32 activation tensor [items][rows][C] (channels-last), box = [1][box_rows][C], no swizzle: rows outside
+// [0, rows) of the addressed item arrive as zeros - exactly the conv's zero padding.
+bool get_tmap_x3(const float* ptr, int C, int rows, int n_items, int box_rows, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapHash> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  const MapKey key{ptr, (long long)rows * 65536 + n_items, C, box_rows};
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return true; }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)n_items};
+  cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)rows * C * 4};
+  cuuint32_t box[3] = {(cuuint32_t)C, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return false;
   if (cache.size() > 4096) cache.clear();
@@ -1862,6 +1910,176 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
   }
 }
 
+// ============================================================================ fused ResidualUnit, TMA-staged input
+// k_ru_tc for C = 64 (decoder block 3) with the fp32 input rows of the tile (128 + 6*DIL rows, halo included) brought
+// into shared memory by ONE TMA load of a 3-D tensor map [item][row][C] (rows outside the item come back as zeros =
+// the conv's zero padding): the depthwise units read them with LDS.64 at immediate offsets - no per-input LDG,
+// predicate or address arithmetic, nothing in flight in registers - and the epilogue takes the residual from the
+// same tile instead of re-reading global memory.  70-76 KB per CTA, still three CTAs per SM.
+template <int DIL> struct RuxSmem {
+  static constexpr int C = 64;
+  static constexpr int kABytes = BM * C * 2;
+  static constexpr int kWBytes = C * C * 2;
+  static constexpr int kBoxRows = BM + 6 * DIL;                        // rows the tile's outputs depend on
+  static constexpr int kFirstMax = (DIL == 1) ? 112 : (DIL == 3) ? 98 : 8;
+  static constexpr int kRows = kFirstMax + 21 * DIL + 1;               // rows the unrolled units may touch (the rest is never used)
+  static constexpr int kXBytes = (kRows > kBoxRows ? kRows : kBoxRows) * C * 4;  // DIL = 9: 50688 B -> 3 CTAs fit the SM's 228 KB
+  static constexpr int kBytes = kABytes + kWBytes + kXBytes + 64 + 1024;
+};
+
+template <int DIL>
+__global__ void __launch_bounds__(kRuThreads, 3) k_ru_x(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
+                                                        const RuDev a) {
+  constexpr int C = 64;
+  using S = RuxSmem<DIL>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_align1024(smem_raw);
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + S::kABytes;
+  float* sX = reinterpret_cast<float*>(smem + S::kABytes + S::kWBytes);
+  float* sStg = reinterpret_cast<float*>(smem);  // valid once the accumulator barrier has fired
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kABytes + S::kWBytes + S::kXBytes);  // [0] weight, [1] accumulator, [2] input tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int item = blockIdx.y;
+  const int row0 = (int)blockIdx.x * BM;
+  const ItemRef it = get_item(a.items, a.base, item, a.out_len);
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    mbar_init(smem_u32(&bars[2]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) tmem_alloc(smem_u32(tmem_slot), C);
+  if (a.prefetch_ahead > 0 && tid == 64) {
+    const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + a.prefetch_ahead;
+    const int pit = (int)(lin / gridDim.x), ptile = (int)(lin - (long long)pit * gridDim.x);
+    if (pit < (int)gridDim.y) {
+      const int r_lo = max(a.out_lo + ptile * BM - 3 * DIL - a.in_lo, 0);
+      const int r_hi = min(a.out_lo + ptile * BM + BM + 3 * DIL - a.in_lo, a.in_rows);
+      const char* p = reinterpret_cast<const char*>(a.x + ((size_t)pit * a.in_rows + r_lo) * C);
+      if (r_hi > r_lo) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"((uint32_t)(r_hi - r_lo) * C * 4) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 9) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(smem_u32(&bars[2]), (uint32_t)(S::kBoxRows * C * 4));
+      tma_load_3d(smem_u32(sX), &tmX, smem_u32(&bars[2]), 0, a.out_lo + row0 - 3 * DIL - a.in_lo, item);
+      mbar_arrive_expect_tx(smem_u32(&bars[0]), S::kWBytes);
+      tma_load_2d(smem_u32(sW), &tmW, smem_u32(&bars[0]), 0, 0);
+    }
+  } else {
+    constexpr int CP = C / 2;
+    constexpr int U = (DIL == 1) ? 8 : 9;
+    const int idx = tid;  // CP * U <= 288 workers: one unit per thread
+    if (idx < CP * U) {
+      const int cp = idx % CP, u = idx / CP;
+      int first;
+      if (DIL == 1) first = u * 16;
+      else if (DIL == 3) first = (u % 3) + (u / 3) * 48;
+      else first = u;
+      const int c = cp * 2;
+      DwPairW W;
+      W.load(a.w7, a.dw_b, a.a1, a.i1, a.a2, a.i2, C, c);
+      uint8_t* a_kb = sA + ((c * 2) & 15);
+      const int chunk = (c * 2) >> 4;
+      mbar_wait(smem_u32(&bars[2]), 0);
+      dw_unit_smem<C, DIL, 16>(sX + first * C + c, W, [&](int j, float2 v) {
+        const int trow = first + j * DIL;
+        if (trow < BM)
+          *reinterpret_cast<__half2*>(a_kb + trow * 128 + (((chunk ^ trow) & 7) << 4)) = __floats2half2_rn(v.x, v.y);
+      });
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == 9) {
+    if (lane == 0) {
+      mbar_wait(smem_u32(&bars[0]), 0);
+      tc_fence_after();
+      constexpr uint32_t idesc = umma_idesc_f16(C);
+      const uint64_t da = umma_desc_k_sw128(smem_u32(sA)), db = umma_desc_k_sw128(smem_u32(sW));
+#pragma unroll
+      for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, k ? 1u : 0u);
+      umma_commit(smem_u32(&bars[1]));
+    }
+  } else if (warp < 8) {
+    const int q = warp & 3, half = warp >> 2;
+    constexpr int NH = C / 32;
+    const int c4 = lane & 3, r8 = lane >> 2;
+    float* stg = sStg + warp * (32 * 16);
+    float* st_p = stg + lane * 16;
+    const int st_x = (lane >> 1) & 3;
+    const float* ld_p = stg + r8 * 16 + ((c4 ^ ((r8 >> 1) & 3)) << 2);
+    const int orow_b = row0 + q * 32 + r8;
+    const int tabs_b = a.out_lo + orow_b + it.shift0 * a.up;
+    uint32_t vmask = 0, lmask = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (orow_b + 8 * i < a.out_rows) {
+        vmask |= 1u << i;
+        const int t = tabs_b + 8 * i;
+        if (t >= 0 && t < a.T0 * a.up) lmask |= 1u << i;
+      }
+    }
+    const int colb = half * (C / 2) + c4 * 4;
+    const size_t ob = ((size_t)item * a.out_rows + orow_b) * C + colb;
+    const float* rs = sX + (q * 32 + r8 + 3 * DIL) * C + colb;  // residual = centre-tap input rows of the tile
+    mbar_wait(smem_u32(&bars[1]), 0);
+    tc_fence_after();
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (C / 2) + h * 16), r);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<float4*>(st_p + ((j ^ st_x) << 2)) =
+            make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                        __uint_as_float(r[4 * j + 3]));
+      __syncwarp();
+      float4 v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(ld_p + i * 128);
+      __syncwarp();
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.pw_b + colb + h * 16));
+      float4 al = make_float4(0.f, 0.f, 0.f, 0.f), iv = al;
+      if (a.sn_alpha) {
+        al = __ldg(reinterpret_cast<const float4*>(a.sn_alpha + colb + h * 16));
+        iv = __ldg(reinterpret_cast<const float4*>(a.sn_inv + colb + h * 16));
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (!((vmask >> i) & 1u)) continue;
+        const float4 res = *reinterpret_cast<const float4*>(rs + i * 8 * C + h * 16);
+        float4 x = add4(add4(v[i], b4), res);
+        if (!((lmask >> i) & 1u)) x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.out32) *reinterpret_cast<float4*>(a.out32 + ob + i * 8 * C + h * 16) = x;
+        if (a.out16) {
+          if (a.sn_alpha) {
+            const float2 lo = snake2(make_float2(x.x, x.y), make_float2(al.x, al.y), make_float2(iv.x, iv.y));
+            const float2 hi = snake2(make_float2(x.z, x.w), make_float2(al.z, al.w), make_float2(iv.z, iv.w));
+            x = make_float4(lo.x, lo.y, hi.x, hi.y);
+          }
+          store_half4(a.out16 + ob + i * 8 * C + h * 16, x);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C);
+  }
+}
+
 // ============================================================================ persistent fused ResidualUnit
 // Same math as k_ru_tc, restructured so that nothing waits on anything it does not need:
 // one persistent CTA per SM walks tiles (item, 128 rows) round-robin with three kinds of warps running
@@ -2136,8 +2354,27 @@ cudaError_t launch_ru_tail(const CUtensorMap& mw, const RuDev& d, dim3 grid, cud
   k_ru_tc<64, 9, true><<<grid, kRuThreads, bytes, st>>>(mw, d);
   return cudaGetLastError();
 }
+const bool g_ru_tma = [] { const char* v = getenv("SNACB_RU_TMA"); return !(v && v[0] == '0'); }();
+template <int DIL>
+cudaError_t launch_ru_x(const CUtensorMap& mw, const RuDev& d, dim3 grid, cudaStream_t st) {
+  CUtensorMap mx;
+  if (!get_tmap_x3(d.x, 64, d.in_rows, (int)grid.y, RuxSmem<DIL>::kBoxRows, &mx)) return cudaErrorNotSupported;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_ru_x<DIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, RuxSmem<DIL>::kBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  k_ru_x<DIL><<<grid, kRuThreads, RuxSmem<DIL>::kBytes, st>>>(mw, mx, d);
+  return cudaGetLastError();
+}
 template <int C>
 cudaError_t launch_ru_c(int dil, const CUtensorMap& mw, const RuDev& d, dim3 grid, cudaStream_t st) {
+  if (C == 64 && g_ru_tma && d.in_rows < 65536 && grid.y < 65536) {
+    if (dil == 1) return launch_ru_x<1>(mw, d, grid, st);
+    if (dil == 3) return launch_ru_x<3>(mw, d, grid, st);
+    return launch_ru_x<9>(mw, d, grid, st);
+  }
   if (dil == 1) return launch_ru_t<C, 1>(mw, d, grid, st);
   if (dil == 3) return launch_ru_t<C, 3>(mw, d, grid, st);
   return launch_ru_t<C, 9>(mw, d, grid, st);
