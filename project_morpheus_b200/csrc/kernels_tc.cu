@@ -957,18 +957,19 @@ bool get_tmap(const void* ptr, long long rows, int cols, int box_rows, CUtensorM
 
 // fp32 activation tensor [items][rows][C] (channels-last), box = [1][box_rows][C], no swizzle: rows outside
 // [0, rows) of the addressed item arrive as zeros - exactly the conv's zero padding.
-bool get_tmap_x3(const float* ptr, int C, int rows, int n_items, int box_rows, CUtensorMap* out) {
+bool get_tmap_x3(const float* ptr, int C, int rows, int n_items, int box_rows, CUtensorMap* out, int box_c = 0) {
+  if (box_c <= 0) box_c = C;
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapHash> cache;
   std::lock_guard<std::mutex> lk(mu);
-  const MapKey key{ptr, (long long)rows * 65536 + n_items, C, box_rows};
+  const MapKey key{ptr, (long long)rows * 65536 + n_items, C * 1024 + box_c, box_rows};
   auto it = cache.find(key);
   if (it != cache.end()) { *out = it->second; return true; }
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)n_items};
   cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)rows * C * 4};
-  cuuint32_t box[3] = {(cuuint32_t)C, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[3] = {(cuuint32_t)box_c, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMap m;
   CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
@@ -1637,7 +1638,10 @@ void launch_dw_tc_c(const GroupCtx& g, const DwTcArgs& a) {
   else k_dw_tc<C, 9><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, a);
 }
 
+bool launch_dw_x(const GroupCtx& g, const DwTcArgs& a);  // TMA-staged variant (defined below), false = not applicable
+
 void launch_dw_tc(const GroupCtx& g, const DwTcArgs& a) {
+  if (launch_dw_x(g, a)) return;
   switch (a.C) {
     case 64: launch_dw_tc_c<64>(g, a); break;
     case 128: launch_dw_tc_c<128>(g, a); break;
@@ -2080,6 +2084,69 @@ __global__ void __launch_bounds__(kRuThreads, 3) k_ru_x(const __grid_constant__ 
   }
 }
 
+// ============================================================================ depthwise k=7 -> fp16, TMA-staged input
+// k_dw_tc for the wide blocks (C = 256 / 512) with the same input staging as k_ru_x: one CTA = 128 output rows x 64
+// channels of one item, its (128 + 6*DIL) x 64 fp32 input rows arrive by one 3-D TMA load (zero-filled outside the
+// item), every thread runs one 16-output unit out of shared memory.  Replaces 22 cp.async + address / predicate
+// arithmetic per unit (the standalone kernel is issue-bound: ncu 0.65 instructions per cycle and scheduler).
+template <int DIL>
+__global__ void __launch_bounds__((DIL == 1) ? 256 : 288, (DIL == 1) ? 4 : 3)
+k_dw_x(const __grid_constant__ CUtensorMap tmX, const Item* items, int base, int out_len, int T0, DwTcArgs a, int n_cb, int pf) {
+  constexpr int CB = 64;
+  using S = RuxSmem<DIL>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  float* sX = reinterpret_cast<float*>(smem);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::kXBytes);
+  const int tid = threadIdx.x;
+  const int item = blockIdx.y;
+  const int tile = (int)blockIdx.x / n_cb, cb = (int)blockIdx.x % n_cb;  // channel block fastest
+  const int row0 = tile * BM;
+  const int out_rows = a.out_r.n();
+  if (tid == 0) {
+    mbar_init(smem_u32(bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_arrive_expect_tx(smem_u32(bar), (uint32_t)(S::kBoxRows * CB * 4));
+    tma_load_3d(smem_u32(sX), &tmX, smem_u32(bar), cb * CB, a.out_r.lo + row0 - 3 * DIL - a.in_r.lo, item);
+  }
+  if (pf > 0 && cb == 0 && tid == 32) {
+    // the row tile `pf` CTAs ahead in launch order (all its channel blocks: whole rows, contiguous) -> L2
+    const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + pf;
+    const int pit = (int)(lin / gridDim.x), ptile = (int)(lin - (long long)pit * gridDim.x) / n_cb;
+    if (pit < (int)gridDim.y) {
+      const int in_rows = a.in_r.n();
+      const int r_lo = max(a.out_r.lo + ptile * BM - 3 * DIL - a.in_r.lo, 0);
+      const int r_hi = min(a.out_r.lo + ptile * BM + BM + 3 * DIL - a.in_r.lo, in_rows);
+      const char* p = reinterpret_cast<const char*>(a.in + ((size_t)pit * in_rows + r_lo) * a.C);
+      if (r_hi > r_lo) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"((uint32_t)(r_hi - r_lo) * a.C * 4) : "memory");
+    }
+  }
+  constexpr int CP = CB / 2;
+  const int cp = tid % CP, u = tid / CP;
+  int first;
+  if (DIL == 1) first = u * 16;
+  else if (DIL == 3) first = (u % 3) + (u / 3) * 48;
+  else first = u;
+  const int cl = cp * 2, c = cb * CB + cl;
+  const ItemRef it = get_item(items, base, item, out_len);
+  DwPairW W;
+  W.load(a.w7, a.bias, a.a1, a.i1, a.a2, a.i2, a.C, c);
+  __half* o = a.out + ((size_t)item * out_rows + row0) * a.C + c;
+  const int t_abs0 = a.out_r.lo + row0 + it.shift0 * a.up, t_hi = T0 * a.up;
+  mbar_wait(smem_u32(bar), 0);
+  dw_unit_smem<CB, DIL, 16>(sX + first * CB + cl, W, [&](int j, float2 v) {
+    const int trow = first + j * DIL;
+    if (trow < BM && row0 + trow < out_rows) {
+      const int t_abs = t_abs0 + trow;
+      if (t_abs < 0 || t_abs >= t_hi) v = make_float2(0.f, 0.f);
+      *reinterpret_cast<__half2*>(o + (size_t)trow * a.C) = __floats2half2_rn(v.x, v.y);
+    }
+  });
+}
+
 // ============================================================================ persistent fused ResidualUnit
 // Same math as k_ru_tc, restructured so that nothing waits on anything it does not need:
 // one persistent CTA per SM walks tiles (item, 128 rows) round-robin with three kinds of warps running
@@ -2381,6 +2448,31 @@ cudaError_t launch_ru_c(int dil, const CUtensorMap& mw, const RuDev& d, dim3 gri
 }
 
 }  // namespace
+
+// measured 0.61 vs 0.59 ms per tick for the standalone depthwise class (HBM-bound either way): opt-in
+const bool g_dw_tma = [] { const char* v = getenv("SNACB_DW_TMA"); return v && v[0] == '1'; }();
+template <int DIL>
+bool launch_dw_x_t(const GroupCtx& g, const DwTcArgs& a, const CUtensorMap& mx) {
+  constexpr int bytes = RuxSmem<DIL>::kXBytes + 16 + 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_dw_x<DIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) { cudaGetLastError(); return false; }
+    attr_set = true;
+  }
+  const int n_cb = a.C / 64, tiles = (a.out_r.n() + BM - 1) / BM;
+  dim3 grid((unsigned)(tiles * n_cb), (unsigned)g.n_items);
+  static const int pf_on = [] { const char* v = getenv("SNACB_PREFETCH"); return (v && v[0] == '0') ? 0 : 1; }();
+  const int pf = pf_on ? sm_count() * ((DIL == 1) ? 4 : 3) : 0;
+  k_dw_x<DIL><<<grid, (DIL == 1) ? 256 : 288, bytes, g.stream>>>(mx, g.items, g.base, g.out_len, g.T0, a, n_cb, pf);
+  return true;
+}
+bool launch_dw_x(const GroupCtx& g, const DwTcArgs& a) {
+  if (!g_dw_tma || a.C % 64 || a.C < 128 || g.n_items >= 65536 || a.in_r.n() >= 65536 || a.out_r.n() <= 0) return false;
+  CUtensorMap mx;
+  const int box = BM + 6 * a.dil;
+  if (!get_tmap_x3(a.in, a.C, a.in_r.n(), g.n_items, box, &mx, 64)) return false;
+  return a.dil == 1 ? launch_dw_x_t<1>(g, a, mx) : a.dil == 3 ? launch_dw_x_t<3>(g, a, mx) : launch_dw_x_t<9>(g, a, mx);
+}
 
 bool ru_tc_supported(int C, bool persistent) { return C == 64 || C == 128 || (C == 256 && persistent); }
 
