@@ -1954,6 +1954,11 @@ __global__ void __launch_bounds__(kRuThreads, 3) k_ru_x(const __grid_constant__ 
     mbar_init(smem_u32(&bars[1]), 1);
     mbar_init(smem_u32(&bars[2]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // the loads start before anything else of the CTA's setup (the issuing thread initialised the barriers itself)
+    mbar_arrive_expect_tx(smem_u32(&bars[2]), (uint32_t)(S::kBoxRows * C * 4));
+    tma_load_3d(smem_u32(sX), &tmX, smem_u32(&bars[2]), 0, a.out_lo + row0 - 3 * DIL - a.in_lo, item);
+    mbar_arrive_expect_tx(smem_u32(&bars[0]), S::kWBytes);
+    tma_load_2d(smem_u32(sW), &tmW, smem_u32(&bars[0]), 0, 0);
   }
   if (warp == 9) tmem_alloc(smem_u32(tmem_slot), C);
   if (a.prefetch_ahead > 0 && tid == 64) {
@@ -1971,14 +1976,7 @@ __global__ void __launch_bounds__(kRuThreads, 3) k_ru_x(const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 9) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(smem_u32(&bars[2]), (uint32_t)(S::kBoxRows * C * 4));
-      tma_load_3d(smem_u32(sX), &tmX, smem_u32(&bars[2]), 0, a.out_lo + row0 - 3 * DIL - a.in_lo, item);
-      mbar_arrive_expect_tx(smem_u32(&bars[0]), S::kWBytes);
-      tma_load_2d(smem_u32(sW), &tmW, smem_u32(&bars[0]), 0, 0);
-    }
-  } else {
+  if (warp != 9) {
     constexpr int CP = C / 2;
     constexpr int U = (DIL == 1) ? 8 : 9;
     const int idx = tid;  // CP * U <= 288 workers: one unit per thread
