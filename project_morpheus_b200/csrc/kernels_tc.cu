@@ -267,6 +267,17 @@ __device__ __forceinline__ void dw_unit_smem(const float* p0, const DwPairW& W, 
     if (m >= 6) sink(m - 6, snake2(acc[(m - 6) % 7], W.al2, W.iv2));
   }
 }
+// Unit lengths of the 128-row tile decomposition used by the fused ResidualUnit kernels (unit u of a channel pair:
+// DIL 1 -> rows 16u..16u+15; DIL 3 -> residue u%3 of the 48-row segment u/3; DIL 9 -> residue u): the number of
+// outputs that fall inside the tile is a compile-time constant per group, so no unit computes (or loads inputs for)
+// rows beyond row 127 and the per-output bound check disappears.
+template <int N> struct IntC { static constexpr int value = N; };
+template <int DIL, typename F>
+__device__ __forceinline__ void unit_len_dispatch(int u, F&& f) {
+  if (DIL == 1) f(IntC<16>{});
+  else if (DIL == 9) { if (u < 2) f(IntC<15>{}); else f(IntC<14>{}); }
+  else { if (u < 6) f(IntC<16>{}); else if (u % 3 != 2) f(IntC<11>{}); else f(IntC<10>{}); }
+}
 // Same unit with its L+6 inputs staged through shared memory by cp.async: all loads of the unit are in
 // flight at once without holding a register each (the register-resident version lets the compiler
 // interleave loads and uses, which exposes the global latency at almost every input - ncu: long
@@ -1756,15 +1767,17 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
       DwPairW W;
       W.load(a.w7, a.dw_b, a.a1, a.i1, a.a2, a.i2, C, c);
       const int in_first = a.out_lo + row0 + first - 3 * DIL - a.in_lo;  // operand row of window element 0
-      uint32_t mlo, mhi;
-      row_mask<DIL>(in_first, a.in_rows, 22, mlo, mhi);
       // K-major SWIZZLE_128B operand tile: byte (row, col) -> row*128 + ((col/16 ^ row%8) * 16) + col%16
       uint8_t* a_kb = sA + (c / BK) * (BM * 128) + ((c % BK) * 2 & 15);
       const int chunk = ((c % BK) * 2) >> 4;
-      dw_unit<C, DIL, 16>(xin + (long long)in_first * C + c, mlo, mhi, W, [&](int j, float2 v) {
-        const int trow = first + j * DIL;
-        if (trow < BM)
+      unit_len_dispatch<DIL>(u, [&](auto len) {
+        constexpr int L = decltype(len)::value;
+        uint32_t mlo, mhi;
+        row_mask<DIL>(in_first, a.in_rows, L + 6, mlo, mhi);
+        dw_unit<C, DIL, L>(xin + (long long)in_first * C + c, mlo, mhi, W, [&](int j, float2 v) {
+          const int trow = first + j * DIL;  // < 128 by construction of the unit length
           *reinterpret_cast<__half2*>(a_kb + trow * 128 + (((chunk ^ trow) & 7) << 4)) = __floats2half2_rn(v.x, v.y);
+        });
       });
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
@@ -1925,9 +1938,7 @@ template <int DIL> struct RuxSmem {
   static constexpr int kABytes = BM * C * 2;
   static constexpr int kWBytes = C * C * 2;
   static constexpr int kBoxRows = BM + 6 * DIL;                        // rows the tile's outputs depend on
-  static constexpr int kFirstMax = (DIL == 1) ? 112 : (DIL == 3) ? 98 : 8;
-  static constexpr int kRows = kFirstMax + 21 * DIL + 1;               // rows the unrolled units may touch (the rest is never used)
-  static constexpr int kXBytes = (kRows > kBoxRows ? kRows : kBoxRows) * C * 4;  // DIL = 9: 50688 B -> 3 CTAs fit the SM's 228 KB
+  static constexpr int kXBytes = kBoxRows * C * 4;  // unit lengths are exact (unit_len_dispatch): no unit reads past the box
   static constexpr int kBytes = kABytes + kWBytes + kXBytes + 64 + 1024;
 };
 
@@ -1992,10 +2003,11 @@ __global__ void __launch_bounds__(kRuThreads, 3) k_ru_x(const __grid_constant__ 
       uint8_t* a_kb = sA + ((c * 2) & 15);
       const int chunk = (c * 2) >> 4;
       mbar_wait(smem_u32(&bars[2]), 0);
-      dw_unit_smem<C, DIL, 16>(sX + first * C + c, W, [&](int j, float2 v) {
-        const int trow = first + j * DIL;
-        if (trow < BM)
+      unit_len_dispatch<DIL>(u, [&](auto len) {
+        dw_unit_smem<C, DIL, decltype(len)::value>(sX + first * C + c, W, [&](int j, float2 v) {
+          const int trow = first + j * DIL;  // < 128 by construction of the unit length
           *reinterpret_cast<__half2*>(a_kb + trow * 128 + (((chunk ^ trow) & 7) << 4)) = __floats2half2_rn(v.x, v.y);
+        });
       });
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -2135,13 +2147,15 @@ k_dw_x(const __grid_constant__ CUtensorMap tmX, const Item* items, int base, int
   __half* o = a.out + ((size_t)item * out_rows + row0) * a.C + c;
   const int t_abs0 = a.out_r.lo + row0 + it.shift0 * a.up, t_hi = T0 * a.up;
   mbar_wait(smem_u32(bar), 0);
-  dw_unit_smem<CB, DIL, 16>(sX + first * CB + cl, W, [&](int j, float2 v) {
-    const int trow = first + j * DIL;
-    if (trow < BM && row0 + trow < out_rows) {
-      const int t_abs = t_abs0 + trow;
-      if (t_abs < 0 || t_abs >= t_hi) v = make_float2(0.f, 0.f);
-      *reinterpret_cast<__half2*>(o + (size_t)trow * a.C) = __floats2half2_rn(v.x, v.y);
-    }
+  unit_len_dispatch<DIL>(u, [&](auto len) {
+    dw_unit_smem<CB, DIL, decltype(len)::value>(sX + first * CB + cl, W, [&](int j, float2 v) {
+      const int trow = first + j * DIL;  // < 128 by construction of the unit length
+      if (row0 + trow < out_rows) {
+        const int t_abs = t_abs0 + trow;
+        if (t_abs < 0 || t_abs >= t_hi) v = make_float2(0.f, 0.f);
+        *reinterpret_cast<__half2*>(o + (size_t)trow * a.C) = __floats2half2_rn(v.x, v.y);
+      }
+    });
   });
 }
 

@@ -8,6 +8,6 @@ $CMD > $OUT/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s 170 -c 120 --csv --log-file $OUT/launches.csv $CMD > $OUT/ncu_list.log 2>&1
 echo "list rc=$?"
 $CMD > $OUT/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_ru_tc -s 24 -c 6 -o $OUT/prof $CMD > $OUT/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_ru_ -s 24 -c 6 -o $OUT/prof $CMD > $OUT/ncu_full.log 2>&1
 echo "full rc=$?"
 tail -n 2 $OUT/plain.log | cut -c1-300
