@@ -231,6 +231,16 @@ int snacb_get_tap_shape(const snacb_engine* e, int32_t* rows, int32_t* channels,
  * (lo, hi) pairs: z, head, then per decoder block: in, q, convT, ru0, ru1, ru2. Needs no GPU. */
 int snacb_plan(int32_t frames, int32_t out_lo, int32_t out_hi, int32_t clip, int32_t* ranges);
 
+/* Pipelined form of snacb_decode_windows_host for throughput: _submit copies the inputs, enqueues H2D + kernels on
+ * `stream` and the PCM / status D2H on an internal copy stream, and returns a ticket without waiting; _wait blocks until
+ * that tick's h_pcm / h_status (the pointers given to _submit; pinned ones are written directly) are complete.  At most
+ * two ticks in flight (submit t+1, then wait t): the D2H and the host work of tick t overlap the kernels of tick t+1.
+ * noise_mode: SNACB_NOISE_OFF or SNACB_NOISE_PHILOX. */
+int snacb_decode_windows_host_submit(snacb_engine* e, const int32_t* h_tokens, int32_t tokens_stride, const int32_t* h_ntok,
+                                     int32_t ntok_uniform, int32_t n_win, int32_t noise_mode, uint64_t seed,
+                                     const uint64_t* h_keys, int16_t* h_pcm, int32_t* h_status, void* stream, int32_t* ticket);
+int snacb_decode_windows_host_wait(snacb_engine* e, int32_t ticket);
+
 /* ---- N2: token ingress for many streams (host only, no GPU) ---------------------------------- */
 
 /* Replaces, batched over streams, the per-token Python of speechpipe.py:146-189 (turn_token_into_id: the last

@@ -82,6 +82,8 @@ SIGNATURES = {
     "snacb_deinterleave_raw": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "snacb_decode_windows": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _i64, _u64, _vp, _vp, _vp, _vp]),
     "snacb_decode_windows_host": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _i64, _u64, _vp, _vp, _vp, _vp]),
+    "snacb_decode_windows_host_submit": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _i32, _u64, _vp, _vp, _vp, _vp, C.POINTER(_i32)]),
+    "snacb_decode_windows_host_wait": (_i32, [_vp, _i32]),
     "snacb_decode_codes": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _u64, _vp, _vp, _vp]),
     "snacb_fill_noise": (_i32, [_vp, _u64, _vp, _i32, _i32, _vp, _i64, _vp]),
     "snacb_profile_enable": (_i32, [_vp, _i32]),

@@ -69,6 +69,20 @@ struct snacb_engine {
   size_t pin_bytes = 0;
   char* dstage = nullptr;
   size_t dstage_bytes = 0;
+  // pipelined host ticks (snacb_decode_windows_host_submit / _wait): two slots, the device -> host copy of tick t runs on
+  // copy_stream under the kernels of tick t+1
+  struct PipeSlot {
+    char* pin = nullptr; size_t pin_bytes = 0;
+    char* dst = nullptr; size_t dst_bytes = 0;
+    cudaEvent_t tail_done = nullptr, copied = nullptr;
+    bool busy = false;
+    int n_win = 0;
+    int16_t* h_pcm = nullptr; int32_t* h_status = nullptr;  // caller's destinations
+    bool direct = false;                                      // D2H went straight into the caller's pinned buffers
+    size_t pcm_off = 0, st_off = 0;
+  } pipe[2];
+  int pipe_next = 0;
+  cudaStream_t copy_stream = nullptr;
   Item* pin_items = nullptr;
   size_t pin_items_cap = 0;
   cudaEvent_t items_ev = nullptr;
@@ -610,6 +624,13 @@ void snacb_destroy(snacb_engine* e) {
   if (e->harena) cudaFree(e->harena);
   if (e->ws) cudaFree(e->ws);
   if (e->dstage) cudaFree(e->dstage);
+  for (auto& sl : e->pipe) {
+    if (sl.dst) cudaFree(sl.dst);
+    if (sl.pin) cudaFreeHost(sl.pin);
+    if (sl.tail_done) cudaEventDestroy(sl.tail_done);
+    if (sl.copied) cudaEventDestroy(sl.copied);
+  }
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->pin) cudaFreeHost(e->pin);
   if (e->pin_items) cudaFreeHost(e->pin_items);
   if (e->items_ev) cudaEventDestroy(e->items_ev);
@@ -982,6 +1003,79 @@ int snacb_decode_windows_host(snacb_engine* e, const int32_t* h_tokens, int32_t 
   CU(e, cudaStreamSynchronize(st));
   if (!pcm_pinned) memcpy(h_pcm, hp + tok_b, (size_t)n_win * 4096);
   memcpy(h_status, hp + tok_b + pcm_b, (size_t)n_win * 4);
+  return SNACB_OK;
+}
+
+int snacb_decode_windows_host_submit(snacb_engine* e, const int32_t* h_tokens, int32_t tokens_stride, const int32_t* h_ntok,
+                                     int32_t ntok_uniform, int32_t n_win, int32_t noise_mode, uint64_t seed,
+                                     const uint64_t* h_keys, int16_t* h_pcm, int32_t* h_status, void* stream, int32_t* ticket) {
+  if (!e) return SNACB_EINVAL;
+  if (n_win <= 0 || !h_tokens || !h_pcm || !h_status || !ticket || noise_mode == SNACB_NOISE_TENSOR)
+    return fail(e, SNACB_EINVAL, "snacb_decode_windows_host_submit: bad argument (n_win > 0, noise off / philox only)");
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(e, cudaSetDevice(e->device));
+  const int si = e->pipe_next;
+  snacb_engine::PipeSlot& sl = e->pipe[si];
+  if (sl.busy) return fail(e, SNACB_ESTATE, "snacb_decode_windows_host_submit: two ticks already in flight, wait for the older one first");
+  if (!e->copy_stream) CU(e, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  if (!sl.tail_done) {
+    CU(e, cudaEventCreateWithFlags(&sl.tail_done, cudaEventDisableTiming));
+    CU(e, cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
+  }
+  const size_t tok_n = (size_t)n_win * tokens_stride * 4;
+  const size_t tok_b = pad256(tok_n), pcm_b = pad256((size_t)n_win * 4096), st_b = pad256((size_t)n_win * 4);
+  const size_t key_b = pad256((size_t)n_win * 8), ntok_b = pad256((size_t)n_win * 4);
+  const size_t total = tok_b + pcm_b + st_b + key_b + ntok_b;
+  if (total > sl.pin_bytes) {
+    if (sl.pin) CU(e, cudaFreeHost(sl.pin));
+    sl.pin_bytes = total + total / 2;
+    CU(e, cudaMallocHost((void**)&sl.pin, sl.pin_bytes));
+  }
+  if (total > sl.dst_bytes) {
+    CU(e, cudaDeviceSynchronize());
+    if (sl.dst) CU(e, cudaFree(sl.dst));
+    sl.dst_bytes = total + total / 2;
+    CU(e, cudaMalloc((void**)&sl.dst, sl.dst_bytes));
+  }
+  char* hp = sl.pin; char* dp = sl.dst;
+  int32_t* d_tok = reinterpret_cast<int32_t*>(dp);
+  int16_t* d_pcm = reinterpret_cast<int16_t*>(dp + tok_b);
+  int32_t* d_st = reinterpret_cast<int32_t*>(dp + tok_b + pcm_b);
+  const size_t key_off = tok_b + pcm_b + st_b, ntok_off = key_off + key_b;
+  // inputs are copied into the slot's pinned block: the caller's arrays may be re-used as soon as this returns
+  memcpy(hp, h_tokens, tok_n);
+  const uint64_t* keys_p = nullptr;
+  if (h_keys) { memcpy(hp + key_off, h_keys, (size_t)n_win * 8); keys_p = reinterpret_cast<const uint64_t*>(hp + key_off); }
+  const int32_t* ntok_p = nullptr;
+  if (h_ntok) { memcpy(hp + ntok_off, h_ntok, (size_t)n_win * 4); ntok_p = reinterpret_cast<const int32_t*>(hp + ntok_off); }
+  CU(e, cudaMemcpyAsync(d_tok, hp, tok_n, cudaMemcpyHostToDevice, st));
+  int rc = snacb_decode_windows(e, d_tok, tokens_stride, ntok_p, ntok_uniform, n_win, noise_mode, nullptr, 0, seed, keys_p, d_pcm,
+                                d_st, stream);
+  if (rc) return rc;
+  CU(e, cudaEventRecord(sl.tail_done, st));
+  CU(e, cudaStreamWaitEvent(e->copy_stream, sl.tail_done, 0));
+  sl.direct = is_pinned(h_pcm) && is_pinned(h_status);
+  sl.pcm_off = tok_b; sl.st_off = tok_b + pcm_b;
+  CU(e, cudaMemcpyAsync(sl.direct ? (void*)h_pcm : (void*)(hp + sl.pcm_off), d_pcm, (size_t)n_win * 4096, cudaMemcpyDeviceToHost, e->copy_stream));
+  CU(e, cudaMemcpyAsync(sl.direct ? (void*)h_status : (void*)(hp + sl.st_off), d_st, (size_t)n_win * 4, cudaMemcpyDeviceToHost, e->copy_stream));
+  CU(e, cudaEventRecord(sl.copied, e->copy_stream));
+  sl.busy = true; sl.n_win = n_win; sl.h_pcm = h_pcm; sl.h_status = h_status;
+  *ticket = si;
+  e->pipe_next = si ^ 1;
+  return SNACB_OK;
+}
+
+int snacb_decode_windows_host_wait(snacb_engine* e, int32_t ticket) {
+  if (!e) return SNACB_EINVAL;
+  if (ticket < 0 || ticket > 1 || !e->pipe[ticket].busy) return fail(e, SNACB_EINVAL, "snacb_decode_windows_host_wait: no tick in flight under this ticket");
+  snacb_engine::PipeSlot& sl = e->pipe[ticket];
+  CU(e, cudaSetDevice(e->device));
+  CU(e, cudaEventSynchronize(sl.copied));
+  if (!sl.direct) {
+    memcpy(sl.h_pcm, sl.pin + sl.pcm_off, (size_t)sl.n_win * 4096);
+    memcpy(sl.h_status, sl.pin + sl.st_off, (size_t)sl.n_win * 4);
+  }
+  sl.busy = false;
   return SNACB_OK;
 }
 

@@ -151,6 +151,7 @@ int32_t snacb_ingest_tick(snacb_ingest* g, int32_t max_win, int32_t* tokens, int
   int32_t n_out = 0;
   for (size_t si = 0; si < g->s.size() && n_out < max_win; ++si) {
     Stream& st = g->s[si];
+    if (st.first_pending) continue;  // its first-chunk probe is still being decoded (pipelined ticks): the next window depends on it
     int emit = 0;      // window length in tokens, taken from the end of ids
     bool pad = false;  // end-of-stream window shorter than 28: padded with the last id
     while (!st.lens.empty() && !emit) {

@@ -215,6 +215,44 @@ class SnacEngine:
         self._check(rc, "snacb_decode_windows_host")
         return h_pcm.numpy(), h_st.numpy()
 
+    def submit_windows(self, tokens, ntok: Optional[Sequence[int]] = None, noise: NoiseArg = "philox", seed: int = 0,
+                       keys: Optional[Sequence[int]] = None) -> int:
+        """Pipelined host tick: enqueue H2D + kernels + D2H and return a ticket at once.  ``wait_windows(ticket)``
+        returns that tick's (pcm, status); submit tick t+1 before waiting for tick t and the copy-back and host work
+        of t overlap the kernels of t+1 (two ticks in flight at most).  Noise "philox" or "off"."""
+        tok = np.ascontiguousarray(np.asarray(tokens, dtype=np.int32))
+        assert tok.ndim == 2
+        n, stride = tok.shape
+        mode = self._noise_mode(noise)
+        if mode == _lib.NOISE_TENSOR:
+            raise ValueError("submit_windows: injected noise is not supported (use decode_windows)")
+        slot = getattr(self, "_pipe_slot", 0)
+        h_pcm = self._pinned(f"pipe_pcm{slot}", (n, SLICE_SAMPLES), torch.int16)
+        h_st = self._pinned(f"pipe_status{slot}", (n,), torch.int32)
+        nt = np.ascontiguousarray(np.asarray(ntok, dtype=np.int32)) if ntok is not None else None
+        kp = np.ascontiguousarray(np.asarray(keys, dtype=np.uint64)) if keys is not None else None
+        ticket = C.c_int32(-1)
+        with torch.cuda.device(self.device):
+            rc = self._lib.snacb_decode_windows_host_submit(
+                self._h, tok.ctypes.data, stride, nt.ctypes.data if nt is not None else None, stride, n, mode,
+                int(seed) & (2**64 - 1), kp.ctypes.data if kp is not None else None, h_pcm.data_ptr(), h_st.data_ptr(),
+                self._stream(), C.byref(ticket))
+        self._check(rc, "snacb_decode_windows_host_submit")
+        if not hasattr(self, "_pipe_out"):
+            self._pipe_out = {}
+        self._pipe_out[int(ticket.value)] = (h_pcm, h_st)
+        self._pipe_slot = slot ^ 1
+        return int(ticket.value)
+
+    def wait_windows(self, ticket: int) -> Tuple[np.ndarray, np.ndarray]:
+        """Block until the tick submitted under ``ticket`` is on the host: (pcm int16 [n,2048], status int32 [n]) as
+        numpy views of pinned buffers (valid until the second next ``submit_windows``)."""
+        with torch.cuda.device(self.device):
+            rc = self._lib.snacb_decode_windows_host_wait(self._h, int(ticket))
+        self._check(rc, "snacb_decode_windows_host_wait")
+        h_pcm, h_st = self._pipe_out.pop(int(ticket))
+        return h_pcm.numpy(), h_st.numpy()
+
     # ------------------------------------------------------------------ one-shot path
     def decode_codes(self, codes: Sequence[torch.Tensor], noise: NoiseArg = "philox", seed: int = 0,
                      want_pcm: bool = False):

@@ -132,13 +132,22 @@ class NativeTickScheduler:
     """``TickScheduler`` with the token parsing and window planning of all streams in native code."""
 
     def __init__(self, decode_batch: Optional[DecodeBatch] = None, max_streams: int = 4096,
-                 max_windows_per_tick: int = 4096, decode_arrays: Optional[DecodeArrays] = None):
+                 max_windows_per_tick: int = 4096, decode_arrays: Optional[DecodeArrays] = None,
+                 engine=None, noise: str = "philox", seed: int = 0):
+        """``engine`` (a ``SnacEngine``) switches to pipelined ticks: ``tick()`` submits the windows that are ready now
+        (``submit_windows``) and returns the audio of the PREVIOUS tick (``wait_windows``), so token parsing, window
+        planning, PCM distribution and the device -> host copy of one tick run under the kernels of the next.  Per
+        stream the windows, their order and their bytes are unchanged; audio arrives one tick later."""
+        self._eng = engine
+        self._noise, self._seed, self._key0 = noise, int(seed), 0
+        self._inflight = None
         self._ing = NativeIngest(max_streams)
         self._decode: Optional[DecodeArrays] = decode_arrays or (_wrap_list_decode(decode_batch) if decode_batch else None)
         self.max_windows_per_tick = int(max_windows_per_tick)
         self._slot: Dict[Hashable, int] = {}
         self._free: List[int] = list(range(max_streams - 1, -1, -1))
         self._sid_of: List[Optional[Hashable]] = [None] * max_streams
+        self._gen: List[int] = [0] * max_streams  # bumped on reset / evict: in-flight windows of an old tenant are dropped
         self._out: Dict[Hashable, Deque[bytes]] = {}
         self._finished: Dict[Hashable, bool] = {}
         self._q_slots: List[int] = []
@@ -154,6 +163,7 @@ class NativeTickScheduler:
             raise RuntimeError("no free stream slot")
         slot = self._free.pop()
         self._ing.reset(slot)
+        self._gen[slot] += 1
         self._slot[sid] = slot
         self._sid_of[slot] = sid
         self._out[sid] = deque()
@@ -165,6 +175,7 @@ class NativeTickScheduler:
             return
         self._flush_queue()
         self._ing.reset(slot)
+        self._gen[slot] += 1
         self._sid_of[slot] = None
         self._free.append(slot)
         self._out.pop(sid, None)
@@ -173,6 +184,7 @@ class NativeTickScheduler:
     def reset_stream(self, sid: Hashable) -> None:
         self._flush_queue()
         self._ing.reset(self._slot[sid])
+        self._gen[self._slot[sid]] += 1
         self._out[sid] = deque()
         self._finished[sid] = False
 
@@ -209,7 +221,54 @@ class NativeTickScheduler:
         self._ing.finish(self._slot[sid])
 
     # ---------------------------------------------------------------- the tick
+    def _deliver(self, pcm: np.ndarray, status: np.ndarray, owner: np.ndarray) -> None:
+        sid_of, out = self._sid_of, self._out
+        for i in np.nonzero(status == _lib.WIN_OK)[0].tolist():
+            q = out.get(sid_of[owner[i]])
+            if q is not None:  # the stream may have been evicted while its window was in flight
+                q.append(pcm[i].tobytes())
+        for i in np.nonzero(status == _lib.WIN_EMPTY)[0].tolist():
+            q = out.get(sid_of[owner[i]])
+            if q is not None:
+                q.append(b"")
+
+    def _tick_pipelined(self) -> int:
+        self._flush_queue()
+        tok, ntok, owner = self._ing.tick(self.max_windows_per_tick)
+        n = len(ntok)
+        nxt = None
+        if n:
+            keys = np.arange(self._key0, self._key0 + n, dtype=np.uint64)
+            self._key0 += n
+            n0 = int(ntok[0])
+            if n0 >= 7 and bool((ntok == n0).all()):
+                ticket = self._eng.submit_windows(tok[:, :n0], noise=self._noise, seed=self._seed, keys=keys)
+            else:
+                ticket = self._eng.submit_windows(tok, ntok=ntok, noise=self._noise, seed=self._seed, keys=keys)
+            gen = [self._gen[s] for s in owner.tolist()]
+            nxt = (ticket, owner.copy(), gen)
+        done = 0
+        if self._inflight is not None:
+            ticket, own, gen = self._inflight
+            pcm, status = self._eng.wait_windows(ticket)
+            status = np.asarray(status)
+            live = np.fromiter((self._gen[s] == g for s, g in zip(own.tolist(), gen)), dtype=bool, count=len(gen))
+            if live.all():
+                self._ing.result(own, status)
+                self._deliver(pcm, status, own)
+            elif live.any():  # windows of slots that were reset / re-used meanwhile are dropped
+                self._ing.result(own[live], status[live])
+                self._deliver(pcm[live], status[live], own[live])
+            done = len(own)
+            self.ticks += 1
+            self.windows_decoded += done
+        self._inflight = nxt
+        return done if done else (-1 if nxt is not None else 0)  # -1: nothing delivered yet, but a tick is in flight
+
     def tick(self) -> int:
+        if self._eng is not None:
+            r = self._tick_pipelined()
+            return 0 if r < 0 else r
         if self._decode is None:
             self._decode = _default_decode_arrays()
         self._flush_queue()
@@ -235,6 +294,12 @@ class NativeTickScheduler:
     def drain(self) -> int:
         total = 0
         while True:
+            if self._eng is not None:
+                r = self._tick_pipelined()
+                if r == 0:
+                    return total
+                total += max(r, 0)
+                continue
             n = self.tick()
             if n == 0:
                 return total

@@ -9,7 +9,7 @@ import json
 try:
     d=json.loads(open("$OUT/bench_$v.json").read().strip().splitlines()[-1])
     r=d["roofline"]
-    print("$VAR=$v value %.0f ms/step %.3f e2e %.0f"%(d["value"],d["ms_per_step"],d["e2e"]["value"]), {k:round(x["ms_per_step"],2) for k,x in r["classes"].items()})
+    print("$VAR=$v value %.0f ms/step %.3f e2e %.0f sync %.0f"%(d["value"],d["ms_per_step"],d["e2e"]["value"],d["e2e"].get("sync_value",0)), {k:round(x["ms_per_step"],2) for k,x in r["classes"].items()})
 except Exception as e: print("$VAR=$v failed", e)
 PY
 done

@@ -493,7 +493,11 @@ def test_native_ingest_scheduler_on_gpu_matches_per_stream_decoder(monkeypatch):
         return [c async for c in speechpipe.tokens_decoder(gen())]
 
     want = {i: asyncio.run(per_stream(s)) for i, s in streams.items()}
-    sched = NativeTickScheduler(max_streams=16)
+    _run_native_scheduler(NativeTickScheduler(max_streams=16), streams, want)
+    _run_native_scheduler(NativeTickScheduler(max_streams=16, engine=speechpipe.model.engine, noise="off"), streams, want)
+
+
+def _run_native_scheduler(sched, streams, want):
     got = {i: [] for i in streams}
     for i in streams:
         sched.add_stream(i)
@@ -598,6 +602,47 @@ def test_kernel_variants_match_oracle(engines, oracle_w1, variant):
     assert (st == _lib.WIN_OK).all()
     want = pcm_trunc(ref).astype(np.float32) / 32767.0
     _check_wave(want, pcm.astype(np.float32) / 32767.0, TOL_MAX_ABS, TOL_SNR_DB - 0.5)
+
+
+def test_pipelined_host_ticks_equal_synchronous_ticks(engines):
+    """snacb_decode_windows_host_submit / _wait with two ticks in flight: every tick's PCM and statuses equal the
+    synchronous host call; a third submit without a wait is refused; ragged ticks work."""
+    eng = engines("fp16")
+    ticks = []
+    for t in range(5):
+        n = [300, 300, 17, 300, 64][t]
+        tok = windows_tokens(n, 4, base_stream=6000 + 100 * t)
+        ticks.append((tok, list(range(1000 * t, 1000 * t + n)), 40 + t))
+    want = []
+    for tok, keys, seed in ticks:
+        pcm, st = eng.decode_windows(tok, noise="philox", seed=seed, keys=keys)
+        want.append((pcm.copy(), st.copy()))
+    got, inflight = [], []
+    for tok, keys, seed in ticks:
+        inflight.append(eng.submit_windows(tok, noise="philox", seed=seed, keys=keys))
+        if len(inflight) == 2:
+            pcm, st = eng.wait_windows(inflight.pop(0))
+            got.append((pcm.copy(), st.copy()))
+    t3 = eng.submit_windows(ticks[0][0], noise="philox", seed=ticks[0][2], keys=ticks[0][1])
+    with pytest.raises(_lib.SnacbError):
+        eng.submit_windows(ticks[0][0], noise="philox", seed=1, keys=ticks[0][1])
+    for tk in inflight + [t3]:
+        pcm, st = eng.wait_windows(tk)
+        got.append((pcm.copy(), st.copy()))
+    with pytest.raises(_lib.SnacbError):
+        eng.wait_windows(0)
+    for (gp, gs), (wp, ws) in zip(got, want + [want[0]]):
+        assert np.array_equal(gs, ws) and np.array_equal(gp, wp)
+    # ragged tick through the pipelined call
+    wins = [windows_tokens(1, 4, 7000)[0].tolist(), [5] * 6, windows_tokens(1, 7, 7001)[0].tolist(), list(range(1, 8))]
+    tok = np.zeros((len(wins), 49), dtype=np.int32)
+    for i, w in enumerate(wins):
+        tok[i, : len(w)] = w
+    lens = [len(w) for w in wins]
+    wp, ws = eng.decode_windows(tok, ntok=lens, noise="off")
+    wp, ws = wp.copy(), ws.copy()
+    gp, gs = eng.wait_windows(eng.submit_windows(tok, ntok=lens, noise="off"))
+    assert np.array_equal(gs, ws) and np.array_equal(gp, wp)
 
 
 def test_c_abi_error_paths(engines):

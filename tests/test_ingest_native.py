@@ -163,3 +163,61 @@ def test_ingest_argument_checks(ensure_lib):
     assert len(ntok) == 0 and ing.done(1) and not ing.done(0)
     assert ing.stats() == {"accepted": 0, "rejected": 0, "windows": 0}
     ing.close()
+
+
+class FakeEngine:
+    """submit_windows / wait_windows with the deterministic stand-in decode (two tickets, like the C ABI)."""
+
+    def __init__(self):
+        self.slots, self.next = {}, 0
+        self.max_inflight = 0
+
+    def submit_windows(self, tokens, ntok=None, noise="philox", seed=0, keys=None):
+        tok = np.array(tokens, dtype=np.int32, copy=True)
+        lens = [tok.shape[1]] * tok.shape[0] if ntok is None else [int(x) for x in ntok]
+        t = self.next
+        assert t not in self.slots, "two ticks already in flight"
+        self.slots[t] = (tok, lens)
+        self.next ^= 1
+        self.max_inflight = max(self.max_inflight, len(self.slots))
+        return t
+
+    def wait_windows(self, ticket):
+        tok, lens = self.slots.pop(ticket)
+        pcm = np.zeros((len(lens), 2048), dtype=np.int16)
+        st_ = np.zeros((len(lens),), dtype=np.int32)
+        for i, n in enumerate(lens):
+            r = fake_convert(tok[i, :n].tolist())
+            if r is None:
+                st_[i] = _lib.WIN_REJECTED
+            elif len(r) == 0:
+                st_[i] = _lib.WIN_EMPTY
+            else:
+                pcm[i] = np.frombuffer(r, dtype="<i2")
+        return pcm, st_
+
+
+def test_pipelined_native_scheduler_keeps_per_stream_results(ensure_lib):
+    """Pipelined ticks (submit now, deliver the previous tick): same chunks per stream as the oracle's per-stream
+    semantics, incl. dirty streams, a rejected first chunk, an evicted stream and slot reuse."""
+    streams = {i: (dirty_stream(i, f) if i % 2 else sp.synth_token_strings(i, f))
+               for i, f in enumerate([1, 2, 3, 4, 5, 8, 10, 13, 7, 9, 0, 21])}
+    streams[12] = ["<custom_token_9000>"] * 3 + sp.synth_token_strings(77, 6)  # out-of-range ids: first chunks are rejected
+    want = {i: list(sp.decode_stream(s, fake_convert)) for i, s in streams.items()}
+    eng = FakeEngine()
+    sched = NativeTickScheduler(max_streams=16, engine=eng)
+    got = run_scheduler(sched, streams, 0)
+    assert eng.max_inflight >= 1
+    for i in streams:
+        assert got[i] == want[i], i
+    # evict with a window in flight: nothing of the evicted stream is delivered afterwards, its slot starts clean
+    sched2 = NativeTickScheduler(max_streams=2, engine=FakeEngine())
+    sched2.add_stream("a")
+    sched2.push_many("a", streams[5])
+    sched2.tick()
+    sched2.evict("a")
+    sched2.add_stream("b")
+    sched2.push_many("b", streams[3])
+    sched2.finish("b")
+    sched2.drain()
+    assert sched2.pop_audio("b") == want[3]
