@@ -317,37 +317,57 @@ __global__ void __launch_bounds__(256) k_tail(const Item* items, int base, int o
   const int t0 = a.out_r.lo + blockIdx.x * 64;  // first output sample (relative) of this CTA
   const int x_rows = a.x_r.n();
   const float* x = a.x + (size_t)i * x_rows * 64;
-  for (int e = tid; e < 70 * 16; e += 256) {  // 16 float4 per row
-    const int r = e >> 4, c = (e & 15) * 4;
-    const int row = t0 - 3 + r - a.x_r.lo;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row >= 0 && row < x_rows) v = *reinterpret_cast<const float4*>(x + (size_t)row * 64 + c);
+  {
+    const int c = (tid & 15) * 4;  // 16 float4 per row: a thread keeps its four channels for every row it stages
     const float4 al = *reinterpret_cast<const float4*>(a.alpha + c), iv = *reinterpret_cast<const float4*>(a.inv + c);
-    float4 o;
-    if (FAST) {
-      float sn;
-      sn = __sinf(al.x * v.x); o.x = fmaf(iv.x, sn * sn, v.x);
-      sn = __sinf(al.y * v.y); o.y = fmaf(iv.y, sn * sn, v.y);
-      sn = __sinf(al.z * v.z); o.z = fmaf(iv.z, sn * sn, v.z);
-      sn = __sinf(al.w * v.w); o.w = fmaf(iv.w, sn * sn, v.w);
-    } else {
-      o.x = snake_exact(v.x, al.x, iv.x); o.y = snake_exact(v.y, al.y, iv.y);
-      o.z = snake_exact(v.z, al.z, iv.z); o.w = snake_exact(v.w, al.w, iv.w);
+    const int row_b = t0 - 3 - a.x_r.lo;
+#pragma unroll
+    for (int r = tid >> 4; r < 70; r += 16) {
+      const int row = row_b + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row >= 0 && row < x_rows) v = *reinterpret_cast<const float4*>(x + (size_t)row * 64 + c);
+      float4 o;
+      if (FAST) {  // packed fp32x2 Snake (MUFU sin), same arithmetic as the tensor-core recipe's other Snakes
+        float2 t = __fmul2_rn(make_float2(al.x, al.y), make_float2(v.x, v.y));
+        float2 sn = make_float2(__sinf(t.x), __sinf(t.y));
+        const float2 lo = __ffma2_rn(make_float2(iv.x, iv.y), __fmul2_rn(sn, sn), make_float2(v.x, v.y));
+        t = __fmul2_rn(make_float2(al.z, al.w), make_float2(v.z, v.w));
+        sn = make_float2(__sinf(t.x), __sinf(t.y));
+        const float2 hi = __ffma2_rn(make_float2(iv.z, iv.w), __fmul2_rn(sn, sn), make_float2(v.z, v.w));
+        o = make_float4(lo.x, lo.y, hi.x, hi.y);
+      } else {
+        o.x = snake_exact(v.x, al.x, iv.x); o.y = snake_exact(v.y, al.y, iv.y);
+        o.z = snake_exact(v.z, al.z, iv.z); o.w = snake_exact(v.w, al.w, iv.w);
+      }
+      *reinterpret_cast<float4*>(&xs[r][c]) = o;
     }
-    *reinterpret_cast<float4*>(&xs[r][c]) = o;
   }
   for (int e = tid; e < 7 * 64; e += 256) ws[e >> 6][e & 63] = a.w7[e];
   __syncthreads();
   const int sx = tid & 63, qc = tid >> 6;  // output sample, channel quarter
   float acc = 0.0f;
+  if (FAST) {
+    float2 a2 = make_float2(0.f, 0.f), b2 = a2;  // two independent packed chains
 #pragma unroll
-  for (int k = 0; k < 7; ++k)
+    for (int k = 0; k < 7; ++k)
 #pragma unroll
-    for (int c = 0; c < 16; c += 4) {
-      const float4 w4 = *reinterpret_cast<const float4*>(&ws[k][qc * 16 + c]);   // warp-uniform: broadcast
-      const float4 x4 = *reinterpret_cast<const float4*>(&xs[sx + k][qc * 16 + c]);
-      acc = fmaf(w4.x, x4.x, acc); acc = fmaf(w4.y, x4.y, acc); acc = fmaf(w4.z, x4.z, acc); acc = fmaf(w4.w, x4.w, acc);
-    }
+      for (int c = 0; c < 16; c += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&ws[k][qc * 16 + c]);   // warp-uniform: broadcast
+        const float4 x4 = *reinterpret_cast<const float4*>(&xs[sx + k][qc * 16 + c]);
+        a2 = __ffma2_rn(make_float2(w4.x, w4.y), make_float2(x4.x, x4.y), a2);
+        b2 = __ffma2_rn(make_float2(w4.z, w4.w), make_float2(x4.z, x4.w), b2);
+      }
+    acc = (a2.x + a2.y) + (b2.x + b2.y);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+#pragma unroll
+      for (int c = 0; c < 16; c += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&ws[k][qc * 16 + c]);   // warp-uniform: broadcast
+        const float4 x4 = *reinterpret_cast<const float4*>(&xs[sx + k][qc * 16 + c]);
+        acc = fmaf(w4.x, x4.x, acc); acc = fmaf(w4.y, x4.y, acc); acc = fmaf(w4.z, x4.z, acc); acc = fmaf(w4.w, x4.w, acc);
+      }
+  }
   part[qc][sx] = acc;
   __syncthreads();
   if (qc != 0) return;
