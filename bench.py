@@ -431,6 +431,41 @@ def run_ours(args) -> None:
                            "*_host_only replaces the decode by a no-op to isolate parsing + window planning + egress")
             extra["n2_token_ingress"] = res
 
+        # Next row N3: PCM egress - the reference's overlap-add stitcher (numpy, one call per chunk) against the native one,
+        # one 4096-byte chunk per stream per tick, 10 ms crossfade (the server's default overlap of 0 is a pass-through).
+        if args.ingest_streams > 0:
+            from oracle import egress_ref
+            ns_e, ticks_e = args.ingest_streams, 8
+            rng_e = np.random.default_rng(7)
+            chunks_e = [rng_e.integers(-20000, 20000, size=2048).astype("<i2").tobytes() for _ in range(16)]
+            from project_morpheus_b200.egress import StitcherBank
+            bank_e = StitcherBank(ns_e, 24000, 10.0)
+            mats = [np.stack([np.frombuffer(chunks_e[(i + t) % 16], dtype="<i2") for i in range(ns_e)]) for t in range(ticks_e)]
+            slots_e = np.arange(ns_e, dtype=np.int32)
+            t0 = time.perf_counter()
+            nbytes = 0
+            for t in range(ticks_e):
+                _, ol, _ = bank_e.push_tick(slots_e, mats[t])
+                nbytes += 2 * int(ol[ol > 0].sum())
+            dt_nat = (time.perf_counter() - t0) / ticks_e
+            bank_e.close()
+            sts = []
+
+            def one_stream(i):
+                return sum(len(p_) for p_, _ in egress_ref.stitch(((chunks_e[(i + t) % 16], False) for t in range(ticks_e)), 24000, 10.0))
+
+            sample = max(1, ns_e // 8)
+            t0 = time.perf_counter()
+            for i in range(sample):
+                one_stream(i)
+            dt_np = (time.perf_counter() - t0) / ticks_e * (ns_e / sample)
+            for s_ in sts:
+                s_.close()
+            extra["n3_pcm_egress"] = {"streams": ns_e, "overlap_ms": 10.0, "native_ms_per_tick": 1e3 * dt_nat,
+                                      "numpy_reference_ms_per_tick": 1e3 * dt_np, "bytes_per_tick": nbytes // ticks_e,
+                                      "note": "overlap-add stitcher, one 2048-sample chunk per stream per tick, native = one StitcherBank.push_tick call per tick; numpy = the "
+                                              "reference's algorithm (oracle restatement), scaled from a 1/8 sample of the streams"}
+
         # BASELINE config 3 (long_read): one-shot decode of 720-frame utterances, time-tiled; reduced batch by default
         if args.long_read_batch > 0:
             Fl, Bl = 720, args.long_read_batch

@@ -271,6 +271,33 @@ int snacb_ingest_done(const snacb_ingest* g, int32_t stream);
 /* which: 0 accepted tokens, 1 rejected token strings, 2 windows emitted. */
 int64_t snacb_ingest_stat(const snacb_ingest* g, int32_t which);
 
+/* ---- N3: PCM egress (host only, no GPU) ----------------------------------------------------- */
+
+/* server.py:50-70 riff_header(): the 44-byte RIFF/WAVE header with unknown (0xFFFFFFFF) lengths, mono PCM16. Returns 44. */
+int snacb_riff_header(int32_t sample_rate, uint8_t* out44);
+/* orchestrator/stitcher.py:10-79 stitch_chunks(): overlap-add crossfade of consecutive int16 chunks, byte-identical to
+ * the numpy code (float64 tail carried between chunks, linspace fades, truncation on emission). */
+typedef struct snacb_stitcher snacb_stitcher;
+int snacb_stitch_create(snacb_stitcher** out, int32_t sample_rate, double overlap_ms);
+void snacb_stitch_destroy(snacb_stitcher* s);
+/* Feed one chunk; writes what the reference yields for it.  Returns samples written, or -(needed) if cap is too small
+ * (nothing consumed).  *emitted = 1 when a chunk is yielded (an eos chunk is yielded even if empty), *out_eos its flag. */
+int64_t snacb_stitch_push(snacb_stitcher* s, const int16_t* pcm, int64_t n, int32_t eos, int16_t* out, int64_t cap,
+                          int32_t* emitted, int32_t* out_eos);
+/* The chunk source ended without an eos chunk: the kept tail (yielded with eos = True when non-empty). */
+int64_t snacb_stitch_flush(snacb_stitcher* s, int16_t* out, int64_t cap);
+int64_t snacb_stitch_overlap_samples(const snacb_stitcher* s);
+/* One stitcher per stream slot, one call per decode tick: chunk i = pcm[i * pcm_stride .. + len) (a row of the PCM matrix
+ * the decode returned) for stream slots[i]; row i of out[n][out_stride >= len + overlap] gets out_len[i] samples
+ * (-1 = the reference yields nothing for this chunk), out_eos[i] its eos flag.  eos_in may be NULL (no chunk ends). */
+typedef struct snacb_stitch_bank snacb_stitch_bank;
+int snacb_stitch_bank_create(snacb_stitch_bank** out, int32_t n_streams, int32_t sample_rate, double overlap_ms);
+void snacb_stitch_bank_destroy(snacb_stitch_bank* b);
+int snacb_stitch_bank_reset(snacb_stitch_bank* b, int32_t stream);
+int snacb_stitch_bank_push(snacb_stitch_bank* b, int32_t n, const int32_t* slots, const int16_t* pcm, int64_t pcm_stride,
+                           int64_t len, const int32_t* eos_in, int16_t* out, int64_t out_stride, int64_t* out_len,
+                           int32_t* out_eos);
+
 #ifdef __cplusplus
 }
 #endif

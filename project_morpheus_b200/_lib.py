@@ -102,6 +102,17 @@ SIGNATURES = {
     "snacb_ingest_result": (_i32, [_vp, _i32, _vp, _vp]),
     "snacb_ingest_done": (_i32, [_vp, _i32]),
     "snacb_ingest_stat": (_i64, [_vp, _i32]),
+    # N3: PCM egress (host only)
+    "snacb_riff_header": (_i32, [_i32, _vp]),
+    "snacb_stitch_create": (_i32, [C.POINTER(_vp), _i32, C.c_double]),
+    "snacb_stitch_destroy": (None, [_vp]),
+    "snacb_stitch_push": (_i64, [_vp, _vp, _i64, _i32, _vp, _i64, C.POINTER(_i32), C.POINTER(_i32)]),
+    "snacb_stitch_flush": (_i64, [_vp, _vp, _i64]),
+    "snacb_stitch_overlap_samples": (_i64, [_vp]),
+    "snacb_stitch_bank_create": (_i32, [C.POINTER(_vp), _i32, _i32, C.c_double]),
+    "snacb_stitch_bank_destroy": (None, [_vp]),
+    "snacb_stitch_bank_reset": (_i32, [_vp, _i32]),
+    "snacb_stitch_bank_push": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp]),
 }
 
 _lib = None
