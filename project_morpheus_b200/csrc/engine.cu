@@ -456,6 +456,27 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
         gemm(a);
       }
       tap(e, sid + 2, X, B.ct, B.Cout, n, first, st);
+      // block 3: the three ResidualUnits + decoder tail + PCM pack as ONE kernel (residual stream in tensor memory)
+      if (b == 3 && blk_tc_supported(B.Cout, true) && !(e->cfg.flags & (SNACB_FLAG_NO_BLOCK_FUSION | SNACB_FLAG_NO_RU_FUSION |
+                                                                      SNACB_FLAG_PERSISTENT_RU | SNACB_FLAG_TAIL_FUSION)) &&
+          !(e->tap_stage > sid + 2 && e->tap_stage <= sid + 8) && ce == cudaSuccess) {
+        BlkTcArgs u{};
+        u.x = X; u.in_r = B.ct; u.C = B.Cout; u.up = B.up_out;
+        double el = 0.0;
+        for (int r = 0; r < 3; ++r) {
+          const RuDev& R = Wb.ru[r];
+          u.ru[r] = BlkTcArgs::Ru{R.dw_w, R.dw_b, R.a1, R.i1, R.a2, R.i2, R.pw_b, R.pw_w, R.pw16};
+          el += (double)n * B.r[r].n() * B.Cout;
+        }
+        u.sn_alpha = W.tail_alpha; u.sn_inv = W.tail_inv; u.tail_w7 = W.tail_w; u.tail_b = W.tail_b; u.tail_out = tail_out;
+        u.status = d_status; u.wav = wav; u.pcm = pcm;
+        const double smp = (double)n * tail_out.n();
+        ProfScope ps(e, KC_RU, 2.0 * el * B.Cout + el * 24.0 + smp * (2.0 * 448 + 4.0 * 64),
+                     (double)n * B.ct.n() * B.Cout * 4.0 + smp * 2.0, st);
+        ce = launch_blk_tc(g, u);
+        tail_done = true;
+        continue;
+      }
       // X holds the residual stream; Ain (dead after the transposed conv) becomes the dw output operand
       __half* D16 = Ain;
       __half* Anext = Aother;

@@ -105,6 +105,16 @@ struct RuTcArgs {
 };
 bool ru_tc_supported(int C, bool persistent);
 cudaError_t launch_ru_tc(const GroupCtx& g, const RuTcArgs& a);
+// Whole DecoderBlock ResidualUnit chain (+ decoder tail and PCM pack) in one persistent kernel (kernels_blk.cu): the
+// residual stream stays in tensor memory, Snake'd activations in shared memory.  x = ConvTranspose1d + NoiseBlock output.
+struct BlkTcArgs {
+  const float* x; Rng in_r; int C, up;
+  struct Ru { const float *w7, *dw_b, *a1, *i1, *a2, *i2, *pw_b, *pw_w; const __half* pw16; } ru[3];
+  const float* sn_alpha; const float* sn_inv;  // Snake after the block (decoder tail)
+  const float* tail_w7; const float* tail_b; Rng tail_out; const int32_t* status; float* wav; int16_t* pcm;
+};
+bool blk_tc_supported(int C, bool tail);
+cudaError_t launch_blk_tc(const GroupCtx& g, const BlkTcArgs& a);
 // from_codes + decoder.model.0 (depthwise k7) -> fp16 operand of the 768->1024 GEMM, z never leaves the SM
 bool codes_head_supported(Rng z);
 void launch_codes_head(const GroupCtx& g, const QuantW& q, const int32_t* c0, const int32_t* c1, const int32_t* c2, int pitch0,

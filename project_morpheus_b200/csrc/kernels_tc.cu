@@ -24,14 +24,12 @@
 
 #include "kernels.h"
 #include "snacb.h"
+#include "tc_ptx.cuh"
 
 namespace snacb {
 namespace {
 
-constexpr int BM = 128;  // rows per tile = TMEM lanes
-constexpr int BK = 64;   // fp16 per k-block = one 128-byte swizzle span
 constexpr int kTcThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr uint32_t kLiveFlag = 0x40000000u;
 const bool g_no_ws = [] { const char* v = getenv("SNACB_NO_WS"); return v && v[0] == '1'; }();
 const bool g_cn_p = [] { const char* v = getenv("SNACB_CN_PERSISTENT"); return !(v && v[0] == '0'); }();
 const bool g_convt_p = [] { const char* v = getenv("SNACB_CONVT_PERSISTENT"); return !(v && v[0] == '0'); }();
@@ -39,182 +37,6 @@ const bool g_convt_p = [] { const char* v = getenv("SNACB_CONVT_PERSISTENT"); re
 // fp32 residual stream, not on the L2 -> SM operand traffic)
 const bool g_ws_cluster = [] { const char* v = getenv("SNACB_WS_CLUSTER"); return v && v[0] == '1'; }();
 
-// ------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Non-blocking probe (try_wait may suspend the thread for a while before it reports failure).
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug becomes a trap (CUDA error) instead of a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) {
-      printf("snacb: mbarrier timeout, block (%d,%d) thread %d\n", (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-// Multicast variants (thread-block clusters): the tile lands at the same shared-memory offset of every CTA in
-// `mask` and completes the transaction on each destination CTA's own mbarrier at that offset.
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
-               : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// mbarrier arrives once every previously issued tcgen05.mma of this thread has completed.
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// Epilogue transpose: a warp holds a 32-row x 16-column fp32 block one row per lane (tcgen05.ld
-// 32x32b.x16); after the trip through its private 2 KB of swizzled shared memory lane l holds, for
-// i = 0..3, the float4 of row (l/4 + 8i), columns 4*(l%4)..+3 - so global accesses are 64-byte row
-// segments.  16-byte chunk index is XORed with (row/2)%4: conflict-free on both sides.
-__device__ __forceinline__ void epi_transpose16(float* stg, int lane, const uint32_t (&r)[16], float4 (&v)[4]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    *reinterpret_cast<float4*>(stg + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) =
-        make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                    __uint_as_float(r[4 * j + 3]));
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int row = (lane >> 2) + 8 * i;
-    v[i] = *reinterpret_cast<const float4*>(stg + row * 16 + (((lane & 3) ^ ((row >> 1) & 3)) << 2));
-  }
-  __syncwarp();
-}
-__device__ __forceinline__ void store_half4(__half* p, float4 v) {
-  const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-  uint2 pk;
-  pk.x = *reinterpret_cast<const uint32_t*>(&h0);
-  pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-  *reinterpret_cast<uint2*>(p) = pk;
-}
-__device__ __forceinline__ float4 add4(float4 a, float4 b) {
-  const float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
-  const float2 hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
-  return make_float4(lo.x, lo.y, hi.x, hi.y);
-}
-// 1024-byte aligned view of the dynamic shared memory that keeps the shared address space (no generic ld/st)
-__device__ __forceinline__ uint8_t* smem_align1024(uint8_t* raw) { return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u); }
-
-// Shared-memory matrix descriptor of a K-major operand tile written by TMA with SWIZZLE_128B:
-// rows of 128 bytes (64 fp16 of K), 8-row groups of 1024 bytes (SBO), tile base 1024-byte aligned.
-__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, bits [0,14)
-  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major), bits [16,30)
-  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset = 8 rows * 128 B, bits [32,46)
-  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell), bits [46,48)
-  d |= (uint64_t)2 << 61;                    // layout type SWIZZLE_128B, bits [61,64)
-  return d;
-}
-// kind::f16 instruction descriptor: fp16 A/B (K-major), fp32 D, M = 128, N = BN.
-__host__ __device__ constexpr uint32_t umma_idesc_f16(int n) {
-  return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
-
-// Packed fp32x2 arithmetic (sm_100 FFMA2/FMUL2/FADD2): the depthwise + Snake work is issue-bound, and
-// every value here comes as a channel pair.
-__device__ __forceinline__ float2 snake2(float2 x, float2 al, float2 iv) {
-  const float2 t = __fmul2_rn(al, x);
-  float2 s = make_float2(__sinf(t.x), __sinf(t.y));
-  s = __fmul2_rn(s, s);
-  return __ffma2_rn(iv, s, x);
-}
 
 // One depthwise unit: L outputs at rows first, first+DIL, ... of one channel pair from L+6 inputs at
 // p0 + m*DIL*C (m = 0..L+5; bit m of `mask` says the row exists, absent rows are the conv's zero pad).
@@ -271,7 +93,6 @@ __device__ __forceinline__ void dw_unit_smem(const float* p0, const DwPairW& W, 
 // DIL 1 -> rows 16u..16u+15; DIL 3 -> residue u%3 of the 48-row segment u/3; DIL 9 -> residue u): the number of
 // outputs that fall inside the tile is a compile-time constant per group, so no unit computes (or loads inputs for)
 // rows beyond row 127 and the per-output bound check disappears.
-template <int N> struct IntC { static constexpr int value = N; };
 template <int DIL, typename F>
 __device__ __forceinline__ void unit_len_dispatch(int u, F&& f) {
   if (DIL == 1) f(IntC<16>{});
@@ -942,6 +763,7 @@ struct MapHash {
 };
 
 // [rows][cols] fp16 row-major, box = 64 columns x box_rows rows, 128-byte swizzle, zero fill out of bounds.
+}  // namespace
 bool get_tmap(const void* ptr, long long rows, int cols, int box_rows, CUtensorMap* out) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapHash> cache;
@@ -966,6 +788,7 @@ bool get_tmap(const void* ptr, long long rows, int cols, int box_rows, CUtensorM
   return true;
 }
 
+namespace {
 // fp32 activation tensor [items][rows][C] (channels-last), box = [1][box_rows][C], no swizzle: rows outside
 // [0, rows) of the addressed item arrive as zeros - exactly the conv's zero padding.
 bool get_tmap_x3(const float* ptr, int C, int rows, int n_items, int box_rows, CUtensorMap* out, int box_c = 0) {
@@ -995,7 +818,8 @@ bool get_tmap_x3(const float* ptr, int C, int rows, int n_items, int box_rows, C
 
 template <int BN, int EPI>
 cudaError_t launch_tc_t(const CUtensorMap& ma, const CUtensorMap& mw, const TcDev& d, dim3 grid, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDev] = {};
+  bool& attr_set = attr_set_dev[cur_dev()];  // kernel attributes are per device
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_gemm_tc<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          TcSmem<BN>::bytes(TcSmem<BN>::kMaxStages));
@@ -1440,19 +1264,24 @@ __global__ void __launch_bounds__(kCnpThreads, 1) k_convt_noise_p(const __grid_c
   }
 }
 
-int sm_count() {
-  static int n = [] {
+}  // namespace
+int sm_count() {  // of the current device (an engine may live on any ordinal)
+  static int n_dev[kMaxDev] = {};
+  int& n = n_dev[cur_dev()];
+  if (!n) {
     int dev = 0, v = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v;
-  }();
+    n = v;
+  }
   return n;
 }
+namespace {
 
 template <int EPI, int CL>
 cudaError_t launch_ws_t(const CUtensorMap& ma, const CUtensorMap& mw, const TcDev& d, int n_slices, cudaStream_t st) {
-  static int max_p = 0;  // co-resident clusters (CL > 1) / CTAs per slice (CL == 1)
+  static int max_p_dev[kMaxDev] = {};  // co-resident clusters (CL > 1) / CTAs per slice (CL == 1), per device
+  int& max_p = max_p_dev[cur_dev()];
   if (!max_p) {
     cudaError_t e = cudaFuncSetAttribute(k_gemm_ws<EPI, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, WsSmem::bytes(512));
     if (e != cudaSuccess) return e;
@@ -1494,7 +1323,8 @@ cudaError_t launch_ws_e(const CUtensorMap& ma, const CUtensorMap& mw, const TcDe
 template <int BN>
 cudaError_t launch_cnp_t(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mn, const TcDev& d, int total,
                          cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDev] = {};
+  bool& attr_set = attr_set_dev[cur_dev()];  // kernel attributes are per device
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_convt_noise_p<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, CnpSmem<BN>::kBytes);
     if (e != cudaSuccess) return e;
@@ -1507,7 +1337,8 @@ cudaError_t launch_cnp_t(const CUtensorMap& ma, const CUtensorMap& mw, const CUt
 template <int BN>
 cudaError_t launch_cn_t(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mn, const TcDev& d, dim3 grid,
                         cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDev] = {};
+  bool& attr_set = attr_set_dev[cur_dev()];  // kernel attributes are per device
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_convt_noise_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          TcSmem<BN>::bytes(TcSmem<BN>::kMaxStages));
@@ -1585,7 +1416,8 @@ cudaError_t launch_gemm_tc(const GroupCtx& g, const TcGemmArgs& a) {
     const long long total = (long long)n_tiles * m_tiles;
     CUtensorMap mw256;
     if (total >= 2LL * sm_count() && get_tmap(a.W, a.N, nseg * a.K, 256, &mw256)) {
-      static bool attr_set = false;
+      static bool attr_set_dev[kMaxDev] = {};
+  bool& attr_set = attr_set_dev[cur_dev()];  // kernel attributes are per device
       if (!attr_set) {
         cudaError_t e0 = cudaFuncSetAttribute(k_convt_p<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, CtpSmem<256>::kBytes);
         if (e0 != cudaSuccess) return e0;
@@ -2394,7 +2226,8 @@ __global__ void __launch_bounds__(RupCfg<C>::kThreads, 1) k_ru_p(const __grid_co
 
 template <int C, int DIL>
 cudaError_t launch_rup_t(const CUtensorMap& mw, const RuDev& d, int tiles_per_item, int total_tiles, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDev] = {};
+  bool& attr_set = attr_set_dev[cur_dev()];  // kernel attributes are per device
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_ru_p<C, DIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, RupSmem<C>::kBytes);
     if (e != cudaSuccess) return e;
@@ -2413,7 +2246,8 @@ cudaError_t launch_rup_c(int dil, const CUtensorMap& mw, const RuDev& d, int tpi
 
 template <int C, int DIL>
 cudaError_t launch_ru_t(const CUtensorMap& mw, const RuDev& d, dim3 grid, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDev] = {};
+  bool& attr_set = attr_set_dev[cur_dev()];  // kernel attributes are per device
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_ru_tc<C, DIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, RuSmem<C>::kBytes);
     if (e != cudaSuccess) return e;
@@ -2424,7 +2258,8 @@ cudaError_t launch_ru_t(const CUtensorMap& mw, const RuDev& d, dim3 grid, cudaSt
 }
 cudaError_t launch_ru_tail(const CUtensorMap& mw, const RuDev& d, dim3 grid, cudaStream_t st) {
   constexpr int bytes = RuSmem<64>::kBytes + RuSmem<64>::kTailBytes;
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDev] = {};
+  bool& attr_set = attr_set_dev[cur_dev()];  // kernel attributes are per device
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_ru_tc<64, 9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
@@ -2438,7 +2273,8 @@ template <int DIL>
 cudaError_t launch_ru_x(const CUtensorMap& mw, const RuDev& d, dim3 grid, cudaStream_t st) {
   CUtensorMap mx;
   if (!get_tmap_x3(d.x, 64, d.in_rows, (int)grid.y, RuxSmem<DIL>::kBoxRows, &mx)) return cudaErrorNotSupported;
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDev] = {};
+  bool& attr_set = attr_set_dev[cur_dev()];  // kernel attributes are per device
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_ru_x<DIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, RuxSmem<DIL>::kBytes);
     if (e != cudaSuccess) return e;
@@ -2466,7 +2302,8 @@ const bool g_dw_tma = [] { const char* v = getenv("SNACB_DW_TMA"); return v && v
 template <int DIL>
 bool launch_dw_x_t(const GroupCtx& g, const DwTcArgs& a, const CUtensorMap& mx) {
   constexpr int bytes = RuxSmem<DIL>::kXBytes + 16 + 128;
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDev] = {};
+  bool& attr_set = attr_set_dev[cur_dev()];  // kernel attributes are per device
   if (!attr_set) {
     if (cudaFuncSetAttribute(k_dw_x<DIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) { cudaGetLastError(); return false; }
     attr_set = true;
@@ -2602,7 +2439,9 @@ bool codes_head_supported(Rng z) { return (size_t)z.n() * (kLatent + 24) * sizeo
 void launch_codes_head(const GroupCtx& g, const QuantW& q, const int32_t* c0, const int32_t* c1, const int32_t* c2, int pitch0,
                        Rng z, Rng h, const float* w7, const float* dw_b, __half* out) {
   const size_t smem = (size_t)z.n() * (kLatent + 24) * sizeof(float);
-  static size_t max_set = 48 * 1024;
+  static size_t max_set_dev[kMaxDev] = {};
+  size_t& max_set = max_set_dev[cur_dev()];
+  if (max_set < 48 * 1024) max_set = 48 * 1024;
   if (smem > max_set) {
     cudaFuncSetAttribute(k_codes_head, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     max_set = smem;

@@ -1,15 +1,10 @@
 #!/bin/bash
-# One gpurun call: plain run, then ncu launch list + one full capture of a kernel.
-# Usage: gpurun -- bash scripts/gpu_ncu.sh <tag> <kernel-regex> [skip] [count] [extra bench args]
-TAG=${1:-ncu}; KRE=${2:-k_gemm}; SKIP=${3:-2000}; CNT=${4:-700}; shift 4
+# One ncu --set full capture of the kernels matching a regex during a short bench run.
+# Usage: gpurun -- bash scripts/gpu_ncu.sh <tag> <kernel regex> [skip] [count]
+TAG=${1:-ncu}; RE=${2:-k_blk}; SKIP=${3:-2}; CNT=${4:-2}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-CMD="python bench.py --streams 256 --steps 2 --warmup 3 --no-cpu-baseline --latency-reps 3 $@"
-$CMD > $OUT/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -s $SKIP -c $CNT --csv --log-file $OUT/launches.csv $CMD > $OUT/ncu_list.log 2>&1
-echo "list rc=$?"
-$CMD > $OUT/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:$KRE -s ${FSKIP:-24} -c ${FCNT:-3} -o $OUT/prof $CMD > $OUT/ncu_full.log 2>&1
-echo "full rc=$?"
-tail -3 $OUT/ncu_list.log $OUT/ncu_full.log
-ls -la $OUT
+ARGS="--steps 2 --warmup 3 --no-cpu-baseline --latency-reps 5 --ingest-streams 0 --ragged-streams 0 --long-read-batch 0 ${BENCH_ARGS:-}"
+SNACB_DEBUG=1 python bench.py $ARGS > $OUT/plain.json 2> $OUT/plain.err &&
+ncu --set full --clock-control none --import-source on -k regex:"$RE" -s $SKIP -c $CNT -o $OUT/prof python bench.py $ARGS > $OUT/ncu.log 2>&1
+echo "rc=$?"; tail -3 $OUT/plain.err; tail -3 $OUT/ncu.log
