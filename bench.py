@@ -209,8 +209,9 @@ def run_ours(args) -> None:
     S, F, K, W = args.streams, args.frames, args.steps, max(3, args.warmup)
     eng = SnacEngine(weights.random_state_dict(0, "w1"), device=local, precision=args.precision, trim=not args.no_trim,
                      chunk_items=args.chunk, lanes=args.lanes, persistent_ru=args.persistent_ru)
-    tok_host = synth_tokens(rank * S, S, F)                      # this rank's stream partition
-    keys = np.arange(rank * S, rank * S + S, dtype=np.uint64)    # Philox stream keys
+    my_streams = rank + world * np.arange(S, dtype=np.int64)     # this rank's partition: stream s -> rank s mod G (partition.py)
+    tok_host = np.concatenate([synth_tokens(int(s_), 1, F) for s_ in my_streams])
+    keys = my_streams.astype(np.uint64)                          # Philox stream keys
     tok_dev = torch.from_numpy(tok_host).to(dev)
     pcm_dev = torch.empty((S, 2048), dtype=torch.int16, device=dev)
     st_dev = torch.empty((S,), dtype=torch.int32, device=dev)
@@ -289,6 +290,128 @@ def run_ours(args) -> None:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     tot_dev_ms, tot_e2e_ms, tot_pipe_ms = float(t_dev[0]), float(t_dev[1]), float(t_dev[2])
 
+    # ---- sustained: back-to-back device ticks for >= 2 s (no flush, no host work in between: the power-capped figure;
+    # the per-tick activation traffic is GBs, far beyond L2), with its own clock samples
+    sus_sampler = ClockSampler(local)
+    if rank == 0:
+        sus_sampler.start()
+    barrier()
+    ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_sus = max(8, int(args.sustained_s / max(1e-4, (sum(dev_ms) / K) * 1e-3)))
+    ev_a.record()
+    for i in range(n_sus):
+        tick_device(400 + i)
+    ev_b.record()
+    barrier()
+    sus_ms = torch.tensor([ev_a.elapsed_time(ev_b)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(sus_ms, op=dist.ReduceOp.MAX)
+    sus_clocks = sus_sampler.stop() if rank == 0 else {}
+    sustained = {"value": world * S * n_sus * AUDIO_S_PER_WINDOW / (float(sus_ms[0]) * 1e-3), "unit": UNIT, "ticks": n_sus,
+                 "seconds": float(sus_ms[0]) * 1e-3, "ms_per_step": float(sus_ms[0]) / n_sus, "clocks": sus_clocks,
+                 "note": "device-resident inputs, ticks issued back to back, max over ranks"}
+
+    # ---- BASELINE config 4 AS WRITTEN (strong scaling): 1024 streams in total, stream s on rank s mod G, one tick = every
+    # rank decodes its 1024/G windows through the host API and the PCM of all streams is gathered on rank 0 (host-side
+    # gather over gloo) INSIDE the timed region.
+    gloo = dist.new_group(backend="gloo") if world > 1 else None
+    from project_morpheus_b200.partition import PartitionedDecoder, local_streams, partition_of
+    cfg4 = None
+    if args.cfg4_streams > 0:
+        tot4 = args.cfg4_streams
+        mine4 = local_streams(tot4, rank, world)
+        tok4 = np.concatenate([synth_tokens(s_, 1, F) for s_ in mine4]) if mine4 else np.zeros((0, 7 * F), np.int32)
+        keys4 = np.asarray(mine4, dtype=np.uint64)
+        pd = PartitionedDecoder(lambda w: [], rank=rank, world_size=world, group=gloo) if world > 1 else None
+        equal = (tot4 % world == 0)
+
+        def tick4(step):
+            pcm4, st4 = eng.decode_windows(tok4, noise="philox", seed=step, keys=keys4)
+            if pd is not None and equal:
+                return pd.gather_pcm(pcm4, dst=0)
+            return pcm4
+
+        for i in range(3):
+            tick4(i)
+        barrier()
+        t0 = time.perf_counter()
+        n4 = max(4, K)
+        for i in range(n4):
+            g4 = tick4(500 + i)
+        torch.cuda.synchronize(dev)
+        dt4 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt4, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            assert g4 is not None and g4.shape == (tot4 if (world == 1 or equal) else len(mine4), 2048)
+            cfg4 = {"streams_total": tot4, "streams_per_gpu": len(mine4), "ticks": n4, "ms_per_tick": 1e3 * float(dt4[0]) / n4,
+                    "audio_s_per_s": tot4 * n4 * AUDIO_S_PER_WINDOW / float(dt4[0]), "scaling": "strong",
+                    "gather": ("gloo host gather of every stream's PCM onto rank 0 inside the timed region" if world > 1
+                               else "single GPU: no gather"),
+                    "api": "SnacEngine.decode_windows (host buffers in and out) per rank, PartitionedDecoder.gather_pcm"}
+
+    # ---- BASELINE config 5 on the whole box: 512 streams per GPU, ragged ticks (0/1/2 pending windows of 1/4/7 frames per
+    # stream), scene lifetimes with evict + slot refill (barge_in) and re-homing of a stream to another partition after
+    # three chunks (mid_stream_swap), every tick through PartitionedDecoder.decode_tick (host gather inside the timing).
+    cfg5p = None
+    if world > 1 and args.cfg5_streams_per_gpu > 0:
+        ns5 = args.cfg5_streams_per_gpu * world
+        rng5 = np.random.default_rng(2024)  # same seed on every rank: all ranks build the same global tick
+        scene = rng5.integers(0, 4, size=ns5)  # breathing_room / long_read / barge_in / mid_stream_swap, 25 % each
+        life = np.where(scene == 0, 2, np.where(scene == 1, 60, np.where(scene == 2, 2, 6)))
+        age = np.zeros(ns5, dtype=np.int64)
+        sid = np.arange(ns5, dtype=np.int64)  # current stream id of slot i (changes on refill / re-homing)
+        next_id = ns5
+        ticks5 = []
+        stats5 = {"evicted": 0, "rehomed": 0, "windows": 0}
+        for t in range(10):
+            tick = []
+            for i in range(ns5):
+                for _ in range(int(rng5.choice([0, 1, 2], p=[0.2, 0.6, 0.2]))):
+                    fr = 1 if age[i] == 0 else (7 if age[i] >= 4 else 4)
+                    tick.append((int(sid[i]), synth_tokens(int(90000 + sid[i] * 13 + t), 1, 7)[0][: 7 * fr].tolist()))
+                    age[i] += 1
+                if scene[i] == 3 and age[i] == 3:      # mid_stream_swap: the stream moves to another adapter / partition
+                    sid[i] = next_id + ((partition_of(int(sid[i]), world) + 1 - next_id) % world)
+                    next_id += world
+                    stats5["rehomed"] += 1
+                if age[i] >= life[i]:                    # scene over (barge_in: evicted after chunk 2): slot refilled
+                    sid[i], age[i] = next_id, 0
+                    next_id += 1
+                    stats5["evicted"] += 1
+            stats5["windows"] += len(tick)
+            ticks5.append(tick)
+
+        def dec5(wins):
+            n5 = len(wins)
+            tok5 = np.zeros((n5, 49), dtype=np.int32)
+            lens5 = [len(w) for w in wins]
+            for i, w in enumerate(wins):
+                tok5[i, : len(w)] = w
+            pcm5, st5 = eng.decode_windows(tok5, ntok=lens5, noise="philox", seed=9, keys=np.arange(n5, dtype=np.uint64))
+            return [pcm5[i].tobytes() if st5[i] == _lib.WIN_OK else (b"" if st5[i] == _lib.WIN_EMPTY else None) for i in range(n5)]
+
+        pd5 = PartitionedDecoder(dec5, rank=rank, world_size=world, group=gloo)
+        for tick in ticks5[:2]:
+            pd5.decode_tick(tick, dst=0)
+        barrier()
+        t0 = time.perf_counter()
+        emitted5 = 0
+        for tick in ticks5:
+            merged = pd5.decode_tick(tick, dst=0)
+            if rank == 0:
+                assert len(merged) == len({s_ for s_, _ in tick})
+                emitted5 += sum(1 for v in merged.values() if v)
+        torch.cuda.synchronize(dev)
+        dt5 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(dt5, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            cfg5p = dict(stats5, streams=ns5, streams_per_gpu=args.cfg5_streams_per_gpu, ticks=len(ticks5),
+                         ms_per_tick=1e3 * float(dt5[0]) / len(ticks5), audio_s_per_s=emitted5 * AUDIO_S_PER_WINDOW / float(dt5[0]),
+                         note="whole box, PartitionedDecoder.decode_tick per tick: ragged host decode per rank + gather_object of "
+                              "every stream's bytes onto rank 0 inside the timed region; evict / refill / re-homing are host "
+                              "bookkeeping (the decoder is stateless across windows)")
+
     # ---- per-kernel-class device time (CUDA events around each launch), same tick, right after
     stats, extra = {}, {}
     if rank == 0:
@@ -333,6 +456,56 @@ def run_ours(args) -> None:
                                               "note": "project_morpheus_b200.speechpipe.convert_to_audio, Python list in -> bytes out"}
         except Exception as exc:  # noqa: BLE001
             extra["convert_to_audio_call"] = {"error": repr(exc)}
+
+        # Through the reference's seam: N requests, one SnacB200Adapter + one pull loop each (orchestrator/core.py:89-117) under
+        # ONE event loop; all of them decode through the shared DecodeTicker (one batched engine call per tick).
+        if args.pull_streams:
+            try:
+                import asyncio
+                from oracle import speechpipe_ref as sp_ref2
+                from project_morpheus_b200.adapter import SnacB200Adapter
+                sp_mod = importlib.import_module("project_morpheus_b200.speechpipe")
+                res_pull = {}
+                for n_ad in [int(x) for x in args.pull_streams.split(",") if x]:
+                    fr_ad = 12
+                    strs = [sp_ref2.synth_token_strings(60000 + i, fr_ad) for i in range(n_ad)]
+
+                    def source(strings):
+                        async def gen(**_):
+                            for j, s_ in enumerate(strings):
+                                if j % 7 == 0:
+                                    await asyncio.sleep(0)
+                                yield s_
+                        return gen
+
+                    async def pull_all():
+                        ads = [SnacB200Adapter("bench", "tara", token_source=source(st_), seed=i) for i, st_ in enumerate(strs)]
+
+                        async def loop(ad):
+                            nb = 0
+                            while True:
+                                c = await ad.pull(4096)
+                                nb += len(c.pcm)
+                                if c.eos:
+                                    return nb
+                        return sum(await asyncio.gather(*[loop(a) for a in ads]))
+
+                    tkr = sp_mod.get_ticker()
+                    asyncio.run(pull_all())  # warm-up (workspace, graphs)
+                    t_before = dict(tkr.stats())
+                    t0 = time.perf_counter()
+                    nbytes = asyncio.run(pull_all())
+                    dt = time.perf_counter() - t0
+                    t_after = tkr.stats()
+                    res_pull[f"{n_ad}_streams"] = {
+                        "audio_s_per_s": nbytes / 2 / SAMPLE_RATE / dt, "seconds": dt, "bytes": nbytes,
+                        "ticks": t_after["ticks"] - t_before["ticks"], "windows": t_after["windows"] - t_before["windows"],
+                        "frames_per_stream": fr_ad}
+                res_pull["note"] = ("token strings -> SnacB200Adapter.pull(4096) per request, per-token Python of tokens_decoder "
+                                    "included; engine calls = ticks, not windows")
+                extra["ticker_pull"] = res_pull
+            except Exception as exc:  # noqa: BLE001
+                extra["ticker_pull"] = {"error": repr(exc)[:300]}
 
         # BASELINE config 5 pattern: ragged ticks (per stream 0/1/2 pending windows, 1 / 4 / 7 frames each)
         if args.ragged_streams > 0:
@@ -566,6 +739,17 @@ def run_ours(args) -> None:
             gpu_torch = {"kind": "oracle port on stock PyTorch CUDA (cuDNN/ATen), not this repo's kernels",
                          "b1_ms_per_window": 1e3 * dt1, "b1_audio_s_per_s": AUDIO_S_PER_WINDOW / dt1,
                          "b64_ms_per_tick": 1e3 * dt64, "b64_audio_s_per_s": 64 * AUDIO_S_PER_WINDOW / dt64}
+            try:  # the whole 1024-window tick as ONE stock-PyTorch batch (the reference never batches; upper bar for cuDNN)
+                tk_all = torch.from_numpy(tok_host.astype(np.int64)).to(dev).reshape(S, F, 7)
+                cs = [tk_all[:, :, 0], tk_all[:, :, [1, 4]].reshape(S, 2 * F), tk_all[:, :, [2, 3, 5, 6]].reshape(S, 4 * F)]
+                one(0, S)
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                one(0, S)
+                dtS = time.perf_counter() - t0
+                gpu_torch.update({f"b{S}_ms_per_tick": 1e3 * dtS, f"b{S}_audio_s_per_s": S * AUDIO_S_PER_WINDOW / dtS})
+            except Exception as exc:  # noqa: BLE001
+                gpu_torch[f"b{S}_error"] = repr(exc)[:200]
             del ref_model
             torch.cuda.empty_cache()
         except Exception as exc:  # noqa: BLE001
@@ -585,7 +769,7 @@ def run_ours(args) -> None:
         "dtype": "f16 operands, f32 accumulate" if args.precision == "fp16" else "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "streams_per_gpu": S, "frames_per_window": F,
                    "tokens_per_window": 7 * F, "weights": "random-init seed 0 variant w1", "noise": "in-kernel philox",
-                   "precision": args.precision, "trim": not args.no_trim, "partition": f"stream s -> rank s // {S}",
+                   "precision": args.precision, "trim": not args.no_trim, "partition": "stream s -> rank s mod G (project_morpheus_b200.partition.partition_of)",
                    "l2": "256 MiB memset between steps (untimed); per-tick activations exceed L2"},
         "windows_per_s": wps, "realtime_factor_per_gpu": value / world,
         "tflops_reference_equivalent": wps * FLOP_PER_WINDOW_REFERENCE / 1e12,
@@ -597,6 +781,7 @@ def run_ours(args) -> None:
                 "sync_value": e2e_value, "sync_ms_per_step": tot_e2e_ms / K,
                 "sync_api": "snacb_decode_windows_host via SnacEngine.decode_windows, one blocking call per tick"},
         "gpu_launches": int(launches), "wall_s_device_region": wall_dev, "clocks": clocks,
+        "sustained": sustained, "cfg4_strong_scaling": cfg4, "cfg5_partitioned": cfg5p,
         "roofline": roof, "cpu_baseline": cpu, "gpu_torch_baseline": gpu_torch, "latency": extra, "checksum": checksum,
     }
     print(json.dumps(line), flush=True)
@@ -623,7 +808,11 @@ def main() -> None:
     ap.add_argument("--latency-reps", type=int, default=200)
     ap.add_argument("--ingest-streams", type=int, default=1024, help="streams of the token-ingress measurement (0 = skip)")
     ap.add_argument("--ragged-streams", type=int, default=512, help="streams of the config-5 ragged-tick side measurement (0 = skip)")
-    ap.add_argument("--long-read-batch", type=int, default=8, help="streams of the config-3 long_read side measurement (0 = skip)")
+    ap.add_argument("--long-read-batch", type=int, default=32, help="streams of the config-3 long_read side measurement (0 = skip)")
+    ap.add_argument("--sustained-s", type=float, default=2.0, help="seconds of back-to-back ticks for the sustained figure")
+    ap.add_argument("--cfg4-streams", type=int, default=1024, help="total streams of the config-4 strong-scaling leg (0 = skip)")
+    ap.add_argument("--cfg5-streams-per-gpu", type=int, default=512, help="config-5 whole-box leg, N > 1 only (0 = skip)")
+    ap.add_argument("--pull-streams", type=str, default="64,1024", help="concurrent adapters of the ticker / pull() leg ('' = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

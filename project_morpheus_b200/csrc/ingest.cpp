@@ -28,12 +28,16 @@ constexpr int kFirstWindow = 7, kShortWindow = 28, kLongWindow = 49;
 constexpr char kPrefix[] = "<custom_token_";
 constexpr int kPrefixLen = 14;
 
+// str.strip() whitespace (ASCII subset): includes the separators 0x1c-0x1f
 inline bool py_space(unsigned char c) { return c == ' ' || (c >= 0x09 && c <= 0x0d) || (c >= 0x1c && c <= 0x1f); }
+// whitespace int() skips around the number: ' ', \t \n \v \f \r only - int("\x1c7") raises ValueError
+// (speechpipe.py:179-181 turns that into None)
+inline bool int_space(unsigned char c) { return c == ' ' || (c >= 0x09 && c <= 0x0d); }
 
 // Python int(str) for the ASCII subset.  Returns false where int() raises ValueError.
 bool py_int(const char* p, const char* e, long long* out) {
-  while (p < e && py_space((unsigned char)*p)) ++p;
-  while (e > p && py_space((unsigned char)e[-1])) --e;
+  while (p < e && int_space((unsigned char)*p)) ++p;
+  while (e > p && int_space((unsigned char)e[-1])) --e;
   if (p >= e) return false;
   bool neg = false;
   if (*p == '+' || *p == '-') { neg = (*p == '-'); ++p; }

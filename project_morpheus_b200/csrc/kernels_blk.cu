@@ -402,30 +402,45 @@ __global__ void __launch_bounds__(kBlkThreads, 2) k_blk_tail(const __grid_consta
     tc_fence_before();
     __syncthreads();
 
-    // ---- decoder tail on the tile: y[o] = tanh(b + sum_{k,c} w[k][c] * s[39 + o + k][c]), o = 0..kTO-1
-    if (warp * 16 < kTO) {
-      const int o = warp * 16 + (lane & 15), half = lane >> 4;
-      float2 a2 = make_float2(0.f, 0.f), b2 = a2;
-      if (o < kTO) {
-        const float* xp = sX + (kBlkHalo + o) * PITCH + half * (C / 2);
-        const float* wp = sTw + half * (C / 2);
+    // ---- decoder tail on the tile: y[o] = tanh(b + sum_{k,c} w[k][c] * s[39 + o + k][c]), o = 0..kTO-1.
+    // Warp w owns outputs [11 w, 11 w + 11), lane = channel pair: every tile row is read ONCE (LDS.64, transposed-form
+    // FIR over the 7 taps as in the depthwise units), then the 11 per-lane partial sums are reduced across the warp.
+    // (One thread per output re-reads each row seven times: that version spent half of the kernel's shared-memory
+    // wavefronts here and kept only 11 of 16 warps busy.)
+    {
+      constexpr int LT = (kTO + kBlkWarps - 1) / kBlkWarps;
+      static_assert(C == 64, "tail: one lane per channel pair");
+      const int o0 = warp * LT;
+      float2 w[7];
 #pragma unroll
-        for (int k = 0; k < 7; ++k)
+      for (int k = 0; k < 7; ++k) w[k] = *reinterpret_cast<const float2*>(sTw + k * C + 2 * lane);
+      const float* p0 = sX + (kBlkHalo + o0) * PITCH + 2 * lane;
+      float vals[LT];
+      float2 acc[7];
 #pragma unroll
-          for (int c = 0; c < C / 2; c += 4) {
-            const float4 w4 = *reinterpret_cast<const float4*>(wp + k * C + c);
-            const float4 x4 = *reinterpret_cast<const float4*>(xp + k * PITCH + c);
-            a2 = __ffma2_rn(make_float2(w4.x, w4.y), make_float2(x4.x, x4.y), a2);
-            b2 = __ffma2_rn(make_float2(w4.z, w4.w), make_float2(x4.z, x4.w), b2);
-          }
+      for (int m = 0; m < LT + 6; ++m) {
+        const float2 v = *reinterpret_cast<const float2*>(p0 + m * PITCH);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+          const int j = m - k;
+          if (j >= 0 && j < LT) acc[j % 7] = (k == 0) ? __fmul2_rn(w[0], v) : __ffma2_rn(w[k], v, acc[j % 7]);
+        }
+        if (m >= 6) vals[m - 6] = acc[(m - 6) % 7].x + acc[(m - 6) % 7].y;
       }
-      float acc = (a2.x + a2.y) + (b2.x + b2.y);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int j = 0; j < LT; ++j) vals[j] += __shfl_xor_sync(0xffffffffu, vals[j], off);
+      float mine = 0.0f;
+#pragma unroll
+      for (int j = 0; j < LT; ++j)
+        if (lane == j) mine = vals[j];
+      const int o = o0 + lane;
       const int oi = t * kTO + o;  // emitted sample index inside [0, o_n)
       const int t_abs = a.o_lo + oi + it.shift0 * a.up;
-      if (half == 0 && o < kTO && oi < a.o_n && t_abs >= 0 && t_abs < t_hi &&
+      if (lane < LT && o < kTO && oi < a.o_n && t_abs >= 0 && t_abs < t_hi &&
           !(a.status && a.status[it.code_row] != SNACB_WIN_OK)) {
-        const float y = tanhf(acc + tail_b);
+        const float y = tanhf(mine + tail_b);
         const long long d = it.dst + oi;
         if (a.wav) a.wav[d] = y;
         if (a.pcm) a.pcm[d] = (int16_t)(y * 32767.0f);

@@ -22,6 +22,7 @@ reference's embedding lookup does.  There is no CPU fallback: without CUDA the d
 from __future__ import annotations
 
 import asyncio
+import itertools
 import logging
 import os
 from typing import AsyncIterator, List, Optional, Sequence
@@ -30,6 +31,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import ticker as ticker_mod
 from .snac import SNAC
 
 log = logging.getLogger("project_morpheus_b200.speechpipe")
@@ -53,18 +55,22 @@ PCM_BYTES = 4096
 # Noise for NoiseBlock: "philox" (fresh in-kernel noise per window, like the reference's randn),
 # "off", or inject explicit tensors through convert_to_audio_batch(noise=...).
 noise_mode = os.environ.get("SNACB_NOISE", "philox")
-_window_counter = 0
+# Philox keys: a window decoded through tokens_decoder is keyed by (its stream's key, its index in the stream) -
+# see ticker.window_key - so a stream's noise never depends on what other streams do.  Bare convert_to_audio calls
+# carry no stream identity (the reference signature has none): they draw from this process-wide sequence.
+_call_counter = itertools.count()
+INT32_MIN, INT32_MAX = -(1 << 31), (1 << 31) - 1
 
 
-def _decode_batch(tokens: np.ndarray, ntok: Optional[Sequence[int]], noise=None):
-    global _window_counter
+def _decode_batch(tokens: np.ndarray, ntok: Optional[Sequence[int]], noise=None, keys: Optional[np.ndarray] = None):
     eng = model.engine
     n = tokens.shape[0]
     mode = noise if noise is not None else noise_mode
-    keys = None
     if isinstance(mode, str) and mode == "philox":
-        keys = np.arange(_window_counter, _window_counter + n, dtype=np.uint64)
-        _window_counter += n
+        if keys is None:
+            keys = np.asarray([ticker_mod.window_key(0, next(_call_counter)) for _ in range(n)], dtype=np.uint64)
+    else:
+        keys = None
     if cuda_stream is not None:
         with torch.cuda.stream(cuda_stream):
             return eng.decode_windows(tokens, ntok=ntok, noise=mode, seed=model.noise_seed, keys=keys)
@@ -81,39 +87,75 @@ def _finish(pcm_row: np.ndarray, status: int) -> Optional[bytes]:
     return None
 
 
+def _as_int32(ids: Sequence[int]) -> Optional[np.ndarray]:
+    """Token ids as int32, or None when one does not fit (the reference's ``torch.tensor(frame, dtype=torch.int32)``
+    raises for those, speechpipe.py:81; they are never wrapped into the valid code range here)."""
+    a = np.asarray(ids, dtype=np.int64)
+    if a.size and (int(a.min()) < INT32_MIN or int(a.max()) > INT32_MAX):
+        return None
+    return a.astype(np.int32)
+
+
 def convert_to_audio(multiframe: Sequence[int], count: int) -> Optional[bytes]:
     """One window of token ids -> PCM16 bytes of samples [2048, 4096) of its decode (``count`` unused)."""
     if len(multiframe) < TOKENS_PER_FRAME:
         return None
     usable = (len(multiframe) // TOKENS_PER_FRAME) * TOKENS_PER_FRAME
-    tokens = np.asarray(multiframe[:usable], dtype=np.int64).astype(np.int32).reshape(1, usable)
-    pcm, status = _decode_batch(tokens, None)
+    tokens = _as_int32(multiframe[:usable])
+    if tokens is None:
+        raise RuntimeError("value cannot be converted to type int32 without overflow")
+    pcm, status = _decode_batch(tokens.reshape(1, usable), None)
     return _finish(pcm[0], int(status[0]))
 
 
-def convert_to_audio_batch(windows: Sequence[Sequence[int]], noise=None) -> List[Optional[bytes]]:
+def convert_to_audio_batch(windows: Sequence[Sequence[int]], noise=None, keys: Optional[np.ndarray] = None,
+                           errors: str = "none") -> List[Optional[bytes]]:
     """All pending windows of a decode tick in one launch sequence; entry i is what
-    ``convert_to_audio(windows[i], _)`` returns (``IndexError`` for a 4096 code is reported as
-    ``None`` here so one poisoned stream cannot fail the tick)."""
+    ``convert_to_audio(windows[i], _)`` returns.  Where that call would RAISE (``IndexError`` for a 4096 code,
+    ``RuntimeError`` for an id outside int32) entry i is ``None`` (``errors="none"``: one poisoned stream cannot fail
+    the tick) or the exception instance itself (``errors="values"``: the ticker re-raises it in that stream only).
+    ``keys``: one uint64 Philox key per window (default: the process-wide call sequence)."""
     n = len(windows)
     if n == 0:
         return []
     lens = [len(w) for w in windows]
     stride = max(TOKENS_PER_FRAME, max(lens))
-    if min(lens) == stride:  # uniform tick (the common case): one vectorised conversion
-        tokens = np.asarray(windows, dtype=np.int64).astype(np.int32).reshape(n, stride)
-    else:
-        tokens = np.zeros((n, stride), dtype=np.int32)
-        for i, w in enumerate(windows):
-            if lens[i]:
-                tokens[i, : lens[i]] = np.asarray(w, dtype=np.int64).astype(np.int32)
+    tokens = np.zeros((n, stride), dtype=np.int32)
+    overflow = set()
+    for i, w in enumerate(windows):
+        if lens[i]:
+            row = _as_int32(w)
+            if row is None:
+                if lens[i] >= TOKENS_PER_FRAME:  # shorter windows return None before the tensor is built (:69-70)
+                    overflow.add(i)
+                lens[i] = 0  # -> WIN_REJECTED
+            else:
+                tokens[i, : lens[i]] = row
     uniform = len(set(lens)) == 1 and lens[0] >= TOKENS_PER_FRAME
-    pcm, status = _decode_batch(tokens, None if uniform else lens, noise=noise)
+    pcm, status = _decode_batch(tokens, None if uniform else lens, noise=noise, keys=keys)
     out: List[Optional[bytes]] = []
     for i in range(n):
         st = int(status[i])
-        out.append(None if st == _lib.WIN_CODE4096 else _finish(pcm[i], st))
+        if i in overflow:
+            out.append(RuntimeError("value cannot be converted to type int32 without overflow") if errors == "values" else None)
+        elif st == _lib.WIN_CODE4096:
+            out.append(IndexError("index out of range in self") if errors == "values" else None)
+        else:
+            out.append(_finish(pcm[i], st))
     return out
+
+
+# ----------------------------------------------------------------------------- the shared decode ticker
+USE_TICKER = os.environ.get("SNACB_TICKER", "1") != "0"
+_ticker: Optional["ticker_mod.DecodeTicker"] = None
+
+
+def get_ticker() -> "ticker_mod.DecodeTicker":
+    """The process-wide ticker every ``tokens_decoder`` coroutine decodes through (created on first use)."""
+    global _ticker
+    if _ticker is None:
+        _ticker = ticker_mod.DecodeTicker(lambda windows, keys: convert_to_audio_batch(windows, keys=keys, errors="values"))
+    return _ticker
 
 
 from .tokens import (  # noqa: E402,F401  (re-exported: same names as the reference module)
@@ -122,20 +164,41 @@ from .tokens import (  # noqa: E402,F401  (re-exported: same names as the refere
 )
 
 
-async def tokens_decoder(token_gen: AsyncIterator[str]):
-    """Token strings in, PCM chunks out; same windows, order and chunk sizes as the reference."""
+async def tokens_decoder(token_gen: AsyncIterator[str], *, stream_key: Optional[int] = None, ticker=None):
+    """Token strings in, PCM chunks out; same windows, order and chunk sizes as the reference.
+
+    Additive keywords: ``stream_key`` seeds this stream's NoiseBlock noise (window w of the stream uses the Philox key
+    ``window_key(stream_key, w)``; default: a fresh key per stream); ``ticker`` overrides the shared
+    :class:`~project_morpheus_b200.ticker.DecodeTicker` (``False`` = decode each window on its own, like the
+    reference).  With the ticker, the windows of all concurrently running ``tokens_decoder`` coroutines of the event
+    loop go to the GPU as one batch per tick."""
     plan = WindowPlanner()
+    key = ticker_mod.fresh_stream_key() if stream_key is None else int(stream_key)
+    tk = get_ticker() if (ticker is None and USE_TICKER) else (ticker or None)
+    n_windows = 0
+
+    async def decode(window):
+        nonlocal n_windows
+        wkey = ticker_mod.window_key(key, n_windows)
+        n_windows += 1
+        if tk is not None:
+            return await tk.decode(list(window), wkey)  # raises what convert_to_audio would raise, in this stream only
+        out = convert_to_audio_batch([window], keys=np.asarray([wkey], dtype=np.uint64), errors="values")[0]
+        if isinstance(out, BaseException):
+            raise out
+        return out
+
     async for token_sim in token_gen:
         window = plan.push(token_sim)
         if window is None:
             continue
-        audio_samples = convert_to_audio(window, plan.count)
+        audio_samples = await decode(window)
         plan.result(audio_samples)
         if audio_samples is not None:
             yield audio_samples
     window = plan.flush()
     if window is not None:
-        audio_samples = convert_to_audio(window, plan.count)
+        audio_samples = await decode(window)
         if audio_samples is not None:
             yield audio_samples
 

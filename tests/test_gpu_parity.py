@@ -366,6 +366,115 @@ def test_speechpipe_module_matches_oracle_stream(oracle_w1, state_dict_w1, monke
         speechpipe.convert_to_audio([4096] + [5] * 27, 0)
     outs = speechpipe.convert_to_audio_batch([[5] * 28, [4096] + [5] * 27, [5] * 7, [5] * 3, strings and [9] * 49])
     assert [None if o is None else len(o) for o in outs] == [4096, None, 0, None, 4096]
+    # ids outside int32: torch.tensor(frame, dtype=torch.int32) raises in the reference (speechpipe.py:81); never wrapped
+    with pytest.raises(RuntimeError, match="int32"):
+        speechpipe.convert_to_audio([(1 << 32) + 5] + [5] * 27, 0)
+    assert speechpipe.convert_to_audio([(1 << 32) + 5] + [5] * 5, 0) is None  # < 7 tokens returns None first (:69-70)
+    outs = speechpipe.convert_to_audio_batch([[(1 << 32) + 5] + [5] * 27, [5] * 28], errors="values")
+    assert isinstance(outs[0], RuntimeError) and len(outs[1]) == 4096
+    assert speechpipe.convert_to_audio_batch([[-(1 << 40)] + [5] * 27])[0] is None
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_cuda_path_matches_committed_g4_golden_pcm(engines, precision):
+    """G4: the config-1 stream's PCM as the VERBATIM reference file produced it over the oracle model (committed in
+    tests/golden/speechpipe_golden.json by make_golden.py), against the CUDA path with the same injected noise."""
+    from project_morpheus_b200.tokens import WindowPlanner
+    g4 = load_golden()["g4_config1"]
+    eng = engines(precision)
+    plan, chunks, call = WindowPlanner(), [], 0
+
+    def decode(win):
+        nonlocal call
+        F = len(win) // 7
+        noise = snac_ref.make_noise(1, F, seed=99 + call)
+        call += 1
+        pcm, st = eng.decode_windows(np.asarray(win[: 7 * F], dtype=np.int32)[None], noise=snac_ref.pack_noise(noise))
+        return b"" if st[0] == _lib.WIN_EMPTY else (pcm[0].tobytes() if st[0] == _lib.WIN_OK else None)
+
+    for s in sp.synth_token_strings(g4["stream"], g4["frames"]):
+        win = plan.push(s)
+        if win is None:
+            continue
+        out = decode(win)
+        plan.result(out)
+        if out is not None:
+            chunks.append(out)
+    win = plan.flush()
+    if win is not None:
+        chunks.append(decode(win))
+    assert [len(c) for c in chunks] == g4["sizes"]
+    for idx, want in g4["pcm"].items():
+        got = np.frombuffer(chunks[int(idx)], dtype="<i2").astype(np.int32)
+        want = np.asarray(want, dtype=np.int32)
+        if precision == "fp32":
+            assert np.abs(got - want).max() <= 2
+        else:
+            _check_wave(want.astype(np.float32) / 32767.0, got.astype(np.float32) / 32767.0, TOL_MAX_ABS, TOL_SNR_DB - 0.5)
+    rms = [float(np.sqrt(np.mean(np.frombuffer(c, dtype="<i2").astype(np.float64) ** 2))) if c else 0.0 for c in chunks]
+    assert np.allclose(rms, g4["rms"], rtol=2e-3, atol=1.0)
+
+
+def test_concurrent_adapters_batch_through_the_ticker_on_gpu(state_dict_w1, monkeypatch):
+    """north_star: concurrent streams are batched into one launch per tick BEHIND the untouched orchestrator.  64
+    requests, one adapter + one orchestrator-style pull loop each (orchestrator/core.py:89-117) under one event loop:
+    bytes identical to the per-stream path (noise off), and the engine saw ticks, not windows."""
+    monkeypatch.setenv("SNACB_NOISE", "off")
+    monkeypatch.setenv("SNACB_PRECISION", "fp16")
+    monkeypatch.setenv("SNACB_RANDOM_INIT", "0:w1")
+    monkeypatch.delenv("ORPHEUS_SNAC_PATH", raising=False)
+    import importlib
+    import sys
+    sys.modules.pop("project_morpheus_b200.speechpipe", None)
+    speechpipe = importlib.import_module("project_morpheus_b200.speechpipe")
+    from project_morpheus_b200.adapter import SnacB200Adapter
+    n = 64
+    streams = [sp.synth_token_strings(300 + i, 5 + (i % 6)) for i in range(n)]
+
+    def source(strings):
+        async def gen(**_):
+            for i, s in enumerate(strings):
+                if i % 7 == 0:
+                    await asyncio.sleep(0)
+                yield s
+        return gen
+
+    async def pull_loop(ad, k):
+        out, sizes = bytearray(), [8, 12, 16, 24, 32, 48, 64]
+        while True:
+            c = await ad.pull(sizes[k % 7] * 16)
+            out += c.pcm
+            k += 1
+            if c.eos:
+                return bytes(out)
+
+    async def main():
+        ads = [SnacB200Adapter("p", "tara", token_source=source(s), seed=i) for i, s in enumerate(streams)]
+        return await asyncio.gather(*[pull_loop(a, i) for i, a in enumerate(ads)])
+
+    eng = speechpipe.model.engine
+    calls = {"n": 0}
+    real_decode = eng.decode_windows
+
+    def counting(*a, **kw):
+        calls["n"] += 1
+        return real_decode(*a, **kw)
+
+    monkeypatch.setattr(eng, "decode_windows", counting)
+    got = asyncio.run(main())
+    batched_calls = calls["n"]
+    st = speechpipe.get_ticker().stats()
+    assert st["ticks"] * 8 < st["windows"] and st["max_tick"] >= n // 2, st
+
+    async def serial(strings):
+        return b"".join([c async for c in speechpipe.tokens_decoder(source(strings)(), ticker=False)])
+
+    calls["n"] = 0
+    want = [asyncio.run(serial(s)) for s in streams]
+    serial_calls = calls["n"]
+    assert got == want
+    assert all(len(g) > 0 for g in got)
+    assert batched_calls == st["ticks"] and serial_calls == st["windows"] and batched_calls * 8 < serial_calls, (batched_calls, serial_calls)
 
 
 def test_snac_shim_runs_decode_like_reference(oracle_w1, state_dict_w1):

@@ -60,6 +60,36 @@ def test_parser_matches_python_restatement_on_ascii(pieces, index):
     assert parse_native(text, index) == want, repr(text)
 
 
+NUMBER_FIELDS = ["7", " 7 ", "\t7\n", "\x0b7\x0c", "\x1c7", "7\x1f", "\x1d7\x1e", " \x1c 7", "+7", "-7", "4_106", "_7", "7_", "", " ",
+                 "0x7", "7.0", "\r28681\r", "1\x1c2"]
+
+
+@pytest.mark.parametrize("field", NUMBER_FIELDS)
+@pytest.mark.parametrize("outer", ["{}", " {} ", "\x1c{}\x1f", "junk{}", "<custom_token_3>{}"])
+def test_parser_number_field_whitespace_is_int_whitespace(ensure_lib, field, outer):
+    """int() skips ' \\t\\n\\v\\f\\r' only: 0x1c-0x1f inside the number field make the reference return None
+    (speechpipe.py:179-181), while str.strip() does remove them around the whole token (speechpipe.py:166)."""
+    text = outer.format("<custom_token_" + field + ">")
+    for index in (0, 1, 6, 9):
+        tokens.token_id_cache.clear()
+        assert parse_native(text, index) == tokens.turn_token_into_id(text, index), repr(text)
+    if "\x1c7" in field or "7\x1f" in field:
+        assert parse_native("<custom_token_" + field + ">", 1) is None
+
+
+@settings(max_examples=400, deadline=None)
+@given(st.lists(st.sampled_from(["0", "1", "7", "42", "4106", " ", "\t", "\x1c", "\x1f", "\r", "_", "+", "-", "x"]), min_size=0, max_size=6),
+       st.integers(min_value=0, max_value=60))
+def test_parser_matches_python_restatement_on_wrapped_number_fields(pieces, index):
+    """Every example is a syntactically complete token: prefix + field + '>' (the open-ended strategy above rarely forms one)."""
+    text = "<custom_token_" + "".join(pieces) + ">"
+    tokens.token_id_cache.clear()
+    want = tokens.turn_token_into_id(text, index)
+    if want is not None and abs(want) > (1 << 61):
+        return
+    assert parse_native(text, index) == want, repr(text)
+
+
 def dirty_stream(seed, frames):
     rng = np.random.default_rng(seed)
     s = sp.synth_token_strings(seed, frames)
