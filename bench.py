@@ -639,6 +639,25 @@ def run_ours(args) -> None:
                                       "note": "overlap-add stitcher, one 2048-sample chunk per stream per tick, native = one StitcherBank.push_tick call per tick; numpy = the "
                                               "reference's algorithm (oracle restatement), scaled from a 1/8 sample of the streams"}
 
+        # precision safety net: the same tick through the split-operand recipe (SNACB_PREC_FP16X3, <= 2 LSB vs fp32)
+        if args.precision == "fp16" and not args.no_cpu_baseline:
+            try:
+                eng3 = SnacEngine(weights.random_state_dict(0, "w1"), device=local, precision="fp16x3", trim=not args.no_trim)
+                for i in range(2):
+                    eng3.decode_windows_device(tok_dev, noise="philox", seed=i, keys=keys, pcm=pcm_dev, status=st_dev)
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                for i in range(3):
+                    eng3.decode_windows_device(tok_dev, noise="philox", seed=10 + i, keys=keys, pcm=pcm_dev, status=st_dev)
+                torch.cuda.synchronize(dev)
+                dt3 = (time.perf_counter() - t0) / 3
+                extra["precision_fp16x3"] = {"ms_per_tick": 1e3 * dt3, "audio_s_per_s": S * AUDIO_S_PER_WINDOW / dt3,
+                                             "note": "two-term fp16 splits of both GEMM operands, 3 tcgen05 products per k-block, fp32 "
+                                                     "elementwise kernels; <= 2 LSB vs the fp32 oracle (tests/test_gpu_parity.py)"}
+                eng3.close()
+            except Exception as exc:  # noqa: BLE001
+                extra["precision_fp16x3"] = {"error": repr(exc)[:300]}
+
         # BASELINE config 3 (long_read): one-shot decode of 720-frame utterances, time-tiled; reduced batch by default
         if args.long_read_batch > 0:
             Fl, Bl = 720, args.long_read_batch

@@ -41,6 +41,7 @@ extern "C" {
 #define SNACB_WIN_REJECTED 1  /* reference returns None: < 7 tokens, or a code < 0 or > 4096        */
 #define SNACB_WIN_CODE4096 2  /* code == 4096 passes the reference validator, then F.embedding raises */
 #define SNACB_WIN_EMPTY 3     /* one whole frame only: slice [2048:4096) is empty, reference returns b'' */
+#define SNACB_WIN_NONFINITE 4 /* the decode produced a non-finite sample (fp16 operand range exceeded): PCM withheld, see SNACB_PREC_* */
 
 /* noise modes for NoiseBlock (x + randn[B,1,T] * W_n x inside the third-party decoder) */
 #define SNACB_NOISE_OFF 0     /* zeros                                                  */
@@ -50,6 +51,8 @@ extern "C" {
 /* arithmetic recipes for the GEMM-shaped layers (1x1 convs, ConvTranspose1d) */
 #define SNACB_PREC_FP32 0     /* CUDA-core fp32 FMA: the exact/bring-up path              */
 #define SNACB_PREC_FP16 1     /* tcgen05 kind::f16, fp16 operands, fp32 TMEM accumulators */
+#define SNACB_PREC_FP16X3 2   /* tcgen05 kind::f16 on two-term fp16 splits of both operands (hi*hi + hi*lo + lo*hi): fp32-grade
+                                 products for checkpoints that outgrow single-pass fp16; exact sinf Snake, fp32 depthwise */
 
 /* snacb_config.flags */
 #define SNACB_FLAG_NO_RU_FUSION 1 /* tensor-core recipe: run every ResidualUnit as dw kernel + GEMM kernel */

@@ -10,9 +10,9 @@ import os
 
 ABI_VERSION = 1
 OK = 0
-WIN_OK, WIN_REJECTED, WIN_CODE4096, WIN_EMPTY = 0, 1, 2, 3
+WIN_OK, WIN_REJECTED, WIN_CODE4096, WIN_EMPTY, WIN_NONFINITE = 0, 1, 2, 3, 4
 NOISE_OFF, NOISE_TENSOR, NOISE_PHILOX = 0, 1, 2
-PREC_FP32, PREC_FP16 = 0, 1
+PREC_FP32, PREC_FP16, PREC_FP16X3 = 0, 1, 2
 FLAG_NO_RU_FUSION = 1
 FLAG_NO_CONVT_NOISE_FUSION = 2
 FLAG_PERSISTENT_RU = 4

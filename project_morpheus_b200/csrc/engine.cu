@@ -19,7 +19,7 @@ thread_local std::string g_create_error;
 
 struct RuDev {
   float *a1, *i1, *dw_w, *dw_b, *a2, *i2, *pw_w, *pw_b;
-  __half* pw16;
+  __half* pw16;  // SNACB_PREC_FP16: [C][C]; SNACB_PREC_FP16X3: [C][3C] = [hi | lo | hi]
 };
 struct BlockDev {
   float *alpha, *inv, *ct_w /*[s*Cout][2*Cin]*/, *ct_b, *noise_w;
@@ -235,7 +235,7 @@ void tap(snacb_engine* e, int stage, const float* p, Rng r, int C, int n_items, 
 // Runs one uniform group of items through the layer stack (fp32 recipe).
 int run_group_f32(snacb_engine* e, const Plan& P, const Item* d_items, int n_total, int out_len, Rng tail_out,
                   const int32_t* c0, const int32_t* c1, const int32_t* c2, int pitch0, const NoiseCfg& nz,
-                  const int32_t* d_status, float* wav, int16_t* pcm, char* ws_free, size_t ws_avail,
+                  int32_t* d_status, float* wav, int16_t* pcm, char* ws_free, size_t ws_avail,
                   cudaStream_t st) {
   const DevWeights& W = e->w;
   const size_t Zf = (size_t)P.z.n() * kLatent, Hf = (size_t)P.h.n() * kLatent, S = P.max_stage_floats;
@@ -348,7 +348,7 @@ int run_group_f32(snacb_engine* e, const Plan& P, const Item* d_items, int n_tot
 // Buffers per chunk: Z (latent, fp32), X/Y (fp32 residual stream ping-pong), P/Q (fp16 GEMM operands).
 int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_total, int out_len, Rng tail_out,
                  const int32_t* c0, const int32_t* c1, const int32_t* c2, int pitch0, const NoiseCfg& nz,
-                 const int32_t* d_status, float* wav, int16_t* pcm, char* ws_free, size_t ws_avail, int chunk,
+                 int32_t* d_status, float* wav, int16_t* pcm, char* ws_free, size_t ws_avail, int chunk,
                  int lanes, cudaStream_t st_caller) {
   const DevWeights& W = e->w;
   const size_t Zf = (size_t)P.z.n() * kLatent, S = P.max_stage_floats;
@@ -549,17 +549,121 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
   return SNACB_OK;
 }
 
+size_t per_item_bytes_x3(const Plan& P) {
+  const size_t Sb = pad256(P.max_stage_floats * 4);
+  return pad256((size_t)P.z.n() * kLatent * 4) + pad256((size_t)P.h.n() * kLatent * 4) + 4 * Sb + 2048;
+}
+
+// Split-operand recipe (SNACB_PREC_FP16X3): the precision safety net for checkpoints whose activations need more than
+// fp16's 11 bits / 65504 range at the GEMM operands.  Every GEMM-shaped layer still runs on tcgen05 (kind::f16), but on
+// two-term fp16 splits of BOTH operands, three products per k-block (hi*hi + hi*lo + lo*hi, SURVEY App. E: 117 dB,
+// <= 1 LSB); everything else is the fp32 CUDA-core recipe's kernels (exact sinf Snake, fp32 depthwise).  One split
+// kernel per GEMM turns the fp32 operand into [hi | lo]; the GEMM's K loop runs over the concatenated segments.
+int run_group_x3(snacb_engine* e, const Plan& P, const Item* d_items, int n_total, int out_len, Rng tail_out,
+                 const int32_t* c0, const int32_t* c1, const int32_t* c2, int pitch0, const NoiseCfg& nz,
+                 int32_t* d_status, float* wav, int16_t* pcm, char* ws_free, size_t ws_avail, cudaStream_t st) {
+  const DevWeights& W = e->w;
+  const size_t Zf = (size_t)P.z.n() * kLatent, Hf = (size_t)P.h.n() * kLatent, S = P.max_stage_floats;
+  const size_t per_item = per_item_bytes_x3(P);
+  int chunk = e->cfg.chunk_items > 0 ? e->cfg.chunk_items : 256;
+  if ((size_t)chunk * per_item > ws_avail) chunk = (int)(ws_avail / per_item);
+  if (chunk < 1) return fail(e, SNACB_ENOMEM, "workspace too small for one item");
+  const int F = P.T0 / 4;
+  const int noise_off[4] = {0, 32 * F, 288 * F, 1312 * F};
+  cudaError_t ce = cudaSuccess;
+  for (int start = 0; start < n_total && ce == cudaSuccess; start += chunk) {
+    const int n = std::min(chunk, n_total - start);
+    Bump bp(ws_free);
+    float* Z = bp.take<float>(Zf * n);
+    float* H0 = bp.take<float>(Hf * n);
+    float* X = bp.take<float>(S * n);
+    float* Y = bp.take<float>(S * n);
+    float* A = bp.take<float>(S * n);
+    __half* A16 = bp.take<__half>(2 * S * n);
+    GroupCtx g{d_items ? d_items + start : nullptr, start, n, out_len, P.T0, st, &e->launches, e->cfg.flags};
+    auto gemm = [&](TcGemmArgs a, const float* a32, Rng a_r, int K, const float* sn_a, const float* sn_i) {
+      if (ce != cudaSuccess) return;
+      {
+        ProfScope ps(e, KC_SNAKE, 4.0 * n * a_r.n() * K, 8.0 * n * a_r.n() * K, st);
+        launch_split16(a32, A16, (size_t)n * a_r.n(), K, sn_a, sn_i, st, &e->launches);
+      }
+      a.A = A16; a.K = K; a.a_rows = a_r.n(); a.a_lo = a_r.lo; a.split = 1;
+      const double M = (double)n * a.a_rows, segs = (a.epi == EPI_CONVT ? 2.0 : 1.0) * 3.0;
+      ProfScope ps(e, a.epi == EPI_CONVT ? KC_CONVT : KC_GEMM1, 2.0 * M * a.N * a.K * segs,
+                   2.0 * (M * a.K * 2.0 + (double)a.N * a.K * segs) + (double)n * a.o_r.n() * a.ldo * (4.0 + (a.R ? 4.0 : 0.0)), st);
+      ce = launch_gemm_tc(g, a);
+    };
+    auto dwconv = [&](const DwArgs& d) {
+      const double el = (double)n * d.out_r.n() * d.C;
+      ProfScope ps(e, KC_DW, el * (14.0 + (d.a1 ? 28.0 : 0.0) + (d.a2 ? 4.0 : 0.0)), 4.0 * ((double)n * d.in_r.n() * d.C + el), st);
+      launch_dwconv(g, d);
+    };
+    {
+      ProfScope ps(e, KC_CODES, 2.0 * 24 * kLatent * n * P.z.n(), 4.0 * kLatent * n * P.z.n(), st);
+      launch_from_codes(g, W.q, c0, c1, c2, pitch0, P.z, Z);
+    }
+    dwconv(DwArgs{Z, P.z, H0, P.h, kLatent, 1, 1, W.head_dw_w, W.head_dw_b, nullptr, nullptr, nullptr, nullptr});
+    {
+      TcGemmArgs a{};
+      a.epi = EPI_BIAS; a.W = W.head_pw16; a.N = kDecDim; a.bias = W.head_pw_b; a.out32 = X; a.o_r = P.h; a.ldo = kDecDim; a.up = 1;
+      gemm(a, H0, P.h, kLatent, nullptr, nullptr);
+    }
+    for (int b = 0; b < 4 && ce == cudaSuccess; ++b) {
+      const BlockPlan& B = P.b[b];
+      const BlockDev& Wb = W.blk[b];
+      {
+        TcGemmArgs a{};
+        a.epi = EPI_CONVT; a.W = Wb.ct16; a.N = B.s * B.Cout; a.bias = Wb.ct_b; a.s = B.s; a.p = B.p; a.Cout = B.Cout;
+        a.out32 = Y; a.o_r = B.ct; a.ldo = B.Cout; a.up = B.up_out;
+        gemm(a, X, B.in, B.Cin, Wb.alpha, Wb.inv);  // the block's Snake is applied by the split kernel
+      }
+      if (nz.mode != SNACB_NOISE_OFF) {
+        TcGemmArgs a{};
+        a.epi = EPI_NOISE; a.W = Wb.noise16; a.N = B.Cout; a.out32 = X; a.o_r = B.ct; a.ldo = B.Cout;
+        a.R = Y; a.r_r = B.ct; a.ldr = B.Cout; a.up = B.up_out;
+        a.noise = NoiseSrc{nz.mode, nz.tensor, nz.stride, noise_off[b], (unsigned long long)nz.seed, nz.d_keys, b, nz.d_seed};
+        gemm(a, Y, B.ct, B.Cout, nullptr, nullptr);
+      } else {
+        std::swap(X, Y);
+      }
+      Rng cur = B.ct;
+      for (int r = 0; r < 3 && ce == cudaSuccess; ++r) {
+        const RuDev& R = Wb.ru[r];
+        dwconv(DwArgs{X, cur, A, B.r[r], B.Cout, kDil[r], B.up_out, R.dw_w, R.dw_b, R.a1, R.i1, R.a2, R.i2});
+        TcGemmArgs a{};
+        a.epi = EPI_RESID; a.W = R.pw16; a.N = B.Cout; a.bias = R.pw_b; a.out32 = Y; a.o_r = B.r[r]; a.ldo = B.Cout;
+        a.R = X; a.r_r = cur; a.ldr = B.Cout; a.up = B.up_out;
+        gemm(a, A, B.r[r], B.Cout, nullptr, nullptr);
+        std::swap(X, Y);
+        cur = B.r[r];
+      }
+    }
+    if (ce != cudaSuccess) return fail(e, SNACB_ECUDA, "split-operand GEMM launch failed: %s", cudaGetErrorString(ce));
+    {
+      const double smp = (double)n * tail_out.n();
+      ProfScope ps(e, KC_TAIL, smp * (2.0 * 448 + 4.0 * 64), 4.0 * (double)n * P.b[3].r[2].n() * 64 + smp * 2.0, st);
+      TailArgs t{X, P.b[3].r[2], tail_out, W.tail_alpha, W.tail_inv, W.tail_w, W.tail_b, d_status, wav, pcm, false};
+      launch_tail(g, t);
+    }
+    int rc = check_launch(e, "split-operand layer pipeline");
+    if (rc) return rc;
+  }
+  return SNACB_OK;
+}
+
 // ---- sizing shared by every entry point
+inline bool is_tc(const snacb_engine* e) { return e->cfg.precision == SNACB_PREC_FP16 || e->cfg.precision == SNACB_PREC_FP16X3; }
 Plan plan_for(const snacb_engine* e, int T0, Rng out, bool clip) {
-  return make_plan(T0, out, clip, e->cfg.precision == SNACB_PREC_FP16);
+  return make_plan(T0, out, clip, is_tc(e));
 }
 size_t per_item_bytes(const snacb_engine* e, const Plan& P) {
   const size_t Zb = pad256((size_t)P.z.n() * kLatent * 4), Sb = pad256(P.max_stage_floats * 4);
   if (e->cfg.precision == SNACB_PREC_FP16) return Zb + 2 * Sb + 2 * pad256(P.max_stage_floats * 2) + 2048;
+  if (e->cfg.precision == SNACB_PREC_FP16X3) return per_item_bytes_x3(P);
   return Zb + pad256((size_t)P.h.n() * kLatent * 4) + 3 * Sb + 1024;
 }
 constexpr size_t kActBudget = size_t(6) << 30;  // activation workspace cap per engine
-int default_chunk(const snacb_engine* e) { return e->cfg.chunk_items > 0 ? e->cfg.chunk_items : 1024; }
+int default_chunk(const snacb_engine* e) { return e->cfg.chunk_items > 0 ? e->cfg.chunk_items : (e->cfg.precision == SNACB_PREC_FP16X3 ? 256 : 1024); }
 int default_lanes(const snacb_engine* e) { return e->cfg.precision == SNACB_PREC_FP16 ? std::max(1, std::min(e->cfg.lanes, 8)) : 1; }
 size_t act_bytes(const snacb_engine* e, const Plan& P, int count) {
   const size_t per = per_item_bytes(e, P);
@@ -570,7 +674,7 @@ size_t act_bytes(const snacb_engine* e, const Plan& P, int count) {
 
 int run_group(snacb_engine* e, const Plan& P, const Item* d_items, int n_total, int out_len, Rng tail_out,
               const int32_t* c0, const int32_t* c1, const int32_t* c2, int pitch0, const NoiseCfg& nz,
-              const int32_t* d_status, float* wav, int16_t* pcm, char* ws_free, size_t ws_avail, cudaStream_t st) {
+              int32_t* d_status, float* wav, int16_t* pcm, char* ws_free, size_t ws_avail, cudaStream_t st) {
   if (e->cfg.precision == SNACB_PREC_FP16) {
     const size_t per = per_item_bytes(e, P);
     int chunk = std::min(default_chunk(e), std::max(1, n_total));
@@ -581,6 +685,8 @@ int run_group(snacb_engine* e, const Plan& P, const Item* d_items, int n_total, 
     return run_group_tc(e, P, d_items, n_total, out_len, tail_out, c0, c1, c2, pitch0, nz, d_status, wav, pcm, ws_free,
                         ws_avail, chunk, lanes, st);
   }
+  if (e->cfg.precision == SNACB_PREC_FP16X3)
+    return run_group_x3(e, P, d_items, n_total, out_len, tail_out, c0, c1, c2, pitch0, nz, d_status, wav, pcm, ws_free, ws_avail, st);
   return run_group_f32(e, P, d_items, n_total, out_len, tail_out, c0, c1, c2, pitch0, nz, d_status, wav, pcm, ws_free,
                        ws_avail, st);
 }
@@ -618,7 +724,7 @@ int snacb_create(snacb_engine** out, const snacb_config* cfg) {
   if (prop.major != 10)
     return fail(nullptr, SNACB_ECUDA, "snacb_create: device %d is sm_%d%d; this library is built for sm_100a only",
                 cfg->device, prop.major, prop.minor);
-  if (cfg->precision != SNACB_PREC_FP32 && cfg->precision != SNACB_PREC_FP16)
+  if (cfg->precision != SNACB_PREC_FP32 && cfg->precision != SNACB_PREC_FP16 && cfg->precision != SNACB_PREC_FP16X3)
     return fail(nullptr, SNACB_EINVAL, "snacb_create: unknown precision %d", cfg->precision);
   c = cudaSetDevice(cfg->device);
   if (c != cudaSuccess) return fail(nullptr, SNACB_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(c));
@@ -732,24 +838,29 @@ int snacb_load_weights(snacb_engine* e, const snacb_weights* w) {
 
   // fp16 operand copies for the tensor-core recipe
   if (e->harena) { CU(e, cudaFree(e->harena)); e->harena = nullptr; }
-  if (e->cfg.precision == SNACB_PREC_FP16) {
-    struct H { __half** dst; const float* src; size_t n; size_t off; };
+  if (is_tc(e)) {
+    const bool x3 = e->cfg.precision == SNACB_PREC_FP16X3;  // operands [N][nseg * 3K] = per tap [hi | lo | hi]
+    struct H { __half** dst; const float* src; int N, nseg, K; size_t off; };
     std::vector<H> hs;
     size_t hoff = 0;
-    auto hput = [&](__half** dst, const float* src, size_t n) { hs.push_back({dst, src, n, hoff}); hoff += (n + 127) & ~size_t(127); };
-    hput(&D.head_pw16, D.head_pw_w, (size_t)kDecDim * kLatent);
+    auto hput = [&](__half** dst, const float* src, int N, int nseg, int K) {
+      hs.push_back({dst, src, N, nseg, K, hoff});
+      hoff += ((size_t)N * nseg * K * (x3 ? 3 : 1) + 127) & ~size_t(127);
+    };
+    hput(&D.head_pw16, D.head_pw_w, kDecDim, 1, kLatent);
     int ci = kDecDim;
     for (int b = 0; b < 4; ++b) {
       const int co = ci / 2;
-      hput(&D.blk[b].ct16, D.blk[b].ct_w, (size_t)kRates[b] * co * 2 * ci);
-      hput(&D.blk[b].noise16, D.blk[b].noise_w, (size_t)co * co);
-      for (int r = 0; r < 3; ++r) hput(&D.blk[b].ru[r].pw16, D.blk[b].ru[r].pw_w, (size_t)co * co);
+      hput(&D.blk[b].ct16, D.blk[b].ct_w, kRates[b] * co, 2, ci);
+      hput(&D.blk[b].noise16, D.blk[b].noise_w, co, 1, co);
+      for (int r = 0; r < 3; ++r) hput(&D.blk[b].ru[r].pw16, D.blk[b].ru[r].pw_w, co, 1, co);
       ci = co;
     }
     CU(e, cudaMalloc((void**)&e->harena, hoff * sizeof(__half)));
     for (const H& h : hs) {
       *h.dst = e->harena + h.off;
-      launch_to_half(h.src, *h.dst, h.n, 0);
+      if (x3) launch_split_w(h.src, *h.dst, h.N, h.nseg, h.K, 0);
+      else launch_to_half(h.src, *h.dst, (size_t)h.N * h.nseg * h.K, 0);
     }
     CU(e, cudaGetLastError());
     CU(e, cudaDeviceSynchronize());

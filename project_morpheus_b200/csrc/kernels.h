@@ -76,8 +76,17 @@ struct TcGemmArgs {
   const float* R; Rng r_r; int ldr;            // EPI_RESID residual / EPI_NOISE carrier (fp32)
   NoiseSrc noise;
   int up;
+  // split-operand recipe (SNACB_PREC_FP16X3): A is [rows][2K] = [hi | lo] fp16 halves of the fp32 operand, W is
+  // [N][nseg * 3K] = per tap [W_hi | W_lo | W_hi]; the GEMM runs over the concatenated K and yields
+  // A_hi W_hi + A_hi W_lo + A_lo W_hi (the fp32 product to ~2^-22).  Forces the generic one-tile kernel.
+  int split = 0;
 };
 cudaError_t launch_gemm_tc(const GroupCtx& g, const TcGemmArgs& a);
+// fp32 [rows][C] (-> optional Snake) -> fp16 [rows][2C] = [hi | lo]: the split operand of the recipe above
+void launch_split16(const float* in, __half* out, size_t rows, int C, const float* alpha, const float* inv, cudaStream_t st,
+                    int64_t* launches);
+// weight [N][nseg * K] fp32 -> [N][nseg * 3K] fp16 = per segment [hi | lo | hi]
+void launch_split_w(const float* in, __half* out, int N, int nseg, int K, cudaStream_t st);
 int tc_tile_n(const TcGemmArgs& a);
 // ConvTranspose1d + NoiseBlock in one kernel (blocks whose Cout is 64 / 128)
 bool convt_noise_supported(int Cin, int Cout);
@@ -101,7 +110,7 @@ struct RuTcArgs {
   int prefetch_ahead;
   bool persistent;   // k_ru_p (persistent, warp-specialised, also C = 256) instead of k_ru_tc
   // non-null tail_w7: fuse the decoder tail (Snake = sn_alpha/sn_inv, conv k7 64->1, tanh, slice, int16 pack)
-  const float* tail_w7; const float* tail_b; Rng tail_out; const int32_t* status; float* wav; int16_t* pcm;
+  const float* tail_w7; const float* tail_b; Rng tail_out; int32_t* status; float* wav; int16_t* pcm;
 };
 bool ru_tc_supported(int C, bool persistent);
 cudaError_t launch_ru_tc(const GroupCtx& g, const RuTcArgs& a);
@@ -111,7 +120,7 @@ struct BlkTcArgs {
   const float* x; Rng in_r; int C, up;
   struct Ru { const float *w7, *dw_b, *a1, *i1, *a2, *i2, *pw_b, *pw_w; const __half* pw16; } ru[3];
   const float* sn_alpha; const float* sn_inv;  // Snake after the block (decoder tail)
-  const float* tail_w7; const float* tail_b; Rng tail_out; const int32_t* status; float* wav; int16_t* pcm;
+  const float* tail_w7; const float* tail_b; Rng tail_out; int32_t* status; float* wav; int16_t* pcm;
 };
 bool blk_tc_supported(int C, bool tail);
 cudaError_t launch_blk_tc(const GroupCtx& g, const BlkTcArgs& a);
@@ -128,7 +137,7 @@ struct TailArgs {
   const float* alpha; const float* inv;
   const float* w7;  // [7][64]
   const float* bias;  // [1]
-  const int32_t* status;  // per code_row; nullptr or skip rows whose status != 0
+  int32_t* status;  // per code_row; nullptr or skip rows whose status != 0; set to SNACB_WIN_NONFINITE by the kernel
   float* wav;   // nullable
   int16_t* pcm; // nullable
   bool fast;    // MUFU sin for the Snake (tensor-core recipe)

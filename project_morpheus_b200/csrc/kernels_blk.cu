@@ -45,7 +45,7 @@ struct BlkDev {
   const float* w7[3]; const float* dw_b[3]; const float* a1[3]; const float* i1[3]; const float* a2[3]; const float* i2[3];
   const float* pw_b[3];
   const float* sn_alpha; const float* sn_inv;  // Snake after the block (decoder tail / next block)
-  const float* tail_w7; const float* tail_b; const int32_t* status; float* wav; int16_t* pcm;
+  const float* tail_w7; const float* tail_b; int32_t* status; float* wav; int16_t* pcm;
 };
 
 template <int C> struct BlkSmem {
@@ -165,7 +165,7 @@ __device__ __forceinline__ void dw_phase(const BlkDev& a, int r, const float* sX
     const int first = LO + rho + k0 * DIL;  // tile row of the unit's first output
     const float* p0 = sX + (first - 3 * DIL) * PITCH + c;
     uint8_t* ap = sA + (c >> 3) * S_::kLbo + (c & 7) * 2 + first * 16;
-    auto sink = [&](int j, float2 v) { *reinterpret_cast<__half2*>(ap + j * (DIL * 16)) = __floats2half2_rn(v.x, v.y); };
+    auto sink = [&](int j, float2 v) { *reinterpret_cast<__half2*>(ap + j * (DIL * 16)) = f2h2_sat(v.x, v.y); };
     if (L == LMAX) fir_unit<PITCH, DIL, LMAX>(p0, W, sink);
     else fir_unit<PITCH, DIL, LMAX - 1>(p0, W, sink);
   }
@@ -440,8 +440,12 @@ __global__ void __launch_bounds__(kBlkThreads, 2) k_blk_tail(const __grid_consta
       const int t_abs = a.o_lo + oi + it.shift0 * a.up;
       if (lane < LT && o < kTO && oi < a.o_n && t_abs >= 0 && t_abs < t_hi &&
           !(a.status && a.status[it.code_row] != SNACB_WIN_OK)) {
-        const float y = tanhf(mine + tail_b);
+        float y = tanhf(mine + tail_b);
         const long long d = it.dst + oi;
+        if (!(fabsf(y) <= 1.0f)) {  // NaN: never emitted, the window is reported (SNACB_WIN_NONFINITE) instead
+          y = 0.0f;
+          if (a.status) a.status[it.code_row] = SNACB_WIN_NONFINITE;
+        }
         if (a.wav) a.wav[d] = y;
         if (a.pcm) a.pcm[d] = (int16_t)(y * 32767.0f);
       }

@@ -119,7 +119,7 @@ void launch_from_codes(const GroupCtx& g, const QuantW& q, const int32_t* c0, co
 // out[t][c] = post( b[c] + sum_k w[k][c] * pre(in[t + (k-3)*dil][c]) ); pre/post = Snake or identity.
 template <typename T> __device__ __forceinline__ void store_act(T* p, float v);
 template <> __device__ __forceinline__ void store_act<float>(float* p, float v) { *p = v; }
-template <> __device__ __forceinline__ void store_act<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+template <> __device__ __forceinline__ void store_act<__half>(__half* p, float v) { *p = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f)); }
 
 template <bool PRE, bool POST, typename OutT = float>
 __global__ void __launch_bounds__(256) k_dwconv(const Item* items, int base, int out_len, int T0, DwArgs a, OutT* outp) {
@@ -376,8 +376,12 @@ __global__ void __launch_bounds__(256) k_tail(const Item* items, int base, int o
   const int t_abs = t_rel + it.shift0 * 512;
   if (t_abs < 0 || t_abs >= T0 * 512) return;
   if (a.status && a.status[it.code_row] != SNACB_WIN_OK) return;
-  const float y = tanhf(((part[0][sx] + part[1][sx]) + (part[2][sx] + part[3][sx])) + a.bias[0]);
+  float y = tanhf(((part[0][sx] + part[1][sx]) + (part[2][sx] + part[3][sx])) + a.bias[0]);
   const long long d = it.dst + (t_rel - a.out_r.lo);
+  if (!(fabsf(y) <= 1.0f)) {  // NaN (an overflowed activation upstream): never emitted, the window is reported instead
+    y = 0.0f;
+    if (a.status) a.status[it.code_row] = SNACB_WIN_NONFINITE;
+  }
   if (a.wav) a.wav[d] = y;
   if (a.pcm) a.pcm[d] = (int16_t)(y * 32767.0f);
 }

@@ -165,6 +165,7 @@ struct TcDev {
   NoiseSrc noise;
   int up;
   int n_tiles;              // k_gemm_tc: N tiles per M tile (linear grid, N tile fastest)
+  int split;                // split-operand recipe: segment = tap * 3 + term, A columns [hi | lo]
 };
 
 template <int BN> struct TcSmem {
@@ -223,7 +224,12 @@ __global__ void __launch_bounds__(kTcThreads, 3) k_gemm_tc(const __grid_constant
         const uint32_t sa = smem_u32(smem + st * S::kStageBytes), sb = sa + BM * BK * 2;
         const int seg = kb / kb_per_seg, kk = (kb - seg * kb_per_seg) * BK;
         mbar_arrive_expect_tx(full, S::kStageBytes);
-        tma_load_2d(sa, &tmA, full, kk, m0 + (seg ? delta : 0));
+        if (a.split) {  // terms hi*hi, hi*lo, lo*hi of tap seg / 3: the operand's lo half sits K columns to the right
+          const int term = seg % 3, tap = seg / 3;
+          tma_load_2d(sa, &tmA, full, kk + (term == 2 ? a.K : 0), m0 + (tap ? delta : 0));
+        } else {
+          tma_load_2d(sa, &tmA, full, kk, m0 + (seg ? delta : 0));
+        }
         tma_load_2d(sb, &tmW, full, seg * a.K + kk, n0);
       }
     }
@@ -677,8 +683,8 @@ __global__ void __launch_bounds__(kTcThreads, (BN == 64) ? 3 : 2) k_convt_noise_
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + col + 4 * j));
-        const __half2 h0 = __floats2half2_rn(__uint_as_float(r[4 * j]) + b4.x, __uint_as_float(r[4 * j + 1]) + b4.y);
-        const __half2 h1 = __floats2half2_rn(__uint_as_float(r[4 * j + 2]) + b4.z, __uint_as_float(r[4 * j + 3]) + b4.w);
+        const __half2 h0 = f2h2_sat(__uint_as_float(r[4 * j]) + b4.x, __uint_as_float(r[4 * j + 1]) + b4.y);
+        const __half2 h1 = f2h2_sat(__uint_as_float(r[4 * j + 2]) + b4.z, __uint_as_float(r[4 * j + 3]) + b4.w);
         pk[2 * j] = *reinterpret_cast<const uint32_t*>(&h0);
         pk[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1);
       }
@@ -1191,7 +1197,7 @@ __global__ void __launch_bounds__(kCnpThreads, 1) k_convt_noise_p(const __grid_c
           const float4 b4 = *reinterpret_cast<const float4*>(sBias + col + 4 * j);
           const float2 lo = __fadd2_rn(make_float2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), make_float2(b4.x, b4.y));
           const float2 hi = __fadd2_rn(make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), make_float2(b4.z, b4.w));
-          const __half2 h0 = __floats2half2_rn(lo.x, lo.y), h1 = __floats2half2_rn(hi.x, hi.y);
+          const __half2 h0 = f2h2_sat(lo.x, lo.y), h1 = f2h2_sat(hi.x, hi.y);
           pk[2 * j] = *reinterpret_cast<const uint32_t*>(&h0);
           pk[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1);
         }
@@ -1387,13 +1393,13 @@ int tc_tile_n(const TcGemmArgs& a) {
 cudaError_t launch_gemm_tc(const GroupCtx& g, const TcGemmArgs& a) {
   const long long Mtot = (long long)g.n_items * a.a_rows;
   if (Mtot <= 0) return cudaSuccess;
-  const int nseg = (a.epi == EPI_CONVT) ? 2 : 1;
+  const int nseg = ((a.epi == EPI_CONVT) ? 2 : 1) * (a.split ? 3 : 1);
   const int bn = tc_tile_n(a);
-  if (a.K % BK || a.N % bn || (a.epi == EPI_CONVT && a.Cout % bn)) return cudaErrorInvalidValue;
+  if (a.K % BK || a.N % bn || (a.epi == EPI_CONVT && a.Cout % bn) || (a.split && a.out16)) return cudaErrorInvalidValue;
   CUtensorMap ma, mw;
-  if (!get_tmap(a.A, Mtot, a.K, BM, &ma) || !get_tmap(a.W, a.N, nseg * a.K, bn, &mw)) return cudaErrorNotSupported;
+  if (!get_tmap(a.A, Mtot, a.split ? 2 * a.K : a.K, BM, &ma) || !get_tmap(a.W, a.N, nseg * a.K, bn, &mw)) return cudaErrorNotSupported;
   // wide square 1x1 layers (blocks 0 / 1): persistent weight-stationary kernel
-  const bool ws = !g_no_ws && (a.epi == EPI_RESID || a.epi == EPI_NOISE) && a.N == a.ldo && a.N == a.K && (a.K == 256 || a.K == 512) &&
+  const bool ws = !a.split && !g_no_ws && (a.epi == EPI_RESID || a.epi == EPI_NOISE) && a.N == a.ldo && a.N == a.K && (a.K == 256 || a.K == 512) &&
                   Mtot >= 4 * BM * (long long)(sm_count() / (a.N / 128));
   TcDev d{};
   d.items = g.items; d.base = g.base; d.out_len = g.out_len; d.T0 = g.T0; d.n_items = g.n_items;
@@ -1401,7 +1407,7 @@ cudaError_t launch_gemm_tc(const GroupCtx& g, const TcGemmArgs& a) {
   d.K = a.K; d.nseg = nseg; d.a_rows = a.a_rows; d.a_lo = a.a_lo; d.s = a.s; d.p = a.p; d.Cout = a.Cout;
   d.bias = a.bias; d.out32 = a.out32; d.out16 = a.out16; d.o_lo = a.o_r.lo; d.o_rows = a.o_r.n(); d.ldo = a.ldo;
   d.sn_alpha = a.sn_alpha; d.sn_inv = a.sn_inv; d.R = a.R; d.r_lo = a.r_r.lo; d.r_rows = a.r_r.n(); d.ldr = a.ldr;
-  d.noise = a.noise; d.up = a.up;
+  d.noise = a.noise; d.up = a.up; d.split = a.split;
   if (ws) {
     const int n_slices = a.N / 128;
     cudaError_t e = (a.epi == EPI_RESID) ? launch_ws_e<EPI_RESID>(ma, mw, d, n_slices, g.stream)
@@ -1409,7 +1415,7 @@ cudaError_t launch_gemm_tc(const GroupCtx& g, const TcGemmArgs& a) {
     ++*g.launches;
     return e;
   }
-  if (g_convt_p && !(g.flags & SNACB_FLAG_NO_PERSISTENT_CONVT) && a.epi == EPI_CONVT && a.Cout % 256 == 0 && !a.sn_alpha) {
+  if (!a.split && g_convt_p && !(g.flags & SNACB_FLAG_NO_PERSISTENT_CONVT) && a.epi == EPI_CONVT && a.Cout % 256 == 0 && !a.sn_alpha) {
     // wide transposed convs: persistent kernel with 128 x 256 tiles (87 FLOP per byte of L2 -> SM operand traffic
     // instead of 65 at 128 x 128, which caps those layers near 770 TFLOP/s)
     const int n_tiles = a.N / 256, m_tiles = (int)((Mtot + BM - 1) / BM);
@@ -1467,7 +1473,7 @@ __global__ void __launch_bounds__(256) k_dw_tc(const Item* items, int base, int 
     if (orow < out_rows) {
       const int t_abs = t_abs0 + j * DIL;
       if (t_abs < 0 || t_abs >= t_hi) v = make_float2(0.f, 0.f);
-      *reinterpret_cast<__half2*>(o + (size_t)orow * C) = __floats2half2_rn(v.x, v.y);
+      *reinterpret_cast<__half2*>(o + (size_t)orow * C) = f2h2_sat(v.x, v.y);
     }
   });
 }
@@ -1518,7 +1524,7 @@ struct RuDev {
   // fused decoder tail (TAIL variant, last ResidualUnit of block 3): Snake(64) -> conv k7 64->1 -> tanh -> pack
   int tile_stride, row_off;            // tile t covers out rows [t*tile_stride + row_off, +128)
   int tail_lo, tail_n;                 // emitted samples: relative times [tail_lo, tail_lo + tail_n)
-  const float* tail_w7; const float* tail_b; const int32_t* status; float* wav; int16_t* pcm;
+  const float* tail_w7; const float* tail_b; int32_t* status; float* wav; int16_t* pcm;
 };
 
 constexpr int kTailPitch = 80;  // floats per row of the Snake'd output tile (conflict-free float4 rows)
@@ -1608,7 +1614,7 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
         row_mask<DIL>(in_first, a.in_rows, L + 6, mlo, mhi);
         dw_unit<C, DIL, L>(xin + (long long)in_first * C + c, mlo, mhi, W, [&](int j, float2 v) {
           const int trow = first + j * DIL;  // < 128 by construction of the unit length
-          *reinterpret_cast<__half2*>(a_kb + trow * 128 + (((chunk ^ trow) & 7) << 4)) = __floats2half2_rn(v.x, v.y);
+          *reinterpret_cast<__half2*>(a_kb + trow * 128 + (((chunk ^ trow) & 7) << 4)) = f2h2_sat(v.x, v.y);
         });
       });
     }
@@ -1742,8 +1748,12 @@ __global__ void __launch_bounds__(kRuThreads, (C == 64) ? 3 : 2) k_ru_tc(const _
           const int oi = (int)blockIdx.x * a.tile_stride + o;  // emitted sample index inside [0, tail_n)
           const int t_abs = a.tail_lo + oi + it.shift0 * 512;
           if (oi < a.tail_n && t_abs >= 0 && t_abs < a.T0 * 512 && !(a.status && a.status[it.code_row] != SNACB_WIN_OK)) {
-            const float y = tanhf(((part[sx] + part[64 + sx]) + (part[128 + sx] + part[192 + sx])) + a.tail_b[0]);
+            float y = tanhf(((part[sx] + part[64 + sx]) + (part[128 + sx] + part[192 + sx])) + a.tail_b[0]);
             const long long d = it.dst + oi;
+            if (!(fabsf(y) <= 1.0f)) {
+              y = 0.0f;
+              if (a.status) a.status[it.code_row] = SNACB_WIN_NONFINITE;
+            }
             if (a.wav) a.wav[d] = y;
             if (a.pcm) a.pcm[d] = (int16_t)(y * 32767.0f);
           }
@@ -1838,7 +1848,7 @@ __global__ void __launch_bounds__(kRuThreads, 3) k_ru_x(const __grid_constant__ 
       unit_len_dispatch<DIL>(u, [&](auto len) {
         dw_unit_smem<C, DIL, decltype(len)::value>(sX + first * C + c, W, [&](int j, float2 v) {
           const int trow = first + j * DIL;  // < 128 by construction of the unit length
-          *reinterpret_cast<__half2*>(a_kb + trow * 128 + (((chunk ^ trow) & 7) << 4)) = __floats2half2_rn(v.x, v.y);
+          *reinterpret_cast<__half2*>(a_kb + trow * 128 + (((chunk ^ trow) & 7) << 4)) = f2h2_sat(v.x, v.y);
         });
       });
     }
@@ -1985,7 +1995,7 @@ k_dw_x(const __grid_constant__ CUtensorMap tmX, const Item* items, int base, int
       if (row0 + trow < out_rows) {
         const int t_abs = t_abs0 + trow;
         if (t_abs < 0 || t_abs >= t_hi) v = make_float2(0.f, 0.f);
-        *reinterpret_cast<__half2*>(o + (size_t)trow * a.C) = __floats2half2_rn(v.x, v.y);
+        *reinterpret_cast<__half2*>(o + (size_t)trow * a.C) = f2h2_sat(v.x, v.y);
       }
     });
   });
@@ -2091,7 +2101,7 @@ __global__ void __launch_bounds__(RupCfg<C>::kThreads, 1) k_ru_p(const __grid_co
         dw_unit<C, DIL, 16>(xin + (long long)in_first * C + c, mlo, mhi, W, [&](int j, float2 v) {
           const int trow = first + j * DIL;
           if (trow < BM)
-            *reinterpret_cast<__half2*>(a_kb + trow * 128 + (((chunk ^ trow) & 7) << 4)) = __floats2half2_rn(v.x, v.y);
+            *reinterpret_cast<__half2*>(a_kb + trow * 128 + (((chunk ^ trow) & 7) << 4)) = f2h2_sat(v.x, v.y);
         });
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -2428,7 +2438,7 @@ __global__ void __launch_bounds__(256) k_codes_head(const Item* items, int base,
       }
       acc += dw_b[c];
     }
-    out[((size_t)i * hr + j) * kLatent + c] = __float2half_rn(acc);
+    out[((size_t)i * hr + j) * kLatent + c] = __low2half(f2h2_sat(acc, 0.0f));
   }
 }
 
@@ -2454,11 +2464,66 @@ namespace {
 // fp32 -> fp16 weight conversion (load time)
 __global__ void k_to_half(const float* __restrict__ in, __half* __restrict__ out, size_t n) {
   const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-  if (i < n) out[i] = __float2half_rn(in[i]);
+  if (i < n) out[i] = __low2half(f2h2_sat(in[i], 0.0f));  // weights beyond fp16 range clamp, never inf
 }
 }  // namespace
 void launch_to_half(const float* in, __half* out, size_t n, cudaStream_t st) {
   if (n) k_to_half<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
+}
+
+namespace {
+// x -> (hi, lo) with hi = fp16(x) (saturating), lo = fp16(x - hi): hi + lo carries ~22 bits of x
+__device__ __forceinline__ void split2(float a, float b, __half2& hi, __half2& lo) {
+  hi = f2h2_sat(a, b);
+  const float2 h = __half22float2(hi);
+  lo = f2h2_sat(a - h.x, b - h.y);
+}
+__global__ void __launch_bounds__(256) k_split16(const float* __restrict__ in, __half* __restrict__ out, size_t rows, int C,
+                                                 const float* __restrict__ alpha, const float* __restrict__ inv) {
+  const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;  // one float4 of one row
+  const int c4 = C / 4;
+  if (idx >= rows * c4) return;
+  const size_t row = idx / c4;
+  const int c = (int)(idx - row * c4) * 4;
+  float4 v = *reinterpret_cast<const float4*>(in + row * C + c);
+  if (alpha) {  // exact Snake (sinf), like the fp32 recipe
+    const float4 al = *reinterpret_cast<const float4*>(alpha + c), iv = *reinterpret_cast<const float4*>(inv + c);
+    v.x = snake_exact(v.x, al.x, iv.x); v.y = snake_exact(v.y, al.y, iv.y);
+    v.z = snake_exact(v.z, al.z, iv.z); v.w = snake_exact(v.w, al.w, iv.w);
+  }
+  __half2 h0, l0, h1, l1;
+  split2(v.x, v.y, h0, l0);
+  split2(v.z, v.w, h1, l1);
+  __half* o = out + row * 2 * C + c;
+  uint2 ph, pl;
+  ph.x = *reinterpret_cast<uint32_t*>(&h0); ph.y = *reinterpret_cast<uint32_t*>(&h1);
+  pl.x = *reinterpret_cast<uint32_t*>(&l0); pl.y = *reinterpret_cast<uint32_t*>(&l1);
+  *reinterpret_cast<uint2*>(o) = ph;
+  *reinterpret_cast<uint2*>(o + C) = pl;
+}
+__global__ void __launch_bounds__(256) k_split_w(const float* __restrict__ in, __half* __restrict__ out, int N, int nseg, int K) {
+  const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
+  const size_t tot = (size_t)N * nseg * K;
+  if (idx >= tot) return;
+  const size_t n = idx / ((size_t)nseg * K);
+  const int rem = (int)(idx - n * nseg * K), seg = rem / K, k = rem - seg * K;
+  const float x = in[idx];
+  const __half hi = __low2half(f2h2_sat(x, 0.0f));
+  const __half lo = __low2half(f2h2_sat(x - __half2float(hi), 0.0f));
+  __half* o = out + (n * nseg + seg) * 3 * (size_t)K;
+  o[k] = hi; o[K + k] = lo; o[2 * K + k] = hi;
+}
+}  // namespace
+void launch_split16(const float* in, __half* out, size_t rows, int C, const float* alpha, const float* inv, cudaStream_t st,
+                    int64_t* launches) {
+  const size_t n = rows * (C / 4);
+  if (!n) return;
+  k_split16<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, rows, C, alpha, inv);
+  ++*launches;
+}
+void launch_split_w(const float* in, __half* out, int N, int nseg, int K, cudaStream_t st) {
+  const size_t n = (size_t)N * nseg * K;
+  if (n) k_split_w<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, N, nseg, K);
 }
 
 }  // namespace snacb

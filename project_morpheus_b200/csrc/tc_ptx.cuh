@@ -162,8 +162,15 @@ __device__ __forceinline__ void epi_transpose16(float* stg, int lane, const uint
   }
   __syncwarp();
 }
+// fp32 pair -> fp16 pair, round to nearest, SATURATING to +-65504 (F2FP.SATFINITE, one instruction like the plain
+// conversion): an activation that outgrows fp16 on a trained checkpoint clamps instead of turning into inf -> NaN.
+__device__ __forceinline__ __half2 f2h2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return *reinterpret_cast<__half2*>(&r);
+}
 __device__ __forceinline__ void store_half4(__half* p, float4 v) {
-  const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  const __half2 h0 = f2h2_sat(v.x, v.y), h1 = f2h2_sat(v.z, v.w);
   uint2 pk;
   pk.x = *reinterpret_cast<const uint32_t*>(&h0);
   pk.y = *reinterpret_cast<const uint32_t*>(&h1);

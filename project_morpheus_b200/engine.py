@@ -38,7 +38,7 @@ class SnacEngine:
         self.device = int(device)
         self.torch_device = torch.device("cuda", self.device)
         self.precision = precision
-        prec = {"fp32": _lib.PREC_FP32, "fp16": _lib.PREC_FP16}[precision]
+        prec = {"fp32": _lib.PREC_FP32, "fp16": _lib.PREC_FP16, "fp16x3": _lib.PREC_FP16X3}[precision]
         cfg = _lib.Config(abi_version=_lib.ABI_VERSION, device=self.device, precision=prec,
                           chunk_items=int(chunk_items), trim=1 if trim else 0,
                           flags=(0 if fuse_ru else _lib.FLAG_NO_RU_FUSION) | (_lib.FLAG_PERSISTENT_RU if persistent_ru else 0)

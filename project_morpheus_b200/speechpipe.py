@@ -84,6 +84,9 @@ def _finish(pcm_row: np.ndarray, status: int) -> Optional[bytes]:
         return b""
     if status == _lib.WIN_CODE4096:
         raise IndexError("index out of range in self")
+    if status == _lib.WIN_NONFINITE:
+        log.error("SNAC decode produced non-finite samples (fp16 operand range exceeded?); window withheld - "
+                  "set SNACB_PRECISION=fp16x3 or fp32 for this checkpoint")
     return None
 
 

@@ -40,6 +40,7 @@ def test_header_constants_match_the_ctypes_binding():
                  "FLAG_NO_PERSISTENT_CONVT", "FLAG_FUSE_RU256", "FLAG_NO_BLOCK_FUSION"):
         assert flag in defs and getattr(_lib, flag) == defs[flag]
     assert checked >= 10
+    assert _lib.PREC_FP16X3 == defs["PREC_FP16X3"] and _lib.WIN_NONFINITE == defs["WIN_NONFINITE"]
 
 
 def test_plan_matches_dependency_cone(ensure_lib):

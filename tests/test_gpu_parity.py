@@ -845,3 +845,71 @@ def test_soak_varying_shapes_graph_cache_and_regrowth(state_dict_w1):
     finally:
         eng.close()
         ref.close()
+
+
+# ------------------------------------------------------------------------------------ precision safety net
+def test_fp16x3_split_recipe_meets_the_lsb_criterion(engines, oracle_w1):
+    """SNACB_PREC_FP16X3: two-term fp16 splits of both GEMM operands, three tcgen05 products per k-block (SURVEY App. E:
+    117 dB, <= 1 LSB in emulation).  north_star's strict branch: at most 2 LSB in int16 PCM - which the single-pass fp16
+    recipe does not meet (10 LSB)."""
+    eng = engines("fp16x3")
+    for frames, n in ((4, 12), (7, 5)):
+        tok = windows_tokens(n, frames, base_stream=2300 + frames)
+        noise = snac_ref.make_noise(n, frames, seed=31)
+        ref = oracle_decode_windows(oracle_w1, tok, noise)[:, 2048:4096]
+        pcm, st = eng.decode_windows(tok, noise=snac_ref.pack_noise(noise))
+        assert (st == _lib.WIN_OK).all()
+        diff = np.abs(pcm.astype(np.int32) - pcm_trunc(ref).astype(np.int32))
+        assert diff.max() <= 2, f"fp16x3: {diff.max()} LSB"
+        _check_wave(ref, pcm.astype(np.float32) / 32767.0, 6.2e-5, 78.0)  # the int16 grid itself caps this at ~79.4 dB
+    # one-shot decode path (no slice) as well
+    tok = windows_tokens(3, 4, base_stream=77)
+    noise = snac_ref.make_noise(3, 4, seed=1)
+    ref = oracle_decode_windows(oracle_w1, tok, noise)
+    lv = [sp.split_levels(row.tolist()) for row in tok]
+    codes = [torch.from_numpy(np.stack([l[k] for l in lv])) for k in range(3)]
+    wav, _ = eng.decode_codes(codes, noise=snac_ref.pack_noise(noise), want_pcm=True)
+    _check_wave(ref, wav[:, 0].cpu().numpy(), 2e-5, 95.0)
+
+
+def _scaled_state_dict(sd, gain):
+    """W1 weights with the decoder head's 1x1 conv scaled up: activations `gain` x larger from block 0 on."""
+    out = {k: v.clone() for k, v in sd.items()}
+    hits = 0
+    for k in out:
+        if k.startswith("decoder.model.1.") and ("weight_g" in k or k.endswith("original0") or k.endswith(".bias")):
+            out[k] = out[k] * gain
+            hits += 1
+    assert hits >= 2, [k for k in out if k.startswith("decoder.model.1.")]
+    return out
+
+
+def test_fp16_overflow_guard_and_fallback_on_scaled_weights(state_dict_w1):
+    """A checkpoint whose activations outgrow single-pass fp16 (head scaled so |x| reaches ~1e5 and |alpha x| >> 5):
+    the fp16 recipe must never emit NaN PCM silently - operands saturate (F2FP.SATFINITE) and a window that still ends up
+    non-finite is reported as SNACB_WIN_NONFINITE with its PCM withheld; fp16x3 keeps tracking the fp32 recipe far
+    better than single-pass fp16 does."""
+    from project_morpheus_b200.engine import SnacEngine
+    tok = windows_tokens(6, 4, base_stream=4242)
+    res = {}
+    for gain in (40.0, 4000.0):
+        sd = _scaled_state_dict(state_dict_w1, gain)
+        outs = {}
+        for prec in ("fp32", "fp16", "fp16x3"):
+            eng = SnacEngine(sd, device=0, precision=prec)
+            pcm, st = eng.decode_windows(tok, noise="off")
+            outs[prec] = (pcm.astype(np.float64), st.copy())
+            eng.close()
+        ref, st32 = outs["fp32"]
+        for prec in ("fp16", "fp16x3"):
+            pcm, st = outs[prec]
+            assert np.isin(st, (_lib.WIN_OK, _lib.WIN_NONFINITE)).all()
+            ok = st == _lib.WIN_OK
+            assert np.isfinite(pcm).all()
+            res[(gain, prec)] = float(np.abs(pcm[ok] - ref[ok]).mean()) if ok.any() else None
+        assert (st32 == _lib.WIN_OK).all()
+    # moderate gain: the split recipe stays close to fp32 (mean error in LSB) while single-pass fp16 drifts
+    assert res[(40.0, "fp16x3")] is not None and res[(40.0, "fp16x3")] <= 8.0, res
+    if res[(40.0, "fp16")] is not None:
+        assert res[(40.0, "fp16x3")] <= res[(40.0, "fp16")], res
+    print("overflow guard:", res)
