@@ -658,6 +658,28 @@ def run_ours(args) -> None:
             except Exception as exc:  # noqa: BLE001
                 extra["precision_fp16x3"] = {"error": repr(exc)[:300]}
 
+        # Next row N4: the encode direction (voice prompts / data preparation): audio -> 3 code levels, fp32 CUDA-core kernels
+        if not args.no_cpu_baseline:
+            try:
+                sd_full = dict(weights.random_state_dict(0, "w1"))
+                sd_full.update(weights.random_encoder_state_dict(0, "w1"))
+                eng_e = SnacEngine(sd_full, device=local, precision="fp32")
+                secs, Be = 10.0, 8
+                aud = (0.3 * torch.randn((Be, 1, int(secs * SAMPLE_RATE)), generator=torch.Generator().manual_seed(3))).to(dev)
+                eng_e.encode(aud)
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    codes_e = eng_e.encode(aud)
+                torch.cuda.synchronize(dev)
+                dt_e = (time.perf_counter() - t0) / 3
+                extra["n4_encoder"] = {"batch": Be, "seconds_per_item": secs, "ms": 1e3 * dt_e, "audio_s_per_s": Be * secs / dt_e,
+                                       "frames": int(codes_e[0].shape[1]),
+                                       "note": "SNAC.encode (encoder + residual VQ) through snacb_encode, exact fp32 kernels"}
+                eng_e.close()
+            except Exception as exc:  # noqa: BLE001
+                extra["n4_encoder"] = {"error": repr(exc)[:300]}
+
         # BASELINE config 3 (long_read): one-shot decode of 720-frame utterances, time-tiled; reduced batch by default
         if args.long_read_batch > 0:
             Fl, Bl = 720, args.long_read_batch

@@ -247,6 +247,35 @@ int snacb_decode_windows_host_wait(snacb_engine* e, int32_t ticket);
 
 /* ---- N2: token ingress for many streams (host only, no GPU) ---------------------------------- */
 
+/* ---- SNAC encoder: audio -> the 3 code levels `snacb_decode_codes` consumes.  Replaces the third-party
+ * `snac` package's SNAC.encode (referenced from Orpheus-TTS/README.md:111-120 data preparation); fp32 CUDA-core kernels.
+ * All tensors folded fp32 host arrays in PyTorch layouts: in_w [48][7] (Conv1d 1->48), block b (C = 48 * 2^b, stride
+ * 2/4/8/8): ru[3] as in the decoder, alpha [C], down_w [2C][C][2s], down_b [2C]; out_dw_w [768][7]; inproj_w [8][768]. */
+typedef struct snacb_enc_block_weights {
+  snacb_ru_weights ru[3];
+  const float* alpha;
+  const float* down_w;
+  const float* down_b;
+} snacb_enc_block_weights;
+
+typedef struct snacb_encoder_weights {
+  const float* in_w;
+  const float* in_b;
+  snacb_enc_block_weights block[4];
+  const float* out_dw_w;
+  const float* out_dw_b;
+  const float* inproj_w[3];
+  const float* inproj_b[3];
+} snacb_encoder_weights;
+
+/* Needs snacb_load_weights first (codebooks and out-projections are shared with the decode path). */
+int snacb_load_encoder_weights(snacb_engine* e, const snacb_encoder_weights* w);
+/* d_audio [batch][n_samples] float32 on the device, n_samples a multiple of 2048 (caller pads with zeros like
+ * SNAC.preprocess); d_c0 [batch][n/2048], d_c1 [batch][n/1024], d_c2 [batch][n/512] int32; d_latent (nullable)
+ * [batch][n/512][768] receives the encoder output z before quantisation. */
+int snacb_encode(snacb_engine* e, const float* d_audio, int32_t batch, int32_t n_samples, int32_t* d_c0, int32_t* d_c1,
+                 int32_t* d_c2, float* d_latent, void* stream);
+
 /* Replaces, batched over streams, the per-token Python of speechpipe.py:146-189 (turn_token_into_id: the last
  * "<custom_token_N>" of the stripped string -> N - 10 - 4096 * (accepted_count % 7), None on any parse failure)
  * and the window control flow of tokens_decoder, speechpipe.py:191-293 (ids <= 0 dropped without advancing the

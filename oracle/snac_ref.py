@@ -68,17 +68,17 @@ class _WNBase(nn.Module):
 
 
 class WNConv1d(_WNBase):
-    def __init__(self, cin, cout, kernel_size, padding=0, dilation=1, groups=1, bias=True):
+    def __init__(self, cin, cout, kernel_size, padding=0, dilation=1, groups=1, bias=True, stride=1):
         super().__init__()
         conv = nn.Conv1d(cin, cout, kernel_size, padding=padding, dilation=dilation, groups=groups, bias=bias)
         v = conv.weight.detach()
         self.weight_g = nn.Parameter(v.flatten(1).norm(dim=1).reshape(-1, 1, 1).clone())
         self.weight_v = nn.Parameter(v.clone())
         self.bias = nn.Parameter(conv.bias.detach().clone()) if bias else None
-        self.padding, self.dilation, self.groups = padding, dilation, groups
+        self.padding, self.dilation, self.groups, self.stride = padding, dilation, groups, stride
 
     def forward(self, x):
-        return F.conv1d(x, self._w(), self.bias, 1, self.padding, self.dilation, self.groups)
+        return F.conv1d(x, self._w(), self.bias, self.stride, self.padding, self.dilation, self.groups)
 
 
 class WNConvTranspose1d(_WNBase):
@@ -171,19 +171,78 @@ class Decoder(nn.Module):
         return self.model(z)
 
 
+class EncoderBlock(nn.Module):
+    """ResidualUnit d = 1, 3, 9 -> Snake -> strided WN Conv1d (k = 2s, stride s, pad ceil(s/2)); depthwise RUs."""
+
+    def __init__(self, cin, cout, stride):
+        super().__init__()
+        self.block = nn.Sequential(
+            ResidualUnit(cin, 1),
+            ResidualUnit(cin, 3),
+            ResidualUnit(cin, 9),
+            Snake1d(cin),
+            WNConv1d(cin, cout, 2 * stride, padding=math.ceil(stride / 2), stride=stride),
+        )
+
+    def forward(self, x):
+        return self.block(x)
+
+
+class Encoder(nn.Module):
+    """Published SNAC encoder (snac_24khz: d_model 48, strides [2,4,8,8], depthwise, no attention):
+    WN Conv1d 1->48 k7, 4 x EncoderBlock (channels double), WN depthwise Conv1d k7 on the 768 latent channels."""
+
+    def __init__(self, d_model, rates):
+        super().__init__()
+        layers: List[nn.Module] = [WNConv1d(1, d_model, 7, padding=3)]
+        for s in rates:
+            layers.append(EncoderBlock(d_model, 2 * d_model, s))
+            d_model *= 2
+        layers.append(WNConv1d(d_model, d_model, 7, padding=3, groups=d_model))
+        self.block = nn.Sequential(*layers)
+
+    def forward(self, x):
+        return self.block(x)
+
+
 class VectorQuantize(nn.Module):
     def __init__(self, latent, size, dim, stride):
         super().__init__()
-        self.in_proj = WNConv1d(latent, dim, 1)  # unused by decode; present for key parity
+        self.in_proj = WNConv1d(latent, dim, 1)  # encode only
         self.out_proj = WNConv1d(dim, latent, 1)
         self.codebook = nn.Embedding(size, dim)
         self.stride = stride
+
+    def encode(self, z):
+        """Published VectorQuantize.forward: avg_pool -> in_proj -> nearest codebook entry on L2-normalised vectors ->
+        out_proj -> repeat_interleave.  Returns (z_q [B,768,T], indices [B,T/stride])."""
+        if self.stride > 1:
+            z = F.avg_pool1d(z, self.stride, self.stride)
+        z_e = self.in_proj(z)
+        B, D, T = z_e.shape
+        enc = F.normalize(z_e.transpose(1, 2).reshape(B * T, D))
+        cb = F.normalize(self.codebook.weight)
+        dist = enc.pow(2).sum(1, keepdim=True) - 2 * enc @ cb.t() + cb.pow(2).sum(1, keepdim=True).t()
+        idx = (-dist).max(1)[1].reshape(B, T)
+        z_q = self.out_proj(F.embedding(idx, self.codebook.weight).transpose(1, 2))
+        if self.stride > 1:
+            z_q = z_q.repeat_interleave(self.stride, dim=-1)
+        return z_q, idx
 
 
 class ResidualVectorQuantize(nn.Module):
     def __init__(self, latent, size, dim, strides):
         super().__init__()
         self.quantizers = nn.ModuleList(VectorQuantize(latent, size, dim, s) for s in strides)
+
+    def encode(self, z):
+        """Published ResidualVectorQuantize.forward: each level quantises what the previous ones left."""
+        residual, codes = z, []
+        for q in self.quantizers:
+            z_q, idx = q.encode(residual)
+            residual = residual - z_q
+            codes.append(idx)
+        return codes
 
     def from_codes(self, codes: Sequence[torch.Tensor]) -> torch.Tensor:
         z = 0.0
@@ -216,7 +275,8 @@ PRETRAINED: Dict[str, Dict[str, torch.Tensor]] = {}
 
 
 class SNAC(nn.Module):
-    """Decode-side restatement (the encoder is not on the reference's path)."""
+    """Decode-side restatement; the encoder (not on the reference's serving path) is attached when the
+    state dict carries ``encoder.*`` keys."""
 
     def __init__(self, **cfg):
         super().__init__()
@@ -229,12 +289,15 @@ class SNAC(nn.Module):
         self.vq_strides = list(c["vq_strides"])
         self.quantizer = ResidualVectorQuantize(latent, c["codebook_size"], c["codebook_dim"], c["vq_strides"])
         self.decoder = Decoder(latent, c["decoder_dim"], c["decoder_rates"])
+        self.encoder: Optional[Encoder] = None  # built by from_state_dict when the dict carries encoder.* keys
 
     # -- construction -------------------------------------------------------
     @classmethod
     def from_state_dict(cls, sd: Dict[str, torch.Tensor], **cfg) -> "SNAC":
         m = cls(**cfg)
-        sd = {k: v for k, v in normalise_keys(sd).items() if not k.startswith("encoder.")}
+        sd = normalise_keys(sd)
+        if any(k.startswith("encoder.") for k in sd):
+            m.encoder = Encoder(m.config["encoder_dim"], m.config["encoder_rates"])
         missing, unexpected = m.load_state_dict(sd, strict=False)
         missing = [k for k in missing if ".in_proj." not in k]
         if missing or unexpected:
@@ -275,6 +338,21 @@ class SNAC(nn.Module):
     # -- the path -----------------------------------------------------------
     def decode(self, codes: Sequence[torch.Tensor]) -> torch.Tensor:
         return self.decoder(self.quantizer.from_codes(codes))
+
+    # -- N4: the encode direction (published SNAC.preprocess / SNAC.encode) ----
+    def preprocess(self, audio: torch.Tensor) -> torch.Tensor:
+        pad_to = self.hop_length * math.lcm(self.vq_strides[0], self.config["attn_window_size"] or 1)
+        length = audio.shape[-1]
+        return F.pad(audio, (0, math.ceil(length / pad_to) * pad_to - length))
+
+    def encode_latent(self, audio: torch.Tensor) -> torch.Tensor:
+        if self.encoder is None:
+            raise RuntimeError("this oracle model was built without encoder weights")
+        return self.encoder(self.preprocess(audio))
+
+    def encode(self, audio: torch.Tensor) -> List[torch.Tensor]:
+        """audio [B,1,T] -> codes [B,T'/4], [B,T'/2], [B,T'] with T' = padded length / 512."""
+        return self.quantizer.encode(self.encode_latent(audio))
 
 
 def noise_lengths(frames: int, rates=(8, 8, 4, 2)) -> List[int]:

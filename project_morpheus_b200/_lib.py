@@ -48,6 +48,15 @@ class BlockWeights(C.Structure):
     _fields_ = [("alpha", _f32p), ("convt_w", _f32p), ("convt_b", _f32p), ("noise_w", _f32p), ("ru", RuWeights * 3)]
 
 
+class EncBlockWeights(C.Structure):
+    _fields_ = [("ru", RuWeights * 3), ("alpha", _f32p), ("down_w", _f32p), ("down_b", _f32p)]
+
+
+class EncoderWeights(C.Structure):
+    _fields_ = [("in_w", _f32p), ("in_b", _f32p), ("block", EncBlockWeights * 4), ("out_dw_w", _f32p), ("out_dw_b", _f32p),
+                ("inproj_w", _f32p * 3), ("inproj_b", _f32p * 3)]
+
+
 class Weights(C.Structure):
     _fields_ = [
         ("codebook", _f32p * 3),
@@ -76,6 +85,8 @@ SIGNATURES = {
     "snacb_destroy": (None, [_vp]),
     "snacb_last_error": (C.c_char_p, [_vp]),
     "snacb_load_weights": (_i32, [_vp, C.POINTER(Weights)]),
+    "snacb_load_encoder_weights": (_i32, [_vp, C.POINTER(EncoderWeights)]),
+    "snacb_encode": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "snacb_workspace_bytes": (_sz, [_vp]),
     "snacb_launch_count": (_i64, [_vp]),
     "snacb_graph_launch_count": (_i64, [_vp]),

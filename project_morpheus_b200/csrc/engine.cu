@@ -34,6 +34,20 @@ struct DevWeights {
   float *tail_alpha, *tail_inv, *tail_w /*[7][64]*/, *tail_b;
 };
 
+struct EncBlockDev {
+  RuDev ru[3];
+  float *alpha, *inv, *down_w /*[2C][2s*C], k-major*/, *down_b;
+};
+struct EncDev {
+  float *in_w, *in_b;
+  EncBlockDev blk[4];
+  float *out_dw_w /*[7][768]*/, *out_dw_b;
+  float *inproj_w[3], *inproj_b[3], *cb_norm[3];
+};
+constexpr int kEncRates[4] = {2, 4, 8, 8};
+constexpr int kEncDim = 48;
+constexpr int kVqStrides[3] = {4, 2, 1};
+
 enum KClass { KC_DEINT = 0, KC_CODES, KC_DW, KC_SNAKE, KC_GEMM1, KC_CONVT, KC_TAIL, KC_RU, KC_COUNT };
 const char* const kClassName[KC_COUNT] = {"deinterleave", "from_codes", "dwconv_snake", "snake", "gemm_1x1",
                                           "gemm_convt", "tail_pack", "block_ru_fused"};
@@ -62,6 +76,9 @@ struct snacb_engine {
   void* warena = nullptr;
   size_t warena_bytes = 0;
   __half* harena = nullptr;  // fp16 copies of the GEMM-shaped weights (tensor-core recipe)
+  EncDev enc{};
+  void* earena = nullptr;    // encoder weights (snacb_load_encoder_weights)
+  bool enc_loaded = false;
   char* ws = nullptr;
   size_t ws_bytes = 0;
   // pinned + device staging for the host-buffer API and the item tables
@@ -749,6 +766,7 @@ void snacb_destroy(snacb_engine* e) {
   cudaDeviceSynchronize();
   if (e->warena) cudaFree(e->warena);
   if (e->harena) cudaFree(e->harena);
+  if (e->earena) cudaFree(e->earena);
   if (e->ws) cudaFree(e->ws);
   if (e->dstage) cudaFree(e->dstage);
   for (auto& sl : e->pipe) {
@@ -867,6 +885,157 @@ int snacb_load_weights(snacb_engine* e, const snacb_weights* w) {
   }
   e->loaded = true;
   ++e->gen;
+  return SNACB_OK;
+}
+
+// ---------------------------------------------------------------------------------- encoder (N4)
+int snacb_load_encoder_weights(snacb_engine* e, const snacb_encoder_weights* w) {
+  if (!e || !w) return fail(e, SNACB_EINVAL, "snacb_load_encoder_weights: null argument");
+  if (!e->loaded) return fail(e, SNACB_ESTATE, "snacb_load_encoder_weights: load the decode-path weights first");
+  CU(e, cudaSetDevice(e->device));
+  if (!w->in_w || !w->in_b || !w->out_dw_w || !w->out_dw_b) return fail(e, SNACB_EINVAL, "snacb_load_encoder_weights: null tensor");
+  HostPack hp;
+  struct Fix { float** dst; size_t off; };
+  std::vector<Fix> fix;
+  EncDev& D = e->enc;
+  auto put = [&](float** dst, const float* src, size_t n) { fix.push_back({dst, hp.add(src, n)}); };
+  put(&D.in_w, w->in_w, (size_t)kEncDim * 7);
+  put(&D.in_b, w->in_b, kEncDim);
+  int C = kEncDim;
+  for (int b = 0; b < 4; ++b) {
+    const snacb_enc_block_weights& sb = w->block[b];
+    const int st = kEncRates[b], k = 2 * st;
+    if (!sb.alpha || !sb.down_w || !sb.down_b) return fail(e, SNACB_EINVAL, "snacb_load_encoder_weights: null block tensor");
+    for (int r = 0; r < 3; ++r) {
+      const snacb_ru_weights& u = sb.ru[r];
+      RuDev& R = D.blk[b].ru[r];
+      if (!u.alpha1 || !u.dw_w || !u.dw_b || !u.alpha2 || !u.pw_w || !u.pw_b) return fail(e, SNACB_EINVAL, "snacb_load_encoder_weights: null RU tensor");
+      put(&R.a1, u.alpha1, C);
+      fix.push_back({&R.i1, add_inv(hp, u.alpha1, C)});
+      fix.push_back({&R.dw_w, add_transposed(hp, u.dw_w, C, 7)});
+      put(&R.dw_b, u.dw_b, C);
+      put(&R.a2, u.alpha2, C);
+      fix.push_back({&R.i2, add_inv(hp, u.alpha2, C)});
+      put(&R.pw_w, u.pw_w, (size_t)C * C);
+      put(&R.pw_b, u.pw_b, C);
+    }
+    put(&D.blk[b].alpha, sb.alpha, C);
+    fix.push_back({&D.blk[b].inv, add_inv(hp, sb.alpha, C)});
+    {  // Conv1d weight [2C][C][k] -> GEMM operand [2C][k*C]: column kk*C + ci
+      const size_t off = hp.add(nullptr, (size_t)2 * C * k * C);
+      for (int co = 0; co < 2 * C; ++co)
+        for (int ci = 0; ci < C; ++ci)
+          for (int kk = 0; kk < k; ++kk)
+            hp.data[off + ((size_t)co * k + kk) * C + ci] = sb.down_w[((size_t)co * C + ci) * k + kk];
+      fix.push_back({&D.blk[b].down_w, off});
+    }
+    put(&D.blk[b].down_b, sb.down_b, 2 * C);
+    C *= 2;
+  }
+  fix.push_back({&D.out_dw_w, add_transposed(hp, w->out_dw_w, kLatent, 7)});
+  put(&D.out_dw_b, w->out_dw_b, kLatent);
+  std::vector<float> cb((size_t)SNACB_CODEBOOK_SIZE * 8);
+  for (int l = 0; l < 3; ++l) {
+    if (!w->inproj_w[l] || !w->inproj_b[l]) return fail(e, SNACB_EINVAL, "snacb_load_encoder_weights: null in_proj tensor");
+    put(&D.inproj_w[l], w->inproj_w[l], (size_t)8 * kLatent);
+    put(&D.inproj_b[l], w->inproj_b[l], 8);
+    CU(e, cudaMemcpy(cb.data(), e->w.q.codebook[l], cb.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    const size_t off = hp.add(nullptr, cb.size());
+    for (int k = 0; k < SNACB_CODEBOOK_SIZE; ++k) {  // F.normalize(codebook): x / max(||x||_2, 1e-12)
+      float n2 = 0.0f;
+      for (int d = 0; d < 8; ++d) n2 += cb[(size_t)k * 8 + d] * cb[(size_t)k * 8 + d];
+      const float rn = 1.0f / std::max(std::sqrt(n2), 1e-12f);
+      for (int d = 0; d < 8; ++d) hp.data[off + (size_t)k * 8 + d] = cb[(size_t)k * 8 + d] * rn;
+    }
+    fix.push_back({&D.cb_norm[l], off});
+  }
+  const size_t bytes = hp.data.size() * sizeof(float);
+  CU(e, cudaDeviceSynchronize());
+  if (e->earena) { CU(e, cudaFree(e->earena)); e->earena = nullptr; }
+  CU(e, cudaMalloc(&e->earena, bytes));
+  CU(e, cudaMemcpy(e->earena, hp.data.data(), bytes, cudaMemcpyHostToDevice));
+  for (const Fix& f : fix) *f.dst = reinterpret_cast<float*>(e->earena) + f.off;
+  e->enc_loaded = true;
+  return SNACB_OK;
+}
+
+int snacb_encode(snacb_engine* e, const float* d_audio, int32_t batch, int32_t n_samples, int32_t* d_c0, int32_t* d_c1,
+                 int32_t* d_c2, float* d_latent, void* stream) {
+  if (!e) return SNACB_EINVAL;
+  if (!e->enc_loaded) return fail(e, SNACB_ESTATE, "snacb_encode: encoder weights not loaded");
+  if (!d_audio || !d_c0 || !d_c1 || !d_c2 || batch < 0 || n_samples <= 0 || n_samples % 2048)
+    return fail(e, SNACB_EINVAL, "snacb_encode: bad argument (n_samples must be a positive multiple of 2048)");
+  if (batch == 0) return SNACB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(e, cudaSetDevice(e->device));
+  const EncDev& D = e->enc;
+  // largest stage: [T + 2][48] (the padded copy before the first strided conv); three ping-pong buffers
+  const size_t S = (size_t)(n_samples + 8) * kEncDim;
+  const size_t per_item = 3 * pad256(S * 4) + 1024;
+  int rc = ensure_ws(e, std::min<size_t>(per_item * batch, std::max<size_t>(per_item, kActBudget)), st);
+  if (rc) return rc;
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>(batch, e->ws_bytes / per_item));
+  int32_t* codes[3] = {d_c0, d_c1, d_c2};
+  for (int start = 0; start < batch; start += chunk) {
+    const int n = std::min(chunk, batch - start);
+    Bump bp(e->ws);
+    float* X = bp.take<float>(S * n);
+    float* Y = bp.take<float>(S * n);
+    float* A = bp.take<float>(S * n);
+    int T = n_samples, C = kEncDim;
+    {
+      ProfScope ps(e, KC_DW, 14.0 * n * T * C, 4.0 * n * T * (1.0 + C), st);
+      launch_enc_in(d_audio + (size_t)start * n_samples, n, T, D.in_w, D.in_b, X, st, &e->launches);
+    }
+    for (int b = 0; b < 4; ++b) {
+      const EncBlockDev& Wb = D.blk[b];
+      const int s = kEncRates[b], p = (s + 1) / 2;
+      GroupCtx g{nullptr, 0, n, 0, T, st, &e->launches, e->cfg.flags};  // rows [0, T) are the whole sequence at this rate
+      const Rng all{0, T};
+      for (int r = 0; r < 3; ++r) {
+        const RuDev& R = Wb.ru[r];
+        {
+          ProfScope ps(e, KC_DW, 46.0 * n * T * C, 8.0 * n * T * C, st);
+          launch_dwconv(g, DwArgs{X, all, A, all, C, kDil[r], 1, R.dw_w, R.dw_b, R.a1, R.i1, R.a2, R.i2});
+        }
+        GemmArgs a{};
+        a.epi = EPI_RESID; a.A = A; a.lda = C; a.a_r = all; a.W = R.pw_w; a.ldw = C; a.bias = R.pw_b; a.K = C; a.N = C;
+        a.m_r = all; a.out = Y; a.o_r = all; a.ldo = C; a.R = X; a.r_r = all; a.ldr = C; a.up = 1;
+        ProfScope ps(e, KC_GEMM1, 2.0 * n * T * C * C, 12.0 * n * T * C, st);
+        launch_gemm_f32(g, a);
+        std::swap(X, Y);
+      }
+      {
+        ProfScope ps(e, KC_SNAKE, 4.0 * n * T * C, 8.0 * n * T * C, st);
+        launch_snake_pad(X, A, n, T, C, s, p, Wb.alpha, Wb.inv, st, &e->launches);
+      }
+      const int To = T / s;
+      GroupCtx go{nullptr, 0, n, 0, To, st, &e->launches, e->cfg.flags};
+      GemmArgs a{};
+      a.epi = EPI_BIAS; a.A = A; a.lda = s * C; a.a_r = Rng{0, (T + s) / s}; a.W = Wb.down_w; a.ldw = 2 * s * C; a.bias = Wb.down_b;
+      a.K = 2 * s * C; a.N = 2 * C; a.m_r = Rng{0, To}; a.out = Y; a.o_r = Rng{0, To}; a.ldo = 2 * C; a.up = 1;
+      {
+        ProfScope ps(e, KC_GEMM1, 2.0 * n * To * a.K * a.N, 4.0 * n * (T * C + To * 2.0 * C), st);
+        launch_gemm_f32(go, a);
+      }
+      std::swap(X, Y);
+      T = To; C *= 2;
+    }
+    {
+      GroupCtx g{nullptr, 0, n, 0, T, st, &e->launches, e->cfg.flags};
+      ProfScope ps(e, KC_DW, 14.0 * n * T * C, 8.0 * n * T * C, st);
+      launch_dwconv(g, DwArgs{X, Rng{0, T}, Y, Rng{0, T}, C, 1, 1, D.out_dw_w, D.out_dw_b, nullptr, nullptr, nullptr, nullptr});
+    }
+    if (d_latent)
+      CU(e, cudaMemcpyAsync(d_latent + (size_t)start * T * kLatent, Y, (size_t)n * T * kLatent * 4, cudaMemcpyDeviceToDevice, st));
+    for (int l = 0; l < 3; ++l) {  // residual VQ: Y is the running residual
+      ProfScope ps(e, KC_CODES, 2.0 * n * (T / kVqStrides[l]) * (8.0 * kLatent * 2 + 8.0 * SNACB_CODEBOOK_SIZE), 8.0 * n * T * kLatent, st);
+      launch_vq_level(Y, n, T, kVqStrides[l], D.inproj_w[l], D.inproj_b[l], D.cb_norm[l], e->w.q.codebook[l], e->w.q.w[l], e->w.q.b[l],
+                      codes[l] + (size_t)start * (T / kVqStrides[l]), st, &e->launches);
+    }
+    rc = check_launch(e, "encoder pipeline");
+    if (rc) return rc;
+  }
   return SNACB_OK;
 }
 

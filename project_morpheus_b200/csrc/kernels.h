@@ -144,6 +144,13 @@ struct TailArgs {
 };
 void launch_tail(const GroupCtx& g, const TailArgs& a);
 
+// ---- encoder (kernels_enc.cu)
+void launch_enc_in(const float* audio, int B, int T, const float* w, const float* bias, float* out, cudaStream_t st, int64_t* launches);
+void launch_snake_pad(const float* in, float* out, int B, int T, int C, int s, int p, const float* alpha, const float* inv,
+                      cudaStream_t st, int64_t* launches);
+void launch_vq_level(float* residual, int B, int T, int stride, const float* w_in, const float* b_in, const float* cb_norm,
+                     const float* cb, const float* w_out, const float* b_out, int32_t* codes, cudaStream_t st, int64_t* launches);
+
 void launch_fill_noise(uint64_t seed, const unsigned long long* d_keys, int n_win, int F, float* d_noise,
                        long long stride, cudaStream_t st, int64_t* launches);
 

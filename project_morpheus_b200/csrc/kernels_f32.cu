@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(256) k_gemm_f32(const Item* items, int base, i
       }
     }
   }
-  const float* wrow = a.W + (size_t)(n0 + lrow) * a.ldw;
+  const float* wrow = (n0 + lrow < a.N) ? a.W + (size_t)(n0 + lrow) * a.ldw : nullptr;  // N need not be a multiple of 64
 
   float acc[4][4];
 #pragma unroll
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256) k_gemm_f32(const Item* items, int base, i
     const float* ar = arow[sgm];
     for (int k0 = 0; k0 < a.K; k0 += 16) {
       float4 av = ar ? *reinterpret_cast<const float4*>(ar + k0 + lk) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 wv = *reinterpret_cast<const float4*>(wrow + (size_t)sgm * a.K + k0 + lk);
+      float4 wv = wrow ? *reinterpret_cast<const float4*>(wrow + (size_t)sgm * a.K + k0 + lk) : make_float4(0.f, 0.f, 0.f, 0.f);
       As[lk + 0][lrow] = av.x; As[lk + 1][lrow] = av.y; As[lk + 2][lrow] = av.z; As[lk + 3][lrow] = av.w;
       Bs[lk + 0][lrow] = wv.x; Bs[lk + 1][lrow] = wv.y; Bs[lk + 2][lrow] = wv.z; Bs[lk + 3][lrow] = wv.w;
       __syncthreads();
@@ -269,6 +269,7 @@ __global__ void __launch_bounds__(256) k_gemm_f32(const Item* items, int base, i
     const int t_abs = t_rel + it.shift0 * a.up;
     const bool live = (t_abs >= 0) && (t_abs < T0 * a.up);
     const int ncol0 = n0 + tx * 4 - ((EPI == EPI_CONVT) ? phase * a.Cout : 0);
+    if (n0 + tx * 4 >= a.N) continue;
     float v[4];
 #pragma unroll
     for (int jn = 0; jn < 4; ++jn) v[jn] = acc[i][jn];
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(256) k_gemm_f32(const Item* items, int base, i
 void launch_gemm_f32(const GroupCtx& g, const GemmArgs& a) {
   const long long Mtot = (long long)g.n_items * a.m_r.n();
   if (Mtot <= 0) return;
-  dim3 grid((unsigned)((Mtot + 63) / 64), a.N / 64);
+  dim3 grid((unsigned)((Mtot + 63) / 64), (a.N + 63) / 64);
   switch (a.epi) {
     case EPI_BIAS: k_gemm_f32<EPI_BIAS><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, g.n_items, a); break;
     case EPI_RESID: k_gemm_f32<EPI_RESID><<<grid, 256, 0, g.stream>>>(g.items, g.base, g.out_len, g.T0, g.n_items, a); break;

@@ -94,6 +94,19 @@ class SnacEngine:
                     setattr(ru, fld, p(f"b{b}_r{r}_{fld}"))
         w.tail_alpha, w.tail_w, w.tail_b = p("tail_alpha"), p("tail_w"), p("tail_b")
         self._check(self._lib.snacb_load_weights(self._h, C.byref(w)), "snacb_load_weights")
+        self.has_encoder = bool(getattr(fw, "has_encoder", False))
+        if self.has_encoder:  # encode direction
+            ew = _lib.EncoderWeights()
+            ew.in_w, ew.in_b, ew.out_dw_w, ew.out_dw_b = p("enc_in_w"), p("enc_in_b"), p("enc_out_dw_w"), p("enc_out_dw_b")
+            for b in range(4):
+                blk = ew.block[b]
+                blk.alpha, blk.down_w, blk.down_b = p(f"enc{b}_alpha"), p(f"enc{b}_down_w"), p(f"enc{b}_down_b")
+                for r in range(3):
+                    for fld in ("alpha1", "dw_w", "dw_b", "alpha2", "pw_w", "pw_b"):
+                        setattr(blk.ru[r], fld, p(f"enc{b}_r{r}_{fld}"))
+            for i in range(3):
+                ew.inproj_w[i], ew.inproj_b[i] = p(f"inproj_w{i}"), p(f"inproj_b{i}")
+            self._check(self._lib.snacb_load_encoder_weights(self._h, C.byref(ew)), "snacb_load_encoder_weights")
 
     # ------------------------------------------------------------------ helpers
     def _stream(self) -> int:
@@ -278,6 +291,32 @@ class SnacEngine:
         self._check(rc, "snacb_decode_codes")
         self._keep_codes = c
         return (wav, pcm) if want_pcm else wav
+
+    # ------------------------------------------------------------------ encode direction (N4)
+    def encode(self, audio: torch.Tensor, return_latent: bool = False):
+        """``model.encode(audio)`` of the published package: float audio ``[B,1,T]`` (or ``[B,T]``) -> the three code
+        tensors ``[B,T'/4]``, ``[B,T'/2]``, ``[B,T']`` (int64, T' = padded length / 512); zero-padded on the right to a
+        multiple of 2048 samples like ``SNAC.preprocess``."""
+        if not getattr(self, "has_encoder", False):
+            raise _lib.SnacbError("this engine was built from a state dict without encoder.* weights")
+        x = audio.to(device=self.torch_device, dtype=torch.float32)
+        if x.dim() == 3:
+            x = x[:, 0, :]
+        B, T = x.shape
+        Tp = -(-T // 2048) * 2048
+        if Tp != T:
+            x = torch.nn.functional.pad(x, (0, Tp - T))
+        x = x.contiguous()
+        n = Tp // 512
+        codes = [torch.empty((B, n // s), dtype=torch.int32, device=self.torch_device) for s in (4, 2, 1)]
+        lat = torch.empty((B, n, 768), dtype=torch.float32, device=self.torch_device) if return_latent else None
+        with torch.cuda.device(self.device):
+            rc = self._lib.snacb_encode(self._h, x.data_ptr(), B, Tp, codes[0].data_ptr(), codes[1].data_ptr(), codes[2].data_ptr(),
+                                        _ptr(lat), self._stream())
+        self._check(rc, "snacb_encode")
+        self._keep_audio = x
+        out = [c.to(torch.int64) for c in codes]
+        return (out, lat.transpose(1, 2)) if return_latent else out
 
     def fill_noise(self, seed: int, n_win: int, frames: int, keys: Optional[Sequence[int]] = None) -> torch.Tensor:
         out = torch.empty((n_win, _lib.NOISE_PER_FRAME * frames), dtype=torch.float32, device=self.torch_device)

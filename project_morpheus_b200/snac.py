@@ -109,6 +109,11 @@ class SNAC:
     def engine(self):
         return self._ensure_engine()
 
+    def encode(self, audio_data: torch.Tensor):
+        """``snac.SNAC.encode``: float audio ``[B,1,T]`` -> three code tensors (needs a checkpoint that
+        carries the encoder weights, e.g. the published ``pytorch_model.bin``)."""
+        return self._ensure_engine().encode(audio_data)
+
     def decode(self, codes: Sequence[torch.Tensor]) -> torch.Tensor:
         """``[B,F],[B,2F],[B,4F]`` integer codes -> float32 ``[B,1,2048F]`` on the model's device."""
         eng = self._ensure_engine()

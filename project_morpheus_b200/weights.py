@@ -96,6 +96,59 @@ def decoder_layout() -> List[Tuple[str, str, tuple]]:
     return rows
 
 
+ENCODER_DIM = 48
+ENCODER_RATES = (2, 4, 8, 8)
+
+
+def encoder_layout() -> List[Tuple[str, str, tuple]]:
+    """Parametrised layers of the encode direction: encoder + the quantizers' in-projections."""
+    rows: List[Tuple[str, str, tuple]] = [("encoder.block.0", "conv", (ENCODER_DIM, 1, 7, True))]
+    c = ENCODER_DIM
+    for b, s in enumerate(ENCODER_RATES):
+        p = f"encoder.block.{1 + b}.block"
+        for r in range(3):
+            q = f"{p}.{r}.block"
+            rows.append((f"{q}.0", "snake", (c,)))
+            rows.append((f"{q}.1", "conv", (c, 1, 7, True)))
+            rows.append((f"{q}.2", "snake", (c,)))
+            rows.append((f"{q}.3", "conv", (c, c, 1, True)))
+        rows.append((f"{p}.3", "snake", (c,)))
+        rows.append((f"{p}.4", "conv", (2 * c, c, 2 * s, True)))
+        c *= 2
+    rows.append(("encoder.block.5", "conv", (c, 1, 7, True)))
+    for i in range(3):
+        rows.append((f"quantizer.quantizers.{i}.in_proj", "conv", (CODEBOOK_DIM, LATENT, 1, True)))
+    return rows
+
+
+def random_encoder_state_dict(seed: int = 0, variant: str = "default") -> Dict[str, torch.Tensor]:
+    """Seeded random-init weights of the ENCODE direction, drawn from generators of their own so the decode-path
+    weights of ``random_state_dict`` (and every golden vector made from them) are unchanged.  Merge the two dicts for a
+    full model."""
+    g = torch.Generator(device="cpu").manual_seed(1000003 + seed)
+    g1 = torch.Generator(device="cpu").manual_seed(1000003 + seed + 1)
+    w1 = variant == "w1"
+    if variant not in ("default", "w1"):
+        raise ValueError(variant)
+    sd: Dict[str, torch.Tensor] = {}
+    for prefix, kind, info in encoder_layout():
+        if kind == "snake":
+            a = torch.ones(1, info[0], 1)
+            if w1:
+                a = 0.5 + torch.rand(a.shape, generator=g1)
+            sd[f"{prefix}.alpha"] = a
+        else:
+            cout, cin_g, k, _ = info
+            bound = 1.0 / math.sqrt(cin_g * k)
+            v = (torch.rand((cout, cin_g, k), generator=g) * 2 - 1) * bound
+            gain = v.flatten(1).norm(dim=1).reshape(-1, 1, 1)
+            if w1:
+                gain = gain * (0.8 + 0.4 * torch.rand(gain.shape, generator=g1))
+            sd[f"{prefix}.weight_g"], sd[f"{prefix}.weight_v"] = gain, v
+            sd[f"{prefix}.bias"] = (torch.rand((cout,), generator=g) * 2 - 1) * bound
+    return sd
+
+
 # --------------------------------------------------------------------------- random init
 def random_state_dict(seed: int = 0, variant: str = "default") -> Dict[str, torch.Tensor]:
     """Seeded random-init weights of the snac_24khz decode path (no network for checkpoints).
@@ -210,6 +263,32 @@ class FoldedWeights:
         put("tail_alpha", sd["decoder.model.6.alpha"].reshape(c))
         put("tail_w", _fold(sd, "decoder.model.7").reshape(c, 7))
         put("tail_b", sd["decoder.model.7.bias"])
+        # encode direction (N4), when the checkpoint carries it
+        self.has_encoder = "encoder.block.0.bias" in sd
+        if self.has_encoder:
+            put("enc_in_w", _fold(sd, "encoder.block.0").reshape(ENCODER_DIM, 7))
+            put("enc_in_b", sd["encoder.block.0.bias"])
+            c = ENCODER_DIM
+            for b, s in enumerate(ENCODER_RATES):
+                p = f"encoder.block.{1 + b}.block"
+                for r in range(3):
+                    q = f"{p}.{r}.block"
+                    put(f"enc{b}_r{r}_alpha1", sd[f"{q}.0.alpha"].reshape(c))
+                    put(f"enc{b}_r{r}_dw_w", _fold(sd, f"{q}.1").reshape(c, 7))
+                    put(f"enc{b}_r{r}_dw_b", sd[f"{q}.1.bias"])
+                    put(f"enc{b}_r{r}_alpha2", sd[f"{q}.2.alpha"].reshape(c))
+                    put(f"enc{b}_r{r}_pw_w", _fold(sd, f"{q}.3").reshape(c, c))
+                    put(f"enc{b}_r{r}_pw_b", sd[f"{q}.3.bias"])
+                put(f"enc{b}_alpha", sd[f"{p}.3.alpha"].reshape(c))
+                put(f"enc{b}_down_w", _fold(sd, f"{p}.4"))                      # [2C, C, 2s]
+                put(f"enc{b}_down_b", sd[f"{p}.4.bias"])
+                c *= 2
+            put("enc_out_dw_w", _fold(sd, "encoder.block.5").reshape(LATENT, 7))
+            put("enc_out_dw_b", sd["encoder.block.5.bias"])
+            for i in range(3):
+                q = f"quantizer.quantizers.{i}"
+                put(f"inproj_w{i}", _fold(sd, f"{q}.in_proj").reshape(CODEBOOK_DIM, LATENT))
+                put(f"inproj_b{i}", sd[f"{q}.in_proj.bias"])
         self.tensors = t
 
     def num_params(self) -> int:
