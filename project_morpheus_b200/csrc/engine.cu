@@ -106,6 +106,7 @@ struct snacb_engine {
   int64_t launches = 0;
   int prefetch_ahead = 0;  // SM count when L2 prefetch-ahead is on (SNACB_PREFETCH env, default on)
   bool ru256 = false;      // decoder block 1 (C = 256) ResidualUnits through the persistent fused kernel (SNACB_RU256 env)
+  bool ruw = true;         // decoder block 1 ResidualUnits through k_ru_w (SNACB_RUW=0 falls back to k_dw_tc + k_gemm_ws)
   // CUDA graphs of small host-API ticks (latency mode): key -> instantiated graph
   struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t gen = 0; int calls = 0; bool disabled = false; };
   std::map<std::vector<long long>, GraphEntry> graphs;
@@ -500,6 +501,23 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
       Rng cur = B.ct;
       for (int r = 0; r < 3 && ce == cudaSuccess; ++r) {
         const RuDev& R = Wb.ru[r];
+        // block 1 (C = 256): fused persistent ResidualUnit kernel with the residual stream initialised in tensor memory
+        if (ruw_tc_supported(B.Cout) && e->ruw && !(e->cfg.flags & (SNACB_FLAG_NO_RU_FUSION | SNACB_FLAG_PERSISTENT_RU | SNACB_FLAG_FUSE_RU256)) &&
+            n * (long long)B.r[r].n() >= 8 * 128 && e->tap_stage != sid + 4 + 2 * r) {
+          const bool last = (r == 2) && (b < 3);
+          const bool want32 = !last;
+          RuTcArgs u{X, cur, B.r[r], B.Cout, kDil[r], B.up_out, R.dw_w, R.dw_b, R.a1, R.i1, R.a2, R.i2, R.pw16, R.pw_b,
+                     want32 ? Y : nullptr, last ? Anext : nullptr, last ? W.blk[b + 1].alpha : nullptr,
+                     last ? W.blk[b + 1].inv : nullptr, 0, false};
+          const double el = (double)n * B.r[r].n() * B.Cout;
+          ProfScope ps(e, KC_RU, 2.0 * el * B.Cout + el * 24.0,
+                       (double)n * cur.n() * B.Cout * 4.0 + el * ((want32 ? 4.0 : 0.0) + (last ? 2.0 : 0.0)), st);
+          ce = launch_ruw_tc(g, u);
+          tap(e, sid + 4 + 2 * r, Y, B.r[r], B.Cout, n, first, st);
+          std::swap(X, Y);
+          cur = B.r[r];
+          continue;
+        }
         const bool ru_persist = (e->cfg.flags & SNACB_FLAG_PERSISTENT_RU) != 0 || (B.Cout == 256 && (e->ru256 || (e->cfg.flags & SNACB_FLAG_FUSE_RU256)));
         if (ru_tc_supported(B.Cout, ru_persist) && !(e->cfg.flags & SNACB_FLAG_NO_RU_FUSION)) {  // fused dw + 1x1 + residual (blocks 2, 3)
           const bool last = (r == 2) && (b < 3);
@@ -753,6 +771,8 @@ int snacb_create(snacb_engine** out, const snacb_config* cfg) {
     e->prefetch_ahead = (pf && pf[0] == '0') ? 0 : prop.multiProcessorCount;
     const char* r2 = getenv("SNACB_RU256");
     e->ru256 = r2 && r2[0] == '1';
+    const char* rw = getenv("SNACB_RUW");
+    e->ruw = !(rw && rw[0] == '0');
     const char* gr = getenv("SNACB_GRAPHS");
     if (gr) e->graph_max_win = atoi(gr);  // 0 disables the CUDA-graph path
   }

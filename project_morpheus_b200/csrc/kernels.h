@@ -113,6 +113,9 @@ struct RuTcArgs {
   const float* tail_w7; const float* tail_b; Rng tail_out; int32_t* status; float* wav; int16_t* pcm;
 };
 bool ru_tc_supported(int C, bool persistent);
+// wide fused ResidualUnit (C = 256, kernels_ruw.cu): TMA-staged input blocks, residual stream initialised in tensor memory
+bool ruw_tc_supported(int C);
+cudaError_t launch_ruw_tc(const GroupCtx& g, const RuTcArgs& a);
 cudaError_t launch_ru_tc(const GroupCtx& g, const RuTcArgs& a);
 // Whole DecoderBlock ResidualUnit chain (+ decoder tail and PCM pack) in one persistent kernel (kernels_blk.cu): the
 // residual stream stays in tensor memory, Snake'd activations in shared memory.  x = ConvTranspose1d + NoiseBlock output.

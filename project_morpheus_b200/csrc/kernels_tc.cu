@@ -41,17 +41,6 @@ const bool g_ws_cluster = [] { const char* v = getenv("SNACB_WS_CLUSTER"); retur
 // One depthwise unit: L outputs at rows first, first+DIL, ... of one channel pair from L+6 inputs at
 // p0 + m*DIL*C (m = 0..L+5; bit m of `mask` says the row exists, absent rows are the conv's zero pad).
 // Output j = Snake2(b + sum_k w[k] * Snake1(in[j + k])) is handed to sink(j, value).
-struct DwPairW {
-  float2 al1, iv1, al2, iv2, bias, w[7];
-  __device__ __forceinline__ void load(const float* w7, const float* dw_b, const float* a1, const float* i1, const float* a2,
-                                       const float* i2, int C, int c) {
-    al1 = *reinterpret_cast<const float2*>(a1 + c); iv1 = *reinterpret_cast<const float2*>(i1 + c);
-    al2 = *reinterpret_cast<const float2*>(a2 + c); iv2 = *reinterpret_cast<const float2*>(i2 + c);
-    bias = *reinterpret_cast<const float2*>(dw_b + c);
-#pragma unroll
-    for (int k = 0; k < 7; ++k) w[k] = *reinterpret_cast<const float2*>(w7 + k * C + c);
-  }
-};
 template <int C, int DIL, int L, typename Sink>
 __device__ __forceinline__ void dw_unit(const float* p0, uint32_t mask_lo, uint32_t mask_hi, const DwPairW& W, Sink&& sink) {
   // Transposed-form FIR: input m, once Snake'd, is scattered into the (up to) seven outputs j = m-6..m it

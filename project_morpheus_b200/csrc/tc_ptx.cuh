@@ -62,11 +62,12 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug becomes a trap (CUDA error) instead of a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) {
-      printf("snacb: mbarrier timeout, block (%d,%d) thread %d\n", (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x);
+    if (++spins > ((tag >= 100 && tag < 400) ? (1u << 24) : (1u << 22))) {  // dependants time out after what they wait for
+      printf("snacb: mbarrier timeout, block (%d,%d) thread %d tag %d parity %u\n", (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x, tag,
+             parity);
       __trap();
     }
   }
@@ -208,6 +209,19 @@ __device__ __forceinline__ float2 snake2(float2 x, float2 al, float2 iv) {
   s = __fmul2_rn(s, s);
   return __ffma2_rn(iv, s, x);
 }
+
+// Per-channel-pair constants of one ResidualUnit's depthwise stage (Snake -> depthwise k7 -> Snake)
+struct DwPairW {
+  float2 al1, iv1, al2, iv2, bias, w[7];
+  __device__ __forceinline__ void load(const float* w7, const float* dw_b, const float* a1, const float* i1, const float* a2,
+                                       const float* i2, int C, int c) {
+    al1 = *reinterpret_cast<const float2*>(a1 + c); iv1 = *reinterpret_cast<const float2*>(i1 + c);
+    al2 = *reinterpret_cast<const float2*>(a2 + c); iv2 = *reinterpret_cast<const float2*>(i2 + c);
+    bias = *reinterpret_cast<const float2*>(dw_b + c);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) w[k] = *reinterpret_cast<const float2*>(w7 + k * C + c);
+  }
+};
 
 }  // namespace
 
