@@ -76,7 +76,10 @@ __device__ __forceinline__ void dw_unit_swz(const uint8_t* const (&base)[8], con
 #pragma unroll
   for (int m = 0; m < L + 6; ++m) {
     const float2 x = *reinterpret_cast<const float2*>(base[(m * DIL) & 7] + m * DIL * 128);
-    const float2 v = snake2(x, W.al1, W.iv1);
+    // first Snake in its cosine form without the constant: x - h cos(2 a x) (al1 = 2a, iv1 = -h; the "+ h" is folded into
+    // the conv's bias by the caller; zero-padded rows give -h, i.e. Snake = 0) - one packed instruction less per input
+    const float2 t = __fmul2_rn(W.al1, x);
+    const float2 v = __ffma2_rn(W.iv1, make_float2(__cosf(t.x), __cosf(t.y)), x);
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
       const int j = m - k;
@@ -263,6 +266,14 @@ __global__ void __launch_bounds__(kRwThreads, 1) k_ru_w(const __grid_constant__ 
         const int nb = ti * kRwNB + b, st = nb % NST, kb = b >> 1;
         DwPairW W;  // requested before the waits: the latency of these loads hides behind them
         W.load(a.w7, a.dw_b, a.a1, a.i1, a.a2, a.i2, C, b * 32 + p * 2);
+        {  // cosine-form first Snake: scale, sign and the folded constant h * sum_k w[k]
+          float2 sw = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int k = 0; k < 7; ++k) { sw.x += W.w[k].x; sw.y += W.w[k].y; }
+          W.bias = make_float2(fmaf(0.5f * W.iv1.x, sw.x, W.bias.x), fmaf(0.5f * W.iv1.y, sw.y, W.bias.y));
+          W.al1 = make_float2(2.0f * W.al1.x, 2.0f * W.al1.y);
+          W.iv1 = make_float2(-0.5f * W.iv1.x, -0.5f * W.iv1.y);
+        }
         if (ti > 0) mbar_wait(bar(A_FREE + kb), (ti - 1) & 1, 600 + kb);  // the previous tile's MMAs have read this k-block
         mbar_wait(bar(X_FULL + st), (nb / NST) & 1, 700 + b);
         if (has_unit && !(a.dbg & 1)) {
