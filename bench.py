@@ -39,6 +39,7 @@ FLOP_PER_WINDOW_REFERENCE = 3.312e9   # what model.decode executes for a 4-frame
 FLOP_PER_WINDOW_CONE = 1.363e9        # exact dependency cone of samples [2048,4096)
 METRIC = "snac24k_audio_seconds_per_second"
 UNIT = "audio-s/s"
+PROFILE_STEP = os.environ.get("SNACB_PROFILE_STEP", "0") == "1"  # scripts/gpu_profile_r02.sh
 
 
 def synth_tokens(first_stream: int, n: int, frames: int) -> np.ndarray:
@@ -240,7 +241,14 @@ def run_ours(args) -> None:
     for i in range(K):
         flush.zero_()                                  # untimed L2 flush between steps
         evs[i][0].record()
+        prof = PROFILE_STEP and i == K - 1  # `ncu --profile-from-start off` then captures exactly one tick
+        if prof:
+            torch.cuda.synchronize(dev)
+            torch.cuda.profiler.start()
         tick_device(100 + i)
+        if prof:
+            torch.cuda.synchronize(dev)
+            torch.cuda.profiler.stop()
         evs[i][1].record()
     barrier()
     wall_dev = time.perf_counter() - wall0
@@ -478,8 +486,9 @@ def run_ours(args) -> None:
                                 yield s_
                         return gen
 
-                    async def pull_all():
-                        ads = [SnacB200Adapter("bench", "tara", token_source=source(st_), seed=i) for i, st_ in enumerate(strs)]
+                    async def pull_all(gpu_ring=True):
+                        ads = [SnacB200Adapter("bench", "tara", token_source=source(st_), seed=i, gpu_ring=gpu_ring)
+                               for i, st_ in enumerate(strs)]
 
                         async def loop(ad):
                             nb = 0
@@ -497,12 +506,19 @@ def run_ours(args) -> None:
                     nbytes = asyncio.run(pull_all())
                     dt = time.perf_counter() - t0
                     t_after = tkr.stats()
+                    asyncio.run(pull_all(False))
+                    t0 = time.perf_counter()
+                    nbytes_h = asyncio.run(pull_all(False))
+                    dt_h = time.perf_counter() - t0
                     res_pull[f"{n_ad}_streams"] = {
                         "audio_s_per_s": nbytes / 2 / SAMPLE_RATE / dt, "seconds": dt, "bytes": nbytes,
                         "ticks": t_after["ticks"] - t_before["ticks"], "windows": t_after["windows"] - t_before["windows"],
-                        "frames_per_stream": fr_ad}
+                        "frames_per_stream": fr_ad,
+                        "host_bytes_ring": {"audio_s_per_s": nbytes_h / 2 / SAMPLE_RATE / dt_h, "seconds": dt_h, "bytes": nbytes_h}}
                 res_pull["note"] = ("token strings -> SnacB200Adapter.pull(4096) per request, per-token Python of tokens_decoder "
-                                    "included; engine calls = ticks, not windows")
+                                    "included; engine calls = ticks, not windows.  Main figure: the tick's PCM is written by the GPU "
+                                    "into pinned per-stream rings (N3, csrc/egress_ring.cu) and pull() is one native ring read; "
+                                    "host_bytes_ring: PCM matrix D2H + Python bytes per window (gpu_ring=False)")
                 extra["ticker_pull"] = res_pull
             except Exception as exc:  # noqa: BLE001
                 extra["ticker_pull"] = {"error": repr(exc)[:300]}
@@ -638,6 +654,34 @@ def run_ours(args) -> None:
                                       "numpy_reference_ms_per_tick": 1e3 * dt_np, "bytes_per_tick": nbytes // ticks_e,
                                       "note": "overlap-add stitcher, one 2048-sample chunk per stream per tick, native = one StitcherBank.push_tick call per tick; numpy = the "
                                               "reference's algorithm (oracle restatement), scaled from a 1/8 sample of the streams"}
+            # the same join on the GPU: ring kernel right after the decoder tail, PCM written into pinned per-stream rings
+            try:
+                from project_morpheus_b200.egress import GpuPcmRing
+                gr = GpuPcmRing(ns_e, 8192, overlap_ms=10.0, device=local)
+                d_mats = [torch.from_numpy(m).to(dev) for m in mats]
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                stream_ptr = torch.cuda.current_stream(dev).cuda_stream
+                gr.push_device(slots_e, d_mats[0].data_ptr(), 2048, 2048, stream=stream_ptr)
+                gr.sync(stream_ptr)
+                for s_i in range(ns_e):
+                    gr.read(s_i, 1 << 20)
+                t_host, k_ms = 0.0, 0.0
+                for t in range(1, ticks_e):
+                    t0 = time.perf_counter()
+                    ev0.record()
+                    gr.push_device(slots_e, d_mats[t].data_ptr(), 2048, 2048, stream=stream_ptr)
+                    ev1.record()
+                    gr.sync(stream_ptr)
+                    t_host += time.perf_counter() - t0
+                    k_ms += ev0.elapsed_time(ev1)
+                    for s_i in range(ns_e):
+                        gr.read(s_i, 1 << 20)
+                gr.close()
+                extra["n3_pcm_egress"].update({"gpu_ring_ms_per_tick": 1e3 * t_host / (ticks_e - 1), "gpu_ring_kernel_ms": k_ms / (ticks_e - 1),
+                                               "gpu_ring_note": "k_stitch_ring over the device PCM matrix of a tick -> pinned rings (wall time of push + sync; "
+                                                                "kernel time by CUDA events); replaces the D2H matrix copy + the host join"})
+            except Exception as exc:  # noqa: BLE001
+                extra["n3_pcm_egress"]["gpu_ring_error"] = repr(exc)[:200]
 
         # precision safety net: the same tick through the split-operand recipe (SNACB_PREC_FP16X3, <= 2 LSB vs fp32)
         if args.precision == "fp16" and not args.no_cpu_baseline:

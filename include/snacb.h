@@ -331,6 +331,49 @@ int snacb_stitch_bank_push(snacb_stitch_bank* b, int32_t n, const int32_t* slots
                            int64_t len, const int32_t* eos_in, int16_t* out, int64_t out_stride, int64_t* out_len,
                            int32_t* out_eos);
 
+/* ---- N3 on the GPU: decode ticks written straight into pinned per-stream PCM rings ------------
+ * Replaces, for every stream of a tick at once, orchestrator/stitcher.py:10-79 (crossfade of consecutive chunks, same
+ * float64 arithmetic, done by a kernel right after the decoder tail), orchestrator/ring_buffer.py:27-83 (the byte ring)
+ * and the pull(chunk_size) re-chunking of tts_engine/llama_local.py:120-150 (snacb_egress_read).  A ring is
+ * `ring_samples` int16 samples (multiple of 8, >= 4096) of pinned host memory per slot that the GPU writes through its
+ * device mapping; the PCM matrix of the tick never crosses PCIe as a separate copy. */
+typedef struct snacb_egress snacb_egress;
+int snacb_egress_create(snacb_egress** out, int32_t device, int32_t n_slots, int32_t ring_samples, int32_t sample_rate,
+                        double overlap_ms);
+void snacb_egress_destroy(snacb_egress* g);
+const char* snacb_egress_last_error(const snacb_egress* g);
+int64_t snacb_egress_overlap_samples(const snacb_egress* g);
+/* Host address of a slot's ring (for zero-copy consumers). */
+const int16_t* snacb_egress_ring_base(const snacb_egress* g, int32_t slot);
+/* Asynchronous on `stream`: chunk i = d_pcm[i * pcm_stride .. + len) (device memory) joins the ring of slot h_slots[i]
+ * (-1 = not for a ring); windows whose d_status[i] != SNACB_WIN_OK contribute nothing (d_status may be NULL); h_eos[i] != 0
+ * closes the stream (tail emitted, no fade kept), may be NULL.  A slot may appear once per call.  SNACB_ESTATE if a ring
+ * could overflow: nothing is launched, read first. */
+int snacb_egress_push_device(snacb_egress* g, int32_t n_win, const int32_t* h_slots, const int16_t* d_pcm, int64_t pcm_stride,
+                             int32_t len, const int32_t* d_status, const int32_t* h_eos, void* stream);
+/* Synchronises `stream`; afterwards available / read see everything pushed on it. */
+int snacb_egress_sync(snacb_egress* g, void* stream);
+int64_t snacb_egress_available(const snacb_egress* g, int32_t slot);
+/* Samples a push may still add to the slot before SNACB_ESTATE (ring full). */
+int64_t snacb_egress_room(const snacb_egress* g, int32_t slot);
+/* Up to max_samples unread samples of the slot into dst; returns the count (0 = nothing yet). */
+int64_t snacb_egress_read(snacb_egress* g, int32_t slot, int16_t* dst, int64_t max_samples);
+/* The stream ended without an eos chunk: the kept tail is emitted (synchronous). */
+int snacb_egress_flush(snacb_egress* g, int32_t slot, void* stream);
+/* Barge-in / slot reuse: drop unread samples and the kept tail (host-only and immediate, the device state follows with
+ * the slot's next push; no push of this slot may be in flight). */
+int snacb_egress_reset(snacb_egress* g, int32_t slot, void* stream);
+/* Samples written to the slot since its last reset (as of the last snacb_egress_sync). */
+int64_t snacb_egress_written(const snacb_egress* g, int32_t slot);
+/* One tick from host token buffers into the rings: snacb_decode_windows_host with the PCM going to slot h_slots[i] of
+ * `g` instead of a host matrix (H2D tokens -> kernels -> ring kernel -> D2H statuses, synchronous).  h_emitted (may be
+ * NULL) receives the samples window i added to its ring, or -1 when that ring had no room for a window: such a window
+ * is decoded to nowhere so that one stalled consumer cannot fail the tick of everybody else. */
+int snacb_decode_windows_to_ring(snacb_engine* e, snacb_egress* g, const int32_t* h_tokens, int32_t tokens_stride,
+                                 const int32_t* h_ntok, int32_t ntok_uniform, int32_t n_win, int32_t noise_mode, uint64_t seed,
+                                 const uint64_t* h_keys, const int32_t* h_slots, const int32_t* h_eos, int32_t* h_status,
+                                 int32_t* h_emitted, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -125,6 +125,21 @@ SIGNATURES = {
     "snacb_stitch_bank_destroy": (None, [_vp]),
     "snacb_stitch_bank_reset": (_i32, [_vp, _i32]),
     "snacb_stitch_bank_push": (_i32, [_vp, _i32, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp]),
+    # N3 on the GPU: pinned per-stream PCM rings written by the decode tick
+    "snacb_egress_create": (_i32, [C.POINTER(_vp), _i32, _i32, _i32, _i32, C.c_double]),
+    "snacb_egress_destroy": (None, [_vp]),
+    "snacb_egress_last_error": (C.c_char_p, [_vp]),
+    "snacb_egress_overlap_samples": (_i64, [_vp]),
+    "snacb_egress_ring_base": (_vp, [_vp, _i32]),
+    "snacb_egress_push_device": (_i32, [_vp, _i32, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "snacb_egress_sync": (_i32, [_vp, _vp]),
+    "snacb_egress_available": (_i64, [_vp, _i32]),
+    "snacb_egress_room": (_i64, [_vp, _i32]),
+    "snacb_egress_read": (_i64, [_vp, _i32, _vp, _i64]),
+    "snacb_egress_flush": (_i32, [_vp, _i32, _vp]),
+    "snacb_egress_reset": (_i32, [_vp, _i32, _vp]),
+    "snacb_egress_written": (_i64, [_vp, _i32]),
+    "snacb_decode_windows_to_ring": (_i32, [_vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _u64, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

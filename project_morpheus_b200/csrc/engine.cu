@@ -48,9 +48,11 @@ constexpr int kEncRates[4] = {2, 4, 8, 8};
 constexpr int kEncDim = 48;
 constexpr int kVqStrides[3] = {4, 2, 1};
 
-enum KClass { KC_DEINT = 0, KC_CODES, KC_DW, KC_SNAKE, KC_GEMM1, KC_CONVT, KC_TAIL, KC_RU, KC_COUNT };
+enum KClass { KC_DEINT = 0, KC_CODES, KC_DW, KC_SNAKE, KC_GEMM1, KC_CONVT, KC_TAIL, KC_RU, KC_RUW, KC_BLK, KC_COUNT };
 const char* const kClassName[KC_COUNT] = {"deinterleave", "from_codes", "dwconv_snake", "snake", "gemm_1x1",
-                                          "gemm_convt", "tail_pack", "block_ru_fused"};
+                                          "gemm_convt", "tail_pack", "ru_fused",  // one kernel per ResidualUnit (k_ru_tc / k_ru_x / k_ru_p)
+                                          "ru_fused_tmem",                      // k_ru_w: residual stream initialised in tensor memory
+                                          "block_fused_tail"};                  // k_blk_tail: 3 ResidualUnits + decoder tail in one kernel
 
 struct Prof {
   bool on = false;
@@ -489,7 +491,7 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
         u.sn_alpha = W.tail_alpha; u.sn_inv = W.tail_inv; u.tail_w7 = W.tail_w; u.tail_b = W.tail_b; u.tail_out = tail_out;
         u.status = d_status; u.wav = wav; u.pcm = pcm;
         const double smp = (double)n * tail_out.n();
-        ProfScope ps(e, KC_RU, 2.0 * el * B.Cout + el * 24.0 + smp * (2.0 * 448 + 4.0 * 64),
+        ProfScope ps(e, KC_BLK, 2.0 * el * B.Cout + el * 24.0 + smp * (2.0 * 448 + 4.0 * 64),
                      (double)n * B.ct.n() * B.Cout * 4.0 + smp * 2.0, st);
         ce = launch_blk_tc(g, u);
         tail_done = true;
@@ -503,14 +505,14 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
         const RuDev& R = Wb.ru[r];
         // block 1 (C = 256): fused persistent ResidualUnit kernel with the residual stream initialised in tensor memory
         if (ruw_tc_supported(B.Cout) && e->ruw && !(e->cfg.flags & (SNACB_FLAG_NO_RU_FUSION | SNACB_FLAG_PERSISTENT_RU | SNACB_FLAG_FUSE_RU256)) &&
-            n * (long long)B.r[r].n() >= 8 * 128 && e->tap_stage != sid + 4 + 2 * r) {
+            e->tap_stage != sid + 4 + 2 * r) {  // every tick size: a window's samples must not depend on its tick
           const bool last = (r == 2) && (b < 3);
           const bool want32 = !last;
           RuTcArgs u{X, cur, B.r[r], B.Cout, kDil[r], B.up_out, R.dw_w, R.dw_b, R.a1, R.i1, R.a2, R.i2, R.pw16, R.pw_b,
                      want32 ? Y : nullptr, last ? Anext : nullptr, last ? W.blk[b + 1].alpha : nullptr,
                      last ? W.blk[b + 1].inv : nullptr, 0, false};
           const double el = (double)n * B.r[r].n() * B.Cout;
-          ProfScope ps(e, KC_RU, 2.0 * el * B.Cout + el * 24.0,
+          ProfScope ps(e, KC_RUW, 2.0 * el * B.Cout + el * 24.0,
                        (double)n * cur.n() * B.Cout * 4.0 + el * ((want32 ? 4.0 : 0.0) + (last ? 2.0 : 0.0)), st);
           ce = launch_ruw_tc(g, u);
           tap(e, sid + 4 + 2 * r, Y, B.r[r], B.Cout, n, first, st);
@@ -1324,6 +1326,67 @@ int snacb_decode_windows_host(snacb_engine* e, const int32_t* h_tokens, int32_t 
   CU(e, cudaStreamSynchronize(st));
   if (!pcm_pinned) memcpy(h_pcm, hp + tok_b, (size_t)n_win * 4096);
   memcpy(h_status, hp + tok_b + pcm_b, (size_t)n_win * 4);
+  return SNACB_OK;
+}
+
+// N3 on the GPU: the tick's PCM goes from the decoder tail straight into the pinned per-stream rings of `g` (the ring
+// kernel crossfades consecutive chunks of a stream when an overlap is configured); only the statuses come back as a copy.
+int snacb_decode_windows_to_ring(snacb_engine* e, snacb_egress* g, const int32_t* h_tokens, int32_t tokens_stride,
+                                 const int32_t* h_ntok, int32_t ntok_uniform, int32_t n_win, int32_t noise_mode, uint64_t seed,
+                                 const uint64_t* h_keys, const int32_t* h_slots, const int32_t* h_eos, int32_t* h_status,
+                                 int32_t* h_emitted, void* stream) {
+  if (!e) return SNACB_EINVAL;
+  if (!g || n_win < 0 || !h_tokens || !h_slots || !h_status || noise_mode == SNACB_NOISE_TENSOR)
+    return fail(e, SNACB_EINVAL, "snacb_decode_windows_to_ring: bad argument (noise off / philox only)");
+  if (n_win == 0) return SNACB_OK;
+  std::vector<int32_t> slots(h_slots, h_slots + n_win);
+  std::vector<int64_t> before((size_t)n_win, 0);
+  for (int i = 0; i < n_win; ++i) {
+    if (slots[i] < 0) continue;
+    const int64_t room = snacb_egress_room(g, slots[i]);
+    if (room < 0) return fail(e, SNACB_EINVAL, "snacb_decode_windows_to_ring: slot %d out of range", slots[i]);
+    before[(size_t)i] = snacb_egress_written(g, slots[i]);
+    if (room < 2048) { slots[i] = -1; before[(size_t)i] = -1; }  // a stalled consumer: this window goes nowhere (h_emitted = -1)
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(e, cudaSetDevice(e->device));
+  const size_t tok_n = (size_t)n_win * tokens_stride * 4;
+  const size_t tok_b = pad256(tok_n), pcm_b = pad256((size_t)n_win * 4096), st_b = pad256((size_t)n_win * 4);
+  const size_t total = tok_b + pcm_b + st_b + pad256((size_t)n_win * 8) + 256;  // same block layout as the host call
+  if (total > e->pin_bytes) {
+    CU(e, cudaStreamSynchronize(st));
+    if (e->pin) CU(e, cudaFreeHost(e->pin));
+    e->pin_bytes = total + total / 2;
+    CU(e, cudaMallocHost((void**)&e->pin, e->pin_bytes));
+    ++e->gen;
+  }
+  if (total > e->dstage_bytes) {
+    CU(e, cudaDeviceSynchronize());
+    if (e->dstage) CU(e, cudaFree(e->dstage));
+    e->dstage_bytes = total + total / 2;
+    CU(e, cudaMalloc((void**)&e->dstage, e->dstage_bytes));
+    ++e->gen;
+  }
+  char* hp = e->pin; char* dp = e->dstage;
+  int32_t* d_tok = reinterpret_cast<int32_t*>(dp);
+  int16_t* d_pcm = reinterpret_cast<int16_t*>(dp + tok_b);
+  int32_t* d_st = reinterpret_cast<int32_t*>(dp + tok_b + pcm_b);
+  const void* src_tok = h_tokens;
+  if (!is_pinned(h_tokens)) { memcpy(hp, h_tokens, tok_n); src_tok = hp; }
+  CU(e, cudaMemcpyAsync(d_tok, src_tok, tok_n, cudaMemcpyHostToDevice, st));
+  int rc = snacb_decode_windows(e, d_tok, tokens_stride, h_ntok, ntok_uniform, n_win, noise_mode, nullptr, 0, seed, h_keys, d_pcm,
+                                d_st, stream);
+  if (rc) return rc;
+  rc = snacb_egress_push_device(g, n_win, slots.data(), d_pcm, 2048, 2048, d_st, h_eos, stream);
+  if (rc) return fail(e, rc, "snacb_decode_windows_to_ring: %s", snacb_egress_last_error(g));
+  ++e->launches;
+  CU(e, cudaMemcpyAsync(hp + tok_b + pcm_b, d_st, (size_t)n_win * 4, cudaMemcpyDeviceToHost, st));
+  rc = snacb_egress_sync(g, stream);
+  if (rc) return fail(e, rc, "snacb_decode_windows_to_ring: %s", snacb_egress_last_error(g));
+  memcpy(h_status, hp + tok_b + pcm_b, (size_t)n_win * 4);
+  if (h_emitted)
+    for (int i = 0; i < n_win; ++i)
+      h_emitted[i] = before[(size_t)i] < 0 ? -1 : (slots[i] < 0 ? 0 : (int32_t)(snacb_egress_written(g, slots[i]) - before[(size_t)i]));
   return SNACB_OK;
 }
 

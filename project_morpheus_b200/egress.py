@@ -118,6 +118,101 @@ class StitcherBank:
         return out, out_len, out_eos
 
 
+class GpuPcmRing:
+    """Pinned per-stream PCM rings the decode tick writes on the GPU (``csrc/egress_ring.cu``).
+
+    Replaces, for all streams of a tick at once, the reference's per-request chain stitcher -> ring buffer -> ``pull``
+    re-chunking (``orchestrator/stitcher.py:10-79``, ``orchestrator/ring_buffer.py:27-83``,
+    ``tts_engine/llama_local.py:120-150``): consecutive chunks of a slot are crossfaded by a kernel right after the decoder
+    tail (byte-identical to the reference's float64 overlap-add; ``overlap_ms = 0`` is plain concatenation, the server's
+    default) and written through the rings' device mapping; ``read`` is a cursor move and one memcpy out of pinned
+    memory.  Needs a CUDA device: there is no host fallback."""
+
+    def __init__(self, n_slots: int, ring_samples: int = 1 << 15, sample_rate: int = SAMPLE_RATE, overlap_ms: float = 0.0,
+                 device: int = 0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        rc = self._lib.snacb_egress_create(C.byref(self._h), int(device), int(n_slots), int(ring_samples), int(sample_rate),
+                                           float(overlap_ms))
+        if rc != _lib.OK:
+            raise _lib.SnacbError(f"snacb_egress_create failed ({rc}): needs a CUDA device, ring_samples a multiple of 8 "
+                                  f">= 4096 and 2 * overlap + 2048 <= ring_samples")
+        self.n_slots, self.ring_samples, self.device = int(n_slots), int(ring_samples), int(device)
+        self.overlap_samples = int(self._lib.snacb_egress_overlap_samples(self._h))
+        self._free = list(range(self.n_slots - 1, -1, -1))
+        self._scratch = bytearray(8192)
+        self._scratch_c = (C.c_char * len(self._scratch)).from_buffer(self._scratch)
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.snacb_egress_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def _check(self, rc: int, what: str) -> None:
+        if rc < 0:
+            raise _lib.SnacbError(f"{what} failed ({rc}): {self._lib.snacb_egress_last_error(self._h).decode(errors='replace')}")
+
+    # slot bookkeeping (one slot per live stream)
+    def acquire(self) -> int:
+        if not self._free:
+            raise _lib.SnacbError(f"GpuPcmRing: all {self.n_slots} slots are in use")
+        return self._free.pop()
+
+    def release(self, slot: int, stream: Optional[int] = None) -> None:
+        self.reset(slot, stream)
+        self._free.append(int(slot))
+
+    def push_device(self, slots, d_pcm_ptr: int, pcm_stride: int, length: int, d_status_ptr: Optional[int] = None, eos=None,
+                    stream: Optional[int] = None) -> None:
+        """Asynchronous: rows of a DEVICE int16 matrix join the rings (``sync`` before reading)."""
+        sl = np.ascontiguousarray(slots, dtype=np.int32)
+        eo = np.ascontiguousarray(eos, dtype=np.int32) if eos is not None else None
+        self._check(self._lib.snacb_egress_push_device(self._h, len(sl), sl.ctypes.data, d_pcm_ptr, int(pcm_stride), int(length),
+                                                       d_status_ptr, eo.ctypes.data if eo is not None else None, stream),
+                    "snacb_egress_push_device")
+
+    def sync(self, stream: Optional[int] = None) -> None:
+        self._check(self._lib.snacb_egress_sync(self._h, stream), "snacb_egress_sync")
+
+    def available(self, slot: int) -> int:
+        """Unread bytes of the slot."""
+        n = int(self._lib.snacb_egress_available(self._h, int(slot)))
+        self._check(n, "snacb_egress_available")
+        return 2 * n
+
+    def room(self, slot: int) -> int:
+        """Samples a tick may still add to the slot."""
+        n = int(self._lib.snacb_egress_room(self._h, int(slot)))
+        self._check(n, "snacb_egress_room")
+        return n
+
+    def read(self, slot: int, nbytes: int) -> bytes:
+        """Up to ``nbytes`` (rounded down to whole samples) of the slot's unread PCM."""
+        want = max(0, int(nbytes)) // 2
+        if want <= 0:
+            return b""
+        want = min(want, self.ring_samples)
+        if 2 * want > len(self._scratch):
+            self._scratch = bytearray(2 * want)
+            self._scratch_c = (C.c_char * len(self._scratch)).from_buffer(self._scratch)
+        got = int(self._lib.snacb_egress_read(self._h, int(slot), self._scratch_c, want))
+        self._check(got, "snacb_egress_read")
+        return bytes(memoryview(self._scratch)[: 2 * got])
+
+    def flush(self, slot: int, stream: Optional[int] = None) -> None:
+        """End of the stream without an eos chunk: the kept crossfade tail is emitted."""
+        self._check(self._lib.snacb_egress_flush(self._h, int(slot), stream), "snacb_egress_flush")
+
+    def reset(self, slot: int, stream: Optional[int] = None) -> None:
+        self._check(self._lib.snacb_egress_reset(self._h, int(slot), stream), "snacb_egress_reset")
+
+
 async def stitch_chunks(chunks: AsyncIterator[AudioChunk], *, sample_rate: int, overlap_ms: float = 0.0,
                         emit_markers: bool = False) -> AsyncGenerator[AudioChunk, None]:
     """Join ``chunks`` using overlap-add with optional marker propagation (reference signature and results)."""

@@ -229,6 +229,34 @@ class SnacEngine:
         self._check(rc, "snacb_decode_windows_host")
         return h_pcm.numpy(), h_st.numpy()
 
+    def decode_windows_to_ring(self, ring, tokens, slots: Sequence[int], ntok: Optional[Sequence[int]] = None,
+                               noise: NoiseArg = "philox", seed: int = 0, keys: Optional[Sequence[int]] = None,
+                               eos: Optional[Sequence[int]] = None) -> Tuple[np.ndarray, np.ndarray]:
+        """Host tick whose PCM goes straight into the pinned per-stream rings of ``ring`` (``egress.GpuPcmRing``): window i
+        joins the ring of ``slots[i]`` (-1 = discard).  Returns (status int32 [n], emitted int32 [n]): the samples window i
+        added to its ring (read them with ``ring.read(slot, nbytes)``), -1 where the ring had no room for a window (that
+        window is dropped, the rest of the tick is unaffected)."""
+        tok = np.ascontiguousarray(np.asarray(tokens, dtype=np.int32))
+        assert tok.ndim == 2
+        n, stride = tok.shape
+        mode = self._noise_mode(noise)
+        if mode == _lib.NOISE_TENSOR:
+            raise ValueError("decode_windows_to_ring: injected noise is not supported (use decode_windows)")
+        sl = np.ascontiguousarray(np.asarray(slots, dtype=np.int32))
+        assert sl.shape == (n,)
+        nt = np.ascontiguousarray(np.asarray(ntok, dtype=np.int32)) if ntok is not None else None
+        kp = np.ascontiguousarray(np.asarray(keys, dtype=np.uint64)) if keys is not None else None
+        eo = np.ascontiguousarray(np.asarray(eos, dtype=np.int32)) if eos is not None else None
+        st = np.empty(n, dtype=np.int32)
+        em = np.empty(n, dtype=np.int32)
+        with torch.cuda.device(self.device):
+            rc = self._lib.snacb_decode_windows_to_ring(
+                self._h, ring.handle, tok.ctypes.data, stride, nt.ctypes.data if nt is not None else None, stride, n, mode,
+                int(seed) & (2**64 - 1), kp.ctypes.data if kp is not None else None, sl.ctypes.data,
+                eo.ctypes.data if eo is not None else None, st.ctypes.data, em.ctypes.data, self._stream())
+        self._check(rc, "snacb_decode_windows_to_ring")
+        return st, em
+
     def submit_windows(self, tokens, ntok: Optional[Sequence[int]] = None, noise: NoiseArg = "philox", seed: int = 0,
                        keys: Optional[Sequence[int]] = None) -> int:
         """Pipelined host tick: enqueue H2D + kernels + D2H and return a ticket at once.  ``wait_windows(ticket)``

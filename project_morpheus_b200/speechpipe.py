@@ -148,6 +148,101 @@ def convert_to_audio_batch(windows: Sequence[Sequence[int]], noise=None, keys: O
     return out
 
 
+# ----------------------------------------------------------------------------- GPU egress rings (N3)
+_ring = None
+
+
+def get_ring():
+    """The process-wide :class:`~project_morpheus_b200.egress.GpuPcmRing` (created on first use): one pinned ring per live
+    stream that the decode tick fills on the GPU.  ``SNACB_RING_SLOTS`` (1024) streams x ``SNACB_RING_SAMPLES`` (32768 =
+    1.37 s) samples; ``SNACB_RING_OVERLAP_MS`` (0) crossfades consecutive windows of a stream like the reference's
+    stitcher does with a non-zero overlap."""
+    global _ring
+    if _ring is None:
+        from .egress import GpuPcmRing
+
+        _ring = GpuPcmRing(int(os.environ.get("SNACB_RING_SLOTS", "1024")), int(os.environ.get("SNACB_RING_SAMPLES", "32768")),
+                           overlap_ms=float(os.environ.get("SNACB_RING_OVERLAP_MS", "0")),
+                           device=torch.cuda.current_device() if snac_device == "cuda" else 0)
+    return _ring
+
+
+def convert_to_ring_batch(windows: Sequence[Sequence[int]], slots: Sequence[int], keys: Optional[np.ndarray] = None,
+                          errors: str = "none", ring=None) -> list:
+    """``convert_to_audio_batch`` with the PCM of window i appended to ring slot ``slots[i]`` on the GPU instead of being
+    returned: entry i is the number of PCM bytes the window added to its ring (4096 without crossfade, 0 for a single-frame
+    window) where ``convert_to_audio`` returns bytes, and ``None`` / an exception exactly where ``convert_to_audio_batch`` has them."""
+    n = len(windows)
+    if n == 0:
+        return []
+    ring = ring if ring is not None else get_ring()
+    lens = [len(w) for w in windows]
+    stride = max(TOKENS_PER_FRAME, max(lens))
+    tokens = np.zeros((n, stride), dtype=np.int32)
+    overflow = set()
+    for i, w in enumerate(windows):
+        if lens[i]:
+            row = _as_int32(w)
+            if row is None:
+                if lens[i] >= TOKENS_PER_FRAME:
+                    overflow.add(i)
+                lens[i] = 0
+            else:
+                tokens[i, : lens[i]] = row
+    uniform = len(set(lens)) == 1 and lens[0] >= TOKENS_PER_FRAME
+    mode = noise_mode if noise_mode in ("philox", "off") else "philox"
+    if mode == "philox" and keys is None:
+        keys = np.asarray([ticker_mod.window_key(0, next(_call_counter)) for _ in range(n)], dtype=np.uint64)
+    eng = model.engine
+
+    def run():
+        return eng.decode_windows_to_ring(ring, tokens, slots, ntok=None if uniform else lens, noise=mode, seed=model.noise_seed,
+                                          keys=keys if mode == "philox" else None)
+
+    if cuda_stream is not None:
+        with torch.cuda.stream(cuda_stream):
+            status, emitted = run()
+    else:
+        status, emitted = run()
+    out: list = []
+    for i in range(n):
+        st = int(status[i])
+        if i in overflow:
+            out.append(RuntimeError("value cannot be converted to type int32 without overflow") if errors == "values" else None)
+        elif st == _lib.WIN_CODE4096:
+            out.append(IndexError("index out of range in self") if errors == "values" else None)
+        elif st == _lib.WIN_OK and emitted[i] < 0:
+            # no room in that slot: the window was decoded to nowhere, an error of that stream alone (adapters never get
+            # here: their pump stops at a high-water mark)
+            out.append(BufferError("PCM ring slot is full: read it before decoding more") if errors == "values" else None)
+        elif st == _lib.WIN_OK:
+            out.append(2 * int(emitted[i]))  # 4096, or what the crossfade released when an overlap is configured
+        elif st == _lib.WIN_EMPTY:
+            out.append(0)
+        else:
+            out.append(_finish(None, st))  # None (+ the NONFINITE log line)
+    return out
+
+
+def _tick(windows, keys, slots=None):
+    """One decode tick of the shared ticker: ring-bound windows (slot >= 0) and plain ones, each kind in one engine call."""
+    if slots is None:
+        return convert_to_audio_batch(windows, keys=keys, errors="values")
+    to_ring = [i for i, s in enumerate(slots) if s >= 0]
+    plain = [i for i, s in enumerate(slots) if s < 0]
+    out: list = [None] * len(windows)
+    if to_ring:
+        res = convert_to_ring_batch([windows[i] for i in to_ring], [slots[i] for i in to_ring],
+                                    keys=None if keys is None else keys[to_ring], errors="values")
+        for i, r in zip(to_ring, res):
+            out[i] = r
+    if plain:
+        res = convert_to_audio_batch([windows[i] for i in plain], keys=None if keys is None else keys[plain], errors="values")
+        for i, r in zip(plain, res):
+            out[i] = r
+    return out
+
+
 # ----------------------------------------------------------------------------- the shared decode ticker
 USE_TICKER = os.environ.get("SNACB_TICKER", "1") != "0"
 _ticker: Optional["ticker_mod.DecodeTicker"] = None
@@ -157,7 +252,7 @@ def get_ticker() -> "ticker_mod.DecodeTicker":
     """The process-wide ticker every ``tokens_decoder`` coroutine decodes through (created on first use)."""
     global _ticker
     if _ticker is None:
-        _ticker = ticker_mod.DecodeTicker(lambda windows, keys: convert_to_audio_batch(windows, keys=keys, errors="values"))
+        _ticker = ticker_mod.DecodeTicker(lambda *a: _tick(*a))  # late-bound: tests swap the batch functions
     return _ticker
 
 
@@ -167,14 +262,16 @@ from .tokens import (  # noqa: E402,F401  (re-exported: same names as the refere
 )
 
 
-async def tokens_decoder(token_gen: AsyncIterator[str], *, stream_key: Optional[int] = None, ticker=None):
+async def tokens_decoder(token_gen: AsyncIterator[str], *, stream_key: Optional[int] = None, ticker=None,
+                         ring_slot: Optional[int] = None):
     """Token strings in, PCM chunks out; same windows, order and chunk sizes as the reference.
 
     Additive keywords: ``stream_key`` seeds this stream's NoiseBlock noise (window w of the stream uses the Philox key
     ``window_key(stream_key, w)``; default: a fresh key per stream); ``ticker`` overrides the shared
     :class:`~project_morpheus_b200.ticker.DecodeTicker` (``False`` = decode each window on its own, like the
     reference).  With the ticker, the windows of all concurrently running ``tokens_decoder`` coroutines of the event
-    loop go to the GPU as one batch per tick."""
+    loop go to the GPU as one batch per tick.  ``ring_slot``: the PCM is appended to that slot of ``get_ring()`` by the
+    GPU and the generator yields byte COUNTS (4096 / 0) in place of the bytes (``SnacB200Adapter(gpu_ring=True)``)."""
     plan = WindowPlanner()
     key = ticker_mod.fresh_stream_key() if stream_key is None else int(stream_key)
     tk = get_ticker() if (ticker is None and USE_TICKER) else (ticker or None)
@@ -184,9 +281,12 @@ async def tokens_decoder(token_gen: AsyncIterator[str], *, stream_key: Optional[
         nonlocal n_windows
         wkey = ticker_mod.window_key(key, n_windows)
         n_windows += 1
-        if tk is not None:
-            return await tk.decode(list(window), wkey)  # raises what convert_to_audio would raise, in this stream only
-        out = convert_to_audio_batch([window], keys=np.asarray([wkey], dtype=np.uint64), errors="values")[0]
+        if tk is not None:  # raises what convert_to_audio would raise, in this stream only
+            return await (tk.decode(list(window), wkey) if ring_slot is None else tk.decode(list(window), wkey, ring_slot))
+        if ring_slot is None:
+            out = convert_to_audio_batch([window], keys=np.asarray([wkey], dtype=np.uint64), errors="values")[0]
+        else:
+            out = convert_to_ring_batch([window], [ring_slot], keys=np.asarray([wkey], dtype=np.uint64), errors="values")[0]
         if isinstance(out, BaseException):
             raise out
         return out
@@ -204,6 +304,10 @@ async def tokens_decoder(token_gen: AsyncIterator[str], *, stream_key: Optional[
         audio_samples = await decode(window)
         if audio_samples is not None:
             yield audio_samples
+    if ring_slot is not None and get_ring().overlap_samples > 0:
+        before = get_ring().available(ring_slot)
+        get_ring().flush(ring_slot)  # the crossfade tail kept from the last window
+        yield get_ring().available(ring_slot) - before
 
 
 async def tokens_decoder_sync(syn_token_gen):

@@ -25,7 +25,7 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-BatchDecode = Callable[[List[Sequence[int]], Optional[np.ndarray]], List[Optional[bytes]]]
+BatchDecode = Callable[..., List[Optional[bytes]]]  # (windows, keys[, slots]) -> one entry per window
 
 _SPLITMIX = (0x9E3779B97F4A7C15, 0xBF58476D1CE4E5B9, 0x94D049BB133111EB)
 _MASK = (1 << 64) - 1
@@ -64,8 +64,10 @@ class DecodeTicker:
         self.max_batch = int(max_batch)
         self.in_thread = in_thread
         self.settle_turns = max(0, int(settle_turns))
-        self._pending: List[Tuple[Sequence[int], int, asyncio.Future]] = []
+        self._pending: List[Tuple[Sequence[int], int, asyncio.Future, Optional[int]]] = []
         self._wake: Optional[asyncio.Event] = None
+        self._idle: Optional[asyncio.Event] = None  # set whenever no tick is on the GPU
+        self._inflight: set = set()                 # ring slots the running tick writes to
         self._task: Optional[asyncio.Task] = None
         self._loop: Optional[asyncio.AbstractEventLoop] = None
         self.ticks = 0
@@ -73,23 +75,43 @@ class DecodeTicker:
         self.max_tick = 0
 
     # ------------------------------------------------------------------ client side
-    async def decode(self, window: Sequence[int], key: int = 0) -> Optional[bytes]:
-        """What ``convert_to_audio(window, _)`` returns, decoded together with every other pending window."""
+    async def decode(self, window: Sequence[int], key: int = 0, slot: Optional[int] = None):
+        """What ``convert_to_audio(window, _)`` returns, decoded together with every other pending window.
+
+        ``slot``: the window's PCM goes to that slot of the GPU egress ring instead of coming back as bytes (the result is
+        then the byte count).  A caller that is cancelled while its window is queued or on the GPU must ``await
+        forget(slot)`` before the slot is reset or re-used."""
         loop = asyncio.get_running_loop()
         if self._loop is not loop:  # first use on this loop (or the previous loop is gone): (re)start the ticker task
             self._bind(loop)
         fut: asyncio.Future = loop.create_future()
-        self._pending.append((window, key, fut))
+        self._pending.append((window, key, fut, slot))
         self._wake.set()
         return await fut
 
+    async def forget(self, slot: int) -> None:
+        """Drop the queued windows of ``slot`` and wait until no tick that writes to it is on the GPU."""
+        keep = []
+        for p in self._pending:
+            if p[3] == slot:
+                if not p[2].done():
+                    p[2].cancel()
+            else:
+                keep.append(p)
+        self._pending = keep
+        while slot in self._inflight and self._idle is not None and asyncio.get_running_loop() is self._loop:
+            await self._idle.wait()
+
     def _bind(self, loop: asyncio.AbstractEventLoop) -> None:
-        for _, _, fut in self._pending:  # requests of a dead loop can never be answered
+        for _, _, fut, _ in self._pending:  # requests of a dead loop can never be answered
             if not fut.done():
                 fut.cancel()
         self._pending = []
         self._loop = loop
         self._wake = asyncio.Event()
+        self._idle = asyncio.Event()
+        self._idle.set()
+        self._inflight = set()
         self._task = loop.create_task(self._run(), name="snacb-decode-ticker")
 
     # ------------------------------------------------------------------ ticker task
@@ -105,18 +127,26 @@ class DecodeTicker:
                 batch, self._pending = self._pending[: self.max_batch], self._pending[self.max_batch:]
                 windows = [b[0] for b in batch]
                 keys = np.asarray([b[1] & _MASK for b in batch], dtype=np.uint64)
+                args = (windows, keys)
+                if any(b[3] is not None for b in batch):  # ring-bound windows: the batch function also gets the slots
+                    args = (windows, keys, [-1 if b[3] is None else int(b[3]) for b in batch])
+                    self._inflight = {b[3] for b in batch if b[3] is not None}
+                    self._idle.clear()
                 try:
                     if self.in_thread:
-                        out = await asyncio.to_thread(self._decode, windows, keys)
+                        out = await asyncio.to_thread(self._decode, *args)
                     else:
-                        out = self._decode(windows, keys)
+                        out = self._decode(*args)
                     err = None
                 except BaseException as e:  # noqa: BLE001 - handed to every waiter of the tick
                     out, err = None, e
+                if self._inflight:
+                    self._inflight = set()
+                    self._idle.set()
                 self.ticks += 1
                 self.windows += len(batch)
                 self.max_tick = max(self.max_tick, len(batch))
-                for i, (_, _, fut) in enumerate(batch):
+                for i, (_, _, fut, _) in enumerate(batch):
                     if fut.done():
                         continue
                     if err is not None:

@@ -415,11 +415,15 @@ def test_cuda_path_matches_committed_g4_golden_pcm(engines, precision):
     assert np.allclose(rms, g4["rms"], rtol=2e-3, atol=1.0)
 
 
-def test_concurrent_adapters_batch_through_the_ticker_on_gpu(state_dict_w1, monkeypatch):
+@pytest.mark.parametrize("gpu_ring", [False, True])
+def test_concurrent_adapters_batch_through_the_ticker_on_gpu(state_dict_w1, monkeypatch, gpu_ring):
     """north_star: concurrent streams are batched into one launch per tick BEHIND the untouched orchestrator.  64
     requests, one adapter + one orchestrator-style pull loop each (orchestrator/core.py:89-117) under one event loop:
-    bytes identical to the per-stream path (noise off), and the engine saw ticks, not windows."""
+    bytes identical to the per-stream path (noise off), and the engine saw ticks, not windows.  ``gpu_ring``: the
+    tick's PCM waits for ``pull`` in pinned per-stream rings written by the GPU (N3) instead of Python bytes."""
     monkeypatch.setenv("SNACB_NOISE", "off")
+    monkeypatch.setenv("SNACB_GPU_RING", "1" if gpu_ring else "0")
+    monkeypatch.setenv("SNACB_RING_SLOTS", "64")
     monkeypatch.setenv("SNACB_PRECISION", "fp16")
     monkeypatch.setenv("SNACB_RANDOM_INIT", "0:w1")
     monkeypatch.delenv("ORPHEUS_SNAC_PATH", raising=False)
@@ -453,16 +457,24 @@ def test_concurrent_adapters_batch_through_the_ticker_on_gpu(state_dict_w1, monk
         return await asyncio.gather(*[pull_loop(a, i) for i, a in enumerate(ads)])
 
     eng = speechpipe.model.engine
-    calls = {"n": 0}
-    real_decode = eng.decode_windows
+    calls = {"n": 0, "ring": 0}
+    real_decode, real_ring = eng.decode_windows, eng.decode_windows_to_ring
 
     def counting(*a, **kw):
         calls["n"] += 1
         return real_decode(*a, **kw)
 
+    def counting_ring(*a, **kw):
+        calls["ring"] += 1
+        return real_ring(*a, **kw)
+
     monkeypatch.setattr(eng, "decode_windows", counting)
+    monkeypatch.setattr(eng, "decode_windows_to_ring", counting_ring)
     got = asyncio.run(main())
-    batched_calls = calls["n"]
+    batched_calls = calls["ring"] if gpu_ring else calls["n"]
+    assert (calls["n"] == 0) if gpu_ring else (calls["ring"] == 0)
+    if gpu_ring:
+        assert len(speechpipe.get_ring()._free) == 64  # every slot came back when its stream was delivered
     st = speechpipe.get_ticker().stats()
     assert st["ticks"] * 8 < st["windows"] and st["max_tick"] >= n // 2, st
 

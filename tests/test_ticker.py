@@ -31,6 +31,42 @@ def fake_convert(window):
     return (h * 128)[:4096]
 
 
+class FakeGpuRing:
+    """Host stand-in with the interface of egress.GpuPcmRing (the real one needs a CUDA device; GPU tests cover it)."""
+
+    overlap_samples = 0
+    ring_samples = 1 << 15
+
+    def __init__(self, n):
+        self.bufs = [bytearray() for _ in range(n)]
+        self._free = list(range(n - 1, -1, -1))
+
+    def acquire(self):
+        return self._free.pop()
+
+    def release(self, slot):
+        self.reset(slot)
+        self._free.append(slot)
+
+    def available(self, slot):
+        return len(self.bufs[slot])
+
+    def room(self, slot):
+        return self.ring_samples - len(self.bufs[slot]) // 2
+
+    def read(self, slot, nbytes):
+        n = min(nbytes // 2 * 2, len(self.bufs[slot]) // 2 * 2)
+        out = bytes(self.bufs[slot][:n])
+        del self.bufs[slot][:n]
+        return out
+
+    def reset(self, slot):
+        self.bufs[slot].clear()
+
+    def flush(self, slot):
+        pass
+
+
 @pytest.fixture()
 def speechpipe(monkeypatch):
     """The product module on a CPU host, its engine call replaced by a deterministic stand-in that records every call."""
@@ -50,9 +86,26 @@ def speechpipe(monkeypatch):
                 out.append(fake_convert(w))
         return out
 
+    ring = FakeGpuRing(128)
+
+    def fake_ring_batch(windows, slots, keys=None, errors="none", ring_=None):
+        calls.append((len(windows), None if keys is None else [int(k) for k in keys]))
+        out = []
+        for w, sl in zip(windows, slots):
+            r = fake_batch([w], keys=None if keys is None else keys[:1], errors=errors)[0]
+            calls.pop()
+            if isinstance(r, bytes):
+                ring.bufs[sl] += r
+                r = len(r)
+            out.append(r)
+        return out
+
     monkeypatch.setattr(mod, "convert_to_audio_batch", fake_batch)
+    monkeypatch.setattr(mod, "convert_to_ring_batch", fake_ring_batch)
+    monkeypatch.setattr(mod, "get_ring", lambda: ring)
     monkeypatch.setattr(mod, "_ticker", None)
     mod.calls = calls
+    mod.fake_ring = ring
     yield mod
     sys.modules.pop("project_morpheus_b200.speechpipe", None)
 
@@ -251,3 +304,44 @@ def test_ticker_survives_a_new_event_loop():
     for _ in range(3):
         assert asyncio.run(t.decode(w, 1)) == fake_convert(w)
     assert t.ticks == 3
+
+
+def test_adapters_over_gpu_ring_slots(speechpipe):
+    """N3: with gpu_ring the decoder yields byte counts and the PCM waits in a ring slot (here a host stand-in): same
+    bytes as the per-stream path for even AND odd pull sizes, ticks not windows, ring-bound and plain windows share a
+    tick, slots are returned at eos and at reset."""
+    n = 40
+    streams = [sp.synth_token_strings(500 + i, 4 + (i % 7)) for i in range(n)]
+    want = [b"".join(sp.decode_stream(s, fake_convert)) for s in streams]
+
+    async def pull_loop(ad, size):
+        out = bytearray()
+        while True:
+            c = await ad.pull(size)
+            assert len(c.pcm) == size or c.eos or not c.pcm
+            out += c.pcm
+            if c.eos:
+                return bytes(out)
+
+    async def main():
+        ads = [SnacB200Adapter("p", token_source=_source(s, gap=5), seed=i, gpu_ring=(i % 4 != 3)) for i, s in enumerate(streams)]
+        return await asyncio.gather(*[pull_loop(a, (333, 64, 4096, 1001)[i % 4]) for i, a in enumerate(ads)])
+
+    got = asyncio.run(main())
+    assert got == want
+    st = speechpipe.get_ticker().stats()
+    assert len(speechpipe.calls) >= st["ticks"] and st["ticks"] * 6 < st["windows"], st   # <= 2 engine calls per mixed tick
+    assert len(speechpipe.calls) <= 2 * st["ticks"]
+    assert len(speechpipe.fake_ring._free) == 128 and all(not b for b in speechpipe.fake_ring.bufs)
+
+    async def barge():
+        ad = SnacB200Adapter("p", token_source=_source(streams[0], gap=1), seed=0, gpu_ring=True)
+        first = await ad.pull(100)
+        assert len(speechpipe.fake_ring._free) == 127
+        await ad.reset()
+        assert len(speechpipe.fake_ring._free) == 128
+        return first.pcm, await pull_loop(ad, 777)
+
+    first, again = asyncio.run(barge())
+    assert first == want[0][:100] and again == want[0]
+    assert len(speechpipe.fake_ring._free) == 128
