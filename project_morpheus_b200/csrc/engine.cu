@@ -109,6 +109,7 @@ struct snacb_engine {
   int prefetch_ahead = 0;  // SM count when L2 prefetch-ahead is on (SNACB_PREFETCH env, default on)
   bool ru256 = false;      // decoder block 1 (C = 256) ResidualUnits through the persistent fused kernel (SNACB_RU256 env)
   bool ruw = true;         // decoder block 1 ResidualUnits through k_ru_w (SNACB_RUW=0 falls back to k_dw_tc + k_gemm_ws)
+  bool ruw128 = true;      // decoder block 2 ResidualUnits through k_ru_w<128> (SNACB_RUW128=0 falls back to k_ru_tc<128>)
   // CUDA graphs of small host-API ticks (latency mode): key -> instantiated graph
   struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t gen = 0; int calls = 0; bool disabled = false; };
   std::map<std::vector<long long>, GraphEntry> graphs;
@@ -504,7 +505,7 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
       for (int r = 0; r < 3 && ce == cudaSuccess; ++r) {
         const RuDev& R = Wb.ru[r];
         // block 1 (C = 256): fused persistent ResidualUnit kernel with the residual stream initialised in tensor memory
-        if (ruw_tc_supported(B.Cout) && e->ruw && !(e->cfg.flags & (SNACB_FLAG_NO_RU_FUSION | SNACB_FLAG_PERSISTENT_RU | SNACB_FLAG_FUSE_RU256)) &&
+        if (ruw_tc_supported(B.Cout) && e->ruw && (B.Cout != 128 || e->ruw128) && !(e->cfg.flags & (SNACB_FLAG_NO_RU_FUSION | SNACB_FLAG_PERSISTENT_RU | SNACB_FLAG_FUSE_RU256)) &&
             e->tap_stage != sid + 4 + 2 * r) {  // every tick size: a window's samples must not depend on its tick
           const bool last = (r == 2) && (b < 3);
           const bool want32 = !last;
@@ -775,6 +776,8 @@ int snacb_create(snacb_engine** out, const snacb_config* cfg) {
     e->ru256 = r2 && r2[0] == '1';
     const char* rw = getenv("SNACB_RUW");
     e->ruw = !(rw && rw[0] == '0');
+    const char* rw2 = getenv("SNACB_RUW128");
+    e->ruw128 = !(rw2 && rw2[0] == '0');
     const char* gr = getenv("SNACB_GRAPHS");
     if (gr) e->graph_max_win = atoi(gr);  // 0 disables the CUDA-graph path
   }

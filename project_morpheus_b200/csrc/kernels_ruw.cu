@@ -11,13 +11,14 @@
 //                         a two-stage ring
 //   workers (16 warps)    depthwise units out of shared memory (Snake -> k7 -> Snake), fp16 operand k-block written in
 //                         the tcgen05 SWIZZLE_128B layout
-//   init (4 warps)        the tile's OWN rows of the block go from shared memory straight into TENSOR MEMORY
-//                         (row per lane, conflict-free thanks to the swizzle, tcgen05.st): the accumulator starts as x
+//   init (4 warps)        the tile's OWN rows of the block (+ the 1x1 conv's bias) go from shared memory straight into
+//                         TENSOR MEMORY (row per lane, conflict-free thanks to the swizzle, tcgen05.st): the accumulator
+//                         starts as x + b
 //   MMA (1 thread)        once the four blocks are in: D += A W^T, k-block by k-block (N = 256) - the residual add is
 //                         the accumulate flag
-//   epilogue (8 warps)    D + b -> fp32 x' (and, for the block's last unit, the next block's Snake -> fp16 operand),
-//                         row per lane, 64 bytes per lane and step; two accumulators (2 x 256 TMEM columns) let it
-//                         drain tile i while tile i+1 is being built
+//   epilogue (4 warps)    D -> fp32 x' (or, for the block's last unit, the next block's Snake -> fp16 operand): row per
+//                         lane from tensor memory into swizzled staging tiles, out through TMA tensor stores; two
+//                         accumulators (2 x C TMEM columns) let it drain tile i while tile i+1 is being built
 #include <cstdlib>
 
 #include "snacb.h"
@@ -26,9 +27,8 @@
 namespace snacb {
 namespace {
 
-constexpr int kRwC = 256;
-constexpr int kRwKB = kRwC / 64;        // k-blocks of the 1x1 GEMM
-constexpr int kRwNB = kRwC / 32;        // 32-channel input blocks per tile (one TMA box each)
+// C = 256 (decoder block 1) and C = 128 (block 2): C / 64 k-blocks of the 1x1 GEMM, C / 32 input blocks per tile (one TMA
+// box of 32 channels each)
 // Two worker groups of nine warps; group g builds the blocks b with b % 2 == g; the input ring (block counter % stages)
 // keeps the next block of each group in flight while it computes.  One depthwise unit of <= 9 outputs per thread and block:
 // 16 channel pairs x up to 18 units.
@@ -41,27 +41,31 @@ struct RwDev {
   const float* w7; const float* dw_b; const float* a1; const float* i1; const float* a2; const float* i2; const float* pw_b;
   float* out32; __half* out16; const float* sn_alpha; const float* sn_inv;
   int tiles_per_item, total_tiles;
-  int dbg;  // SNACB_RUW_DBG bits (profiling experiments): 1 workers skip the units, 2 init skips the copy, 4 epilogue skips the stores
+  int dbg;  // SNACB_RUW_DBG bits (profiling experiments): 1 workers skip the units, 2 init skips the copy, 4 epilogue skips the stores, 8 no Snake in the fp16 epilogue
 };
 
-template <int DIL> struct RwSmem {
+template <int C, int DIL> struct RwSmem {
   static constexpr int kBoxRows = BM + 6 * DIL;
   // [rows][32 ch] fp32, 128-byte rows (SWIZZLE_128B: the pattern is a function of the ADDRESS, so every box starts on
   // a 1024-byte boundary and the 16-byte chunk of (row, c) is (c/4) ^ (row % 8))
   static constexpr int kXBytes = (kBoxRows * 128 + 1023) / 1024 * 1024;
-  static constexpr int kABytes = BM * kRwC * 2;                // whole-K operand tile: 4 k-blocks of [128][128 B]
-  static constexpr int kWStage = kRwC * BK * 2;                // [256 n][64 k] fp16
+  static constexpr int kABytes = BM * C * 2;                   // whole-K operand tile: C / 64 k-blocks of [128][128 B]
+  static constexpr int kWStage = C * BK * 2;                   // [C n][64 k] fp16
   // Input ring: FOUR stages, so stage s always belongs to worker group s % 2.  (An odd depth hands a stage to the
   // groups alternately; a group then skips every other use of its barrier and its parity wait can pass two uses early -
-  // found the hard way.)  The 182-row boxes of dilation 9 leave room for only one weight stage.
+  // found the hard way.)  At C = 256 there is room for only one weight stage (64-channel slice of W, 32 KB).
   static constexpr int kStages = 4;
-  static constexpr int kWStages = (DIL == 9) ? 1 : 2;
+  static constexpr int kWStages = (C == 256) ? 1 : 2;
+  // Epilogue staging tiles: the TMA store of slab i reads its tile while slab i+1 is written into the next one.  (With a
+  // single tile every slab waited out the previous store: 8 slabs x ~1 us per tile made the epilogue, not the depthwise
+  // workers, the bound of the kernel.)
+  static constexpr int kOutBufs = (C == 256) ? 2 : 4;
   static constexpr int kOutBytes = BM * 128;                   // epilogue staging: [128 rows][128 B], SWIZZLE_128B, TMA store
   static constexpr int kOffX = 0;
   static constexpr int kOffA = kStages * kXBytes;
   static constexpr int kOffW = kOffA + kABytes;
   static constexpr int kOffOut = kOffW + kWStages * kWStage;
-  static constexpr int kOffBar = kOffOut + kOutBytes;
+  static constexpr int kOffBar = kOffOut + kOutBufs * kOutBytes;
   static constexpr int kBytes = kOffBar + 256;
   static_assert(kBytes <= 227 * 1024, "shared memory");
 };
@@ -105,12 +109,12 @@ __device__ __forceinline__ bool rw_unit(int u, int& first, int& len) {
   return u < 18;
 }
 
-template <int DIL>
+template <int CC, int DIL>
 __global__ void __launch_bounds__(kRwThreads, 1) k_ru_w(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                                                         const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
                                                         const RwDev a) {
-  using S = RwSmem<DIL>;
-  constexpr int C = kRwC;
+  using S = RwSmem<CC, DIL>;
+  constexpr int C = CC, kRwKB = C / 64, kRwNB = C / 32;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sX = smem + S::kOffX;   // [4 stages][rows][128 B]
   uint8_t* sA = smem + S::kOffA;   // [4 k-blocks][128 rows][128 B]
@@ -231,8 +235,10 @@ __global__ void __launch_bounds__(kRwThreads, 1) k_ru_w(const __grid_constant__ 
           uint32_t r[16];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint4 v = *reinterpret_cast<const uint4*>(rp + ((((g * 4 + j) ^ row) & 7) << 4));
-            r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
+            const float4 v = *reinterpret_cast<const float4*>(rp + ((((g * 4 + j) ^ row) & 7) << 4));
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.pw_b + b * 32 + g * 16 + 4 * j));
+            r[4 * j] = __float_as_uint(v.x + b4.x); r[4 * j + 1] = __float_as_uint(v.y + b4.y);
+            r[4 * j + 2] = __float_as_uint(v.z + b4.z); r[4 * j + 3] = __float_as_uint(v.w + b4.w);
           }
           asm volatile(
               "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -312,6 +318,11 @@ __global__ void __launch_bounds__(kRwThreads, 1) k_ru_w(const __grid_constant__ 
     const int et = tid - (2 + kRwInit + kRwWorkers) * 32;  // 0..127
     const bool half_out = a.out16 != nullptr;               // the block's last unit emits the fp16 operand only
     const int cols_per_store = half_out ? 64 : 32;
+    // 16-byte chunk c of this thread's staging row sits at swz[c] (SWIZZLE_128B)
+    int swz[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) swz[c] = ((c ^ trow) & 7) << 4;
+    int slab = 0;
     for (int ti = 0; ti < n_my; ++ti) {
       const int tb = ti & 1;
       const int lin = blockIdx.x + ti * gridDim.x;
@@ -319,41 +330,53 @@ __global__ void __launch_bounds__(kRwThreads, 1) k_ru_w(const __grid_constant__ 
       const ItemRef it = get_item(a.items, a.base, item, a.out_len);
       const int t_abs = a.out_lo + row0 + trow + it.shift0 * a.up;
       const bool live = t_abs >= 0 && t_abs < a.T0 * a.up;
+      const bool all_live = __all_sync(0xffffffffu, live);  // the usual case: no masking instructions at all
       mbar_wait(bar(T_FULL + tb), (ti >> 1) & 1, 800);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(hq * 32) << 16) + (uint32_t)(tb * C);
-      uint8_t* rowp = sOut + trow * 128;
-      for (int c0 = 0; c0 < C; c0 += cols_per_store) {
+      for (int c0 = 0; c0 < C; c0 += cols_per_store, ++slab) {
         if (a.dbg & 4) break;
-        // the previous store has finished READING the staging tile
-        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        uint8_t* stage = sOut + (slab % S::kOutBufs) * S::kOutBytes;
+        uint8_t* rowp = stage + trow * 128;
+        // the store that last used this staging tile (kOutBufs slabs ago) has finished READING it
+        if (et == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(S::kOutBufs - 1) : "memory");
         asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll 1
-        for (int g = 0; g < cols_per_store / 16; ++g) {
-          const int col = c0 + g * 16;
-          uint32_t r[16];
-          tmem_ld16(taddr + col, r);
-          float4 x[4];
+        if (!half_out) {
+          // fp32: the accumulator already holds x + b + W s: 32 columns = 8 chunks straight from tensor memory to the
+          // staging row (the bias went in with the init, rows outside the sequence are zeroed only where there are any)
+          uint32_t r0[16], r1[16];
+          tmem_ld16_nowait(taddr + c0, r0);
+          tmem_ld16_nowait(taddr + c0 + 16, r1);
+          tmem_ld_wait();
+          if (!all_live && !live) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { r0[j] = 0u; r1[j] = 0u; }
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.pw_b + col + 4 * j));
-            x[j] = make_float4(__uint_as_float(r[4 * j]) + b4.x, __uint_as_float(r[4 * j + 1]) + b4.y,
-                               __uint_as_float(r[4 * j + 2]) + b4.z, __uint_as_float(r[4 * j + 3]) + b4.w);
-            if (!live) x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<uint4*>(rowp + swz[j]) = make_uint4(r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]);
+            *reinterpret_cast<uint4*>(rowp + swz[4 + j]) = make_uint4(r1[4 * j], r1[4 * j + 1], r1[4 * j + 2], r1[4 * j + 3]);
           }
-          if (!half_out) {  // fp32: 4 chunks of 16 bytes per 16 columns, chunk index g*4 + j of the 128-byte row
+        } else {
+          // fp16 (the next block's Snake applied): 64 columns = 8 chunks of 8 halves
 #pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(rowp + ((((g * 4 + j) ^ trow) & 7) << 4)) = x[j];
-          } else {          // fp16 (Snake'd): 2 chunks per 16 columns, chunk index g*2 + j/2
+          for (int g = 0; g < 4; ++g) {
+            const int col = c0 + g * 16;
+            uint32_t r[16];
+            tmem_ld16(taddr + col, r);
+            float4 x[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              if (a.sn_alpha) {
+              x[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                 __uint_as_float(r[4 * j + 3]));
+              if (a.sn_alpha && !(a.dbg & 8)) {
                 const float4 al = __ldg(reinterpret_cast<const float4*>(a.sn_alpha + col + 4 * j));
                 const float4 iv = __ldg(reinterpret_cast<const float4*>(a.sn_inv + col + 4 * j));
                 const float2 lo = snake2(make_float2(x[j].x, x[j].y), make_float2(al.x, al.y), make_float2(iv.x, iv.y));
                 const float2 hi = snake2(make_float2(x[j].z, x[j].w), make_float2(al.z, al.w), make_float2(iv.z, iv.w));
                 x[j] = make_float4(lo.x, lo.y, hi.x, hi.y);
               }
+              if (!live) x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -362,7 +385,7 @@ __global__ void __launch_bounds__(kRwThreads, 1) k_ru_w(const __grid_constant__ 
               uint4 pk;
               pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
               pk.z = *reinterpret_cast<const uint32_t*>(&h2); pk.w = *reinterpret_cast<const uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(rowp + ((((g * 2 + j) ^ trow) & 7) << 4)) = pk;
+              *reinterpret_cast<uint4*>(rowp + swz[g * 2 + j]) = pk;
             }
           }
         }
@@ -372,7 +395,7 @@ __global__ void __launch_bounds__(kRwThreads, 1) k_ru_w(const __grid_constant__ 
           const CUtensorMap* tm = half_out ? &tmO16 : &tmO32;
           asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
                            reinterpret_cast<uint64_t>(tm)),
-                       "r"(smem_u32(sOut)), "r"(c0), "r"(row0), "r"(item)
+                       "r"(smem_u32(stage)), "r"(c0), "r"(row0), "r"(item)
                        : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -436,36 +459,36 @@ bool get_tmap_out(const void* ptr, bool half, int C, int rows, int n_items, CUte
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int DIL>
+template <int C, int DIL>
 cudaError_t launch_ruw_t(const CUtensorMap& mw, const RwDev& d, const float* x, int n_items, cudaStream_t st) {
   CUtensorMap mx, mo32, mo16;
-  if (!get_tmap_x3_swz(x, kRwC, d.in_rows, n_items, RwSmem<DIL>::kBoxRows, &mx)) return cudaErrorNotSupported;
+  if (!get_tmap_x3_swz(x, C, d.in_rows, n_items, RwSmem<C, DIL>::kBoxRows, &mx)) return cudaErrorNotSupported;
   // exactly one of the two outputs is written by a launch; the other map aliases it (never used)
   const void* o32 = d.out32 ? (const void*)d.out32 : (const void*)d.out16;
   const void* o16 = d.out16 ? (const void*)d.out16 : (const void*)d.out32;
-  if (!get_tmap_out(o32, false, kRwC, d.out_rows, n_items, &mo32) || !get_tmap_out(o16, true, kRwC, d.out_rows, n_items, &mo16))
+  if (!get_tmap_out(o32, false, C, d.out_rows, n_items, &mo32) || !get_tmap_out(o16, true, C, d.out_rows, n_items, &mo16))
     return cudaErrorNotSupported;
   static bool attr_dev[kMaxDev] = {};
   bool& attr_set = attr_dev[cur_dev()];
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_ru_w<DIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, RwSmem<DIL>::kBytes);
+    cudaError_t e = cudaFuncSetAttribute(k_ru_w<C, DIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, RwSmem<C, DIL>::kBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const int grid = std::min(d.total_tiles, sm_count());
-  k_ru_w<DIL><<<grid, kRwThreads, RwSmem<DIL>::kBytes, st>>>(mx, mw, mo32, mo16, d);
+  k_ru_w<C, DIL><<<grid, kRwThreads, RwSmem<C, DIL>::kBytes, st>>>(mx, mw, mo32, mo16, d);
   return cudaGetLastError();
 }
 
 }  // namespace
 
-bool ruw_tc_supported(int C) { return C == kRwC; }
+bool ruw_tc_supported(int C) { return C == 256 || C == 128; }
 
 cudaError_t launch_ruw_tc(const GroupCtx& g, const RuTcArgs& a) {
-  if (a.C != kRwC || g.n_items <= 0 || a.out_r.n() <= 0 || g.n_items >= 65536 || a.in_r.n() >= 65536) return cudaErrorInvalidValue;
+  if (!ruw_tc_supported(a.C) || g.n_items <= 0 || a.out_r.n() <= 0 || g.n_items >= 65536 || a.in_r.n() >= 65536) return cudaErrorInvalidValue;
   if ((a.out32 != nullptr) == (a.out16 != nullptr)) return cudaErrorInvalidValue;  // one output per launch (fp32 stream or fp16 operand)
   CUtensorMap mw;
-  if (!get_tmap(a.pw16, kRwC, kRwC, kRwC, &mw)) return cudaErrorNotSupported;
+  if (!get_tmap(a.pw16, a.C, a.C, a.C, &mw)) return cudaErrorNotSupported;
   RwDev d{};
   d.items = g.items; d.base = g.base; d.out_len = g.out_len; d.T0 = g.T0;
   d.x = a.x; d.in_lo = a.in_r.lo; d.in_rows = a.in_r.n(); d.out_lo = a.out_r.lo; d.out_rows = a.out_r.n(); d.up = a.up;
@@ -477,9 +500,15 @@ cudaError_t launch_ruw_tc(const GroupCtx& g, const RuTcArgs& a) {
   const long long total = (long long)d.tiles_per_item * g.n_items;
   if (total >= (1LL << 31)) return cudaErrorInvalidValue;
   d.total_tiles = (int)total;
-  cudaError_t e = (a.dil == 1) ? launch_ruw_t<1>(mw, d, a.x, g.n_items, g.stream)
-                  : (a.dil == 3) ? launch_ruw_t<3>(mw, d, a.x, g.n_items, g.stream)
-                                 : launch_ruw_t<9>(mw, d, a.x, g.n_items, g.stream);
+  cudaError_t e;
+  if (a.C == 256)
+    e = (a.dil == 1) ? launch_ruw_t<256, 1>(mw, d, a.x, g.n_items, g.stream)
+        : (a.dil == 3) ? launch_ruw_t<256, 3>(mw, d, a.x, g.n_items, g.stream)
+                       : launch_ruw_t<256, 9>(mw, d, a.x, g.n_items, g.stream);
+  else
+    e = (a.dil == 1) ? launch_ruw_t<128, 1>(mw, d, a.x, g.n_items, g.stream)
+        : (a.dil == 3) ? launch_ruw_t<128, 3>(mw, d, a.x, g.n_items, g.stream)
+                       : launch_ruw_t<128, 9>(mw, d, a.x, g.n_items, g.stream);
   ++*g.launches;
   return e;
 }
