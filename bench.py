@@ -339,24 +339,59 @@ def run_ours(args) -> None:
                 return pd.gather_pcm(pcm4, dst=0)
             return pcm4
 
-        for i in range(3):
-            tick4(i)
-        barrier()
-        t0 = time.perf_counter()
+        # device-side gather (N > 1): pinned host tokens -> H2D -> kernels -> NCCL gather over NVLink onto rank 0 -> ONE
+        # D2H of the whole tick there; every rank also reads its window statuses back
+        use_nccl4 = world > 1 and equal and len(mine4) > 0
+        if use_nccl4:
+            tok4_pin = torch.from_numpy(tok4).pin_memory()
+            tok4_dev = torch.empty(tok4.shape, dtype=torch.int32, device=dev)
+            pcm4_dev = torch.empty((len(mine4), 2048), dtype=torch.int16, device=dev)
+            st4_dev = torch.empty((len(mine4),), dtype=torch.int32, device=dev)
+            st4_pin = torch.empty((len(mine4),), dtype=torch.int32).pin_memory()
+            out4_pin = torch.empty((tot4, 2048), dtype=torch.int16).pin_memory() if rank == 0 else None
+
+            def tick4_dev(step):
+                tok4_dev.copy_(tok4_pin, non_blocking=True)
+                eng.decode_windows_device(tok4_dev, noise="philox", seed=step, keys=keys4, pcm=pcm4_dev, status=st4_dev)
+                st4_pin.copy_(st4_dev, non_blocking=True)
+                g = pd.gather_pcm_device(pcm4_dev, dst=0, out_host=out4_pin)
+                torch.cuda.current_stream(dev).synchronize()
+                assert int(st4_pin.sum()) == 0
+                return g
+
+        def timed4(fn):
+            for i in range(3):
+                fn(i)
+            barrier()
+            t0 = time.perf_counter()
+            g = None
+            for i in range(n4):
+                g = fn(500 + i)
+            torch.cuda.synchronize(dev)
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            return g, float(dt[0])
+
         n4 = max(4, K)
-        for i in range(n4):
-            g4 = tick4(500 + i)
-        torch.cuda.synchronize(dev)
-        dt4 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt4, op=dist.ReduceOp.MAX)
+        g4, dt4 = timed4(tick4)
+        g4d, dt4d = timed4(tick4_dev) if use_nccl4 else (None, None)
         if rank == 0:
             assert g4 is not None and g4.shape == (tot4 if (world == 1 or equal) else len(mine4), 2048)
-            cfg4 = {"streams_total": tot4, "streams_per_gpu": len(mine4), "ticks": n4, "ms_per_tick": 1e3 * float(dt4[0]) / n4,
-                    "audio_s_per_s": tot4 * n4 * AUDIO_S_PER_WINDOW / float(dt4[0]), "scaling": "strong",
+            host = {"ms_per_tick": 1e3 * dt4 / n4, "audio_s_per_s": tot4 * n4 * AUDIO_S_PER_WINDOW / dt4,
                     "gather": ("gloo host gather of every stream's PCM onto rank 0 inside the timed region" if world > 1
                                else "single GPU: no gather"),
                     "api": "SnacEngine.decode_windows (host buffers in and out) per rank, PartitionedDecoder.gather_pcm"}
+            cfg4 = {"streams_total": tot4, "streams_per_gpu": len(mine4), "ticks": n4, "scaling": "strong"}
+            if use_nccl4:
+                assert g4d is not None and np.array_equal(g4d, g4)  # same seed on the last tick: both gathers, same bytes
+                cfg4.update({"ms_per_tick": 1e3 * dt4d / n4, "audio_s_per_s": tot4 * n4 * AUDIO_S_PER_WINDOW / dt4d,
+                             "gather": "NCCL gather of every rank's device PCM onto rank 0 over NVLink + one D2H of the whole tick there, "
+                                       "inside the timed region; bytes equal to the host-gather path",
+                             "api": "pinned host tokens -> H2D -> SnacEngine.decode_windows_device -> PartitionedDecoder.gather_pcm_device",
+                             "host_gather": host})
+            else:
+                cfg4.update(host)
 
     # ---- BASELINE config 5 on the whole box: 512 streams per GPU, ragged ticks (0/1/2 pending windows of 1/4/7 frames per
     # stream), scene lifetimes with evict + slot refill (barge_in) and re-homing of a stream to another partition after
@@ -413,12 +448,44 @@ def run_ours(args) -> None:
         torch.cuda.synchronize(dev)
         dt5 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         dist.all_reduce(dt5, op=dist.ReduceOp.MAX)
+        # the same ticks with the gather on the device side: NCCL over NVLink onto rank 0, one D2H of the tick there
+        cap5 = max(1, max(sum(1 for s_, _ in tick if partition_of(s_, world) == rank) for tick in ticks5))
+        tok5_pin = torch.zeros((cap5, 49), dtype=torch.int32).pin_memory()
+        tok5_dev = torch.zeros((cap5, 49), dtype=torch.int32, device=dev)
+
+        def dec5_dev(wins):
+            n5 = len(wins)
+            lens5 = [len(w) for w in wins]
+            t5 = tok5_pin.numpy()
+            t5[:n5] = 0
+            for i, w in enumerate(wins):
+                t5[i, : len(w)] = w
+            tok5_dev[:n5].copy_(tok5_pin[:n5], non_blocking=True)
+            return eng.decode_windows_device(tok5_dev[:n5], ntok=lens5, noise="philox", seed=9, keys=np.arange(n5, dtype=np.uint64))
+
+        for tick in ticks5[:2]:
+            pd5.decode_tick_device(tick, dec5_dev, dst=0)
+        barrier()
+        t0 = time.perf_counter()
+        emitted5d, last_dev = 0, None
+        for tick in ticks5:
+            last_dev = pd5.decode_tick_device(tick, dec5_dev, dst=0)
+            if rank == 0:
+                emitted5d += sum(1 for v in last_dev.values() if v)
+        torch.cuda.synchronize(dev)
+        dt5d = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(dt5d, op=dist.ReduceOp.MAX)
         if rank == 0:
+            assert emitted5d == emitted5 and last_dev == merged  # both gathers: the same bytes for every stream
             cfg5p = dict(stats5, streams=ns5, streams_per_gpu=args.cfg5_streams_per_gpu, ticks=len(ticks5),
-                         ms_per_tick=1e3 * float(dt5[0]) / len(ticks5), audio_s_per_s=emitted5 * AUDIO_S_PER_WINDOW / float(dt5[0]),
-                         note="whole box, PartitionedDecoder.decode_tick per tick: ragged host decode per rank + gather_object of "
-                              "every stream's bytes onto rank 0 inside the timed region; evict / refill / re-homing are host "
-                              "bookkeeping (the decoder is stateless across windows)")
+                         ms_per_tick=1e3 * float(dt5d[0]) / len(ticks5), audio_s_per_s=emitted5d * AUDIO_S_PER_WINDOW / float(dt5d[0]),
+                         note="whole box, PartitionedDecoder.decode_tick_device per tick: ragged decode per rank (pinned host tokens -> "
+                              "H2D -> kernels), NCCL gather of every rank's PCM + statuses onto rank 0 over NVLink, one D2H of the tick "
+                              "there, {stream: bytes} built on rank 0 - all inside the timed region; evict / refill / re-homing are "
+                              "host bookkeeping (the decoder is stateless across windows); bytes equal to the host-gather path",
+                         host_gather={"ms_per_tick": 1e3 * float(dt5[0]) / len(ticks5),
+                                      "audio_s_per_s": emitted5 * AUDIO_S_PER_WINDOW / float(dt5[0]),
+                                      "note": "PartitionedDecoder.decode_tick: host decode per rank + gloo gather_object"})
 
     # ---- per-kernel-class device time (CUDA events around each launch), same tick, right after
     stats, extra = {}, {}

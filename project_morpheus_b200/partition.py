@@ -1,16 +1,20 @@
 """Multi-GPU: streams are independent, so a box of N GPUs is N independent stream partitions.
 
 One process per GPU (``torchrun``); rank r owns the streams with ``partition_of(stream) == r``,
-decodes only their windows on its own engine, and the per-tick PCM is brought together with a
-HOST-side gather (``torch.distributed`` object/tensor gather over gloo or NCCL's CPU path) - the
-decode path has no collective because no window depends on another.  Identical bytes
-come out regardless of how streams are partitioned.
+decodes only their windows on its own engine, and the per-tick PCM is brought together on one rank
+(4 KB per stream per tick to one egress) - the decode path itself has no collective because
+no window depends on another.  Two gathers: host-side over gloo (``decode_tick`` / ``gather_pcm``: works
+anywhere, CPU tests) and device-side over NCCL / NVLink (``gather_pcm_device``: the PCM leaves each GPU
+over NVSwitch and crosses PCIe once, on the egress rank).  Identical bytes come out regardless of how
+streams are partitioned.
 """
 from __future__ import annotations
 
 from typing import Callable, Dict, Hashable, List, Optional, Sequence, Tuple
 
 import numpy as np
+
+from . import _lib
 
 DecodeBatch = Callable[[Sequence[Sequence[int]]], List[Optional[bytes]]]
 
@@ -73,3 +77,77 @@ class PartitionedDecoder:
             return None
         stacked = torch.stack(bufs, dim=1)  # [n_local, world, bytes]: stream s = local*world + rank
         return stacked.reshape(-1, t.shape[1]).numpy().view(np.int16)
+
+    def gather_pcm_device(self, pcm, dst: int = 0, group=None, out_host=None):
+        """Device-side gather for uniform ticks: ``pcm`` is this rank's CUDA int16 [n_local, 2048] (what
+        ``SnacEngine.decode_windows_device`` wrote); rank ``dst`` receives every rank's rows over NCCL (NVLink /
+        NVSwitch), interleaves them to stream order on the GPU and copies the tick to the host ONCE:
+        numpy int16 [world * n_local, 2048], stream s = row s.  ``group``: an NCCL group (default: the default group);
+        ``out_host``: optional pinned int16 tensor [world * n_local, 2048] to receive the tick."""
+        import torch
+
+        assert pcm.is_cuda and pcm.dtype == torch.int16 and pcm.dim() == 2 and pcm.is_contiguous()
+        n_local, width = pcm.shape
+        if self.rank == dst:
+            key = (n_local, width, pcm.device)
+            if getattr(self, "_gbuf_key", None) != key:
+                self._gbuf = torch.empty((self.world_size, n_local, width), dtype=torch.int16, device=pcm.device)
+                self._gperm = torch.empty((n_local, self.world_size, width), dtype=torch.int16, device=pcm.device)
+                self._gbuf_key = key
+            bufs = [self._gbuf[r].view(torch.uint8) for r in range(self.world_size)]  # bytes: NCCL has no int16
+        else:
+            bufs = None
+        self._dist.gather(pcm.view(torch.uint8), bufs, dst=dst, group=group)
+        if self.rank != dst:
+            return None
+        self._gperm.copy_(self._gbuf.permute(1, 0, 2))  # stream s = local * world + rank
+        flat = self._gperm.view(n_local * self.world_size, width)
+        if out_host is None:
+            out_host = torch.empty(flat.shape, dtype=torch.int16, pin_memory=True)
+        out_host.copy_(flat, non_blocking=True)
+        torch.cuda.current_stream(pcm.device).synchronize()
+        return out_host.numpy()
+
+    def decode_tick_device(self, windows: Sequence[Tuple[int, Sequence[int]]], decode_device, dst: int = 0, group=None
+                           ) -> Optional[Dict[int, Optional[bytes]]]:
+        """``decode_tick`` with the gather on the device side.  EVERY rank passes the whole tick (so each knows every
+        rank's window count without talking); ``decode_device(list of windows) -> (pcm cuda int16 [n, 2048], status cuda
+        int32 [n])`` decodes this rank's share (``SnacEngine.decode_windows_device``).  The rows of all ranks, padded to
+        the largest share and carrying their window status in two extra int16 columns, go to ``dst`` in one NCCL gather
+        over NVLink and cross PCIe once; returns {stream: bytes | b"" | None} on ``dst`` (what ``convert_to_audio``
+        returns per window; the last window of a stream wins, as in ``decode_tick``) and None elsewhere."""
+        import torch
+
+        parts = split_tick(windows, self.world_size)
+        mine = parts[self.rank]
+        max_n = max(1, max(len(p) for p in parts))
+        width = 2048 + 2
+        dev = torch.device("cuda", torch.cuda.current_device())
+        key = (max_n, dev)
+        if getattr(self, "_tick_key", None) != key:
+            self._tick_send = torch.zeros((max_n, width), dtype=torch.int16, device=dev)
+            self._tick_recv = torch.empty((self.world_size, max_n, width), dtype=torch.int16, device=dev) if self.rank == dst else None
+            self._tick_host = torch.empty((self.world_size, max_n, width), dtype=torch.int16).pin_memory() if self.rank == dst else None
+            self._tick_key = key
+        if mine:
+            pcm, st = decode_device([w for _, w in mine])
+            n = len(mine)
+            self._tick_send[:n, :2048].copy_(pcm)
+            self._tick_send[:n, 2048:].copy_(st.view(torch.int16).view(n, 2))
+        bufs = [self._tick_recv[r].view(torch.uint8) for r in range(self.world_size)] if self.rank == dst else None
+        self._dist.gather(self._tick_send.view(torch.uint8), bufs, dst=dst, group=group)
+        if self.rank != dst:
+            return None
+        self._tick_host.copy_(self._tick_recv, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        host = self._tick_host.numpy()
+        merged: Dict[int, Optional[bytes]] = {}
+        for r, part in enumerate(parts):
+            if not part:
+                continue
+            status = np.ascontiguousarray(host[r, : len(part), 2048:]).view(np.int32).reshape(-1)
+            rows = host[r]
+            for i, (sidx, _) in enumerate(part):
+                stt = int(status[i])
+                merged[sidx] = rows[i, :2048].tobytes() if stt == _lib.WIN_OK else (b"" if stt == _lib.WIN_EMPTY else None)
+        return merged
