@@ -326,6 +326,21 @@ def test_full_size_properties(engines):
     assert np.array_equal(again, pcm[perm])
 
 
+def test_full_size_tick_matches_oracle_on_a_sample(engines, oracle_w1):
+    """The benchmarked tick itself (1024 windows, production kernels, fp16 recipe) against the oracle with the same
+    injected noise, on a spread of its windows: first / last, around the 148-CTA and 128-row tile boundaries."""
+    n, frames = 1024, 4
+    tok = windows_tokens(n, frames, base_stream=7300)
+    noise = snac_ref.make_noise(n, frames, seed=41)
+    eng = engines("fp16")
+    pcm, st = eng.decode_windows(tok, noise=snac_ref.pack_noise(noise))
+    assert (st == _lib.WIN_OK).all()
+    idx = [0, 1, 73, 147, 148, 149, 295, 296, 400, 511, 512, 513, 640, 767, 768, 900, 1000, 1021, 1022, 1023]
+    ref = oracle_decode_windows(oracle_w1, tok[idx], [z[idx] for z in noise])[:, 2048:4096]
+    want = pcm_trunc(ref).astype(np.float32) / 32767.0
+    _check_wave(want, pcm[idx].astype(np.float32) / 32767.0, TOL_MAX_ABS, TOL_SNR_DB)
+
+
 # ------------------------------------------------------------------------------------ the Python boundary
 def test_speechpipe_module_matches_oracle_stream(oracle_w1, state_dict_w1, monkeypatch):
     monkeypatch.setenv("SNACB_NOISE", "off")
