@@ -8,7 +8,7 @@ import sys
 
 lib = sys.argv[1] if len(sys.argv) > 1 else "project_morpheus_b200/libsnacb.so"
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-WATCH = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UBLKCP", "UBLKPF", "UTCBAR", "SYNCS", "FFMA2", "FMUL2", "FADD2", "MUFU", "LDGSTS",
+WATCH = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UBLKPF", "UTCBAR", "SYNCS", "FFMA2", "FMUL2", "FADD2", "MUFU", "LDGSTS",
          "HMMA", "HGMMA"]
 fn, counts, total = None, collections.OrderedDict(), collections.Counter()
 for line in sass.splitlines():
