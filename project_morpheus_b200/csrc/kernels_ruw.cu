@@ -41,7 +41,7 @@ struct RwDev {
   const float* w7; const float* dw_b; const float* a1; const float* i1; const float* a2; const float* i2; const float* pw_b;
   float* out32; __half* out16; const float* sn_alpha; const float* sn_inv;
   int tiles_per_item, total_tiles;
-  int dbg;  // SNACB_RUW_DBG bits (profiling experiments): 1 workers skip the units, 2 init skips the copy, 4 epilogue skips the stores, 8 no Snake in the fp16 epilogue
+  int dbg;  // SNACB_RUW_DBG bits (profiling experiments): 1 workers skip the units, 2 init skips the copy, 4 epilogue skips the stores, 8 no Snake in the fp16 epilogue, 16 staging written but no TMA store issued
 };
 
 template <int C, int DIL> struct RwSmem {
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(kRwThreads, 1) k_ru_w(const __grid_constant__ 
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (et == 0) {
+        if (et == 0 && !(a.dbg & 16)) {
           const CUtensorMap* tm = half_out ? &tmO16 : &tmO32;
           asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
                            reinterpret_cast<uint64_t>(tm)),
