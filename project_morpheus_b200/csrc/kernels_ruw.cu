@@ -16,9 +16,10 @@
 //                         starts as x + b
 //   MMA (1 thread)        once the four blocks are in: D += A W^T, k-block by k-block (N = 256) - the residual add is
 //                         the accumulate flag
-//   epilogue (4 warps)    D -> fp32 x' (or, for the block's last unit, the next block's Snake -> fp16 operand): row per
-//                         lane from tensor memory into swizzled staging tiles, out through TMA tensor stores; two
-//                         accumulators (2 x C TMEM columns) let it drain tile i while tile i+1 is being built
+//   epilogue (4 + 4 warps) D -> fp32 x' (or, for the block's last unit, the next block's Snake -> fp16 operand): row per
+//                         lane from tensor memory into swizzled staging tiles, out through TMA tensor stores.  Two teams:
+//                         the dedicated warps take the even 128-byte column slabs, the init warps the odd ones.  512 / C
+//                         accumulators in tensor memory (2 at C = 256, 4 at C = 128) decouple it from the tiles being built
 #include <cstdlib>
 
 #include "snacb.h"
@@ -41,7 +42,7 @@ struct RwDev {
   const float* w7; const float* dw_b; const float* a1; const float* i1; const float* a2; const float* i2; const float* pw_b;
   float* out32; __half* out16; const float* sn_alpha; const float* sn_inv;
   int tiles_per_item, total_tiles;
-  int dbg;  // SNACB_RUW_DBG bits (profiling experiments): 1 workers skip the units, 2 init skips the copy, 4 epilogue skips the stores, 8 no Snake in the fp16 epilogue, 16 staging written but no TMA store issued
+  int dbg;  // SNACB_RUW_DBG bits (profiling experiments): 1 workers skip the units, 2 init skips the copy, 4 epilogue skips the stores, 8 no Snake in the fp16 epilogue, 16 staging written but no TMA store issued, 256 one epilogue team
 };
 
 template <int C, int DIL> struct RwSmem {
@@ -59,14 +60,16 @@ template <int C, int DIL> struct RwSmem {
   // Epilogue staging tiles: the TMA store of slab i reads its tile while slab i+1 is written into the next one.  (With a
   // single tile every slab waited out the previous store: 8 slabs x ~1 us per tile made the epilogue, not the depthwise
   // workers, the bound of the kernel.)
-  static constexpr int kOutBufs = (C == 256) ? 2 : 4;
+  static constexpr int kOutBufs = (C == 256) ? 2 : 4;        // split evenly between the two epilogue teams
   static constexpr int kOutBytes = BM * 128;                   // epilogue staging: [128 rows][128 B], SWIZZLE_128B, TMA store
   static constexpr int kOffX = 0;
   static constexpr int kOffA = kStages * kXBytes;
   static constexpr int kOffW = kOffA + kABytes;
   static constexpr int kOffOut = kOffW + kWStages * kWStage;
-  static constexpr int kOffBar = kOffOut + kOutBufs * kOutBytes;
-  static constexpr int kBytes = kOffBar + 256;
+  static constexpr int kOffSn = kOffOut + kOutBufs * kOutBytes;   // next block's Snake constants [alpha C][1/alpha C] (fp16-emitting launches)
+  static constexpr int kOffBar = kOffSn + 2 * C * 4;
+  static constexpr int kAcc = 512 / C;                         // accumulators in tensor memory: 2 (C = 256) or 4 (C = 128)
+  static constexpr int kBytes = kOffBar + 320;
   static_assert(kBytes <= 227 * 1024, "shared memory");
 };
 
@@ -124,10 +127,11 @@ __global__ void __launch_bounds__(kRwThreads, 1) k_ru_w(const __grid_constant__ 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kOffBar);
   // x_full[<=4] 0..3, x_free[<=4] 4..7, w_full[2] 8..9, w_free[2] 10..11, a_full[4] 12..15, a_free[4] 16..19, d_init[2] 20..21,
   // t_full[2] 22..23, t_empty[2] 24..25
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   auto bar = [&](int i) { return smem_u32(&bars[i]); };
-  constexpr int X_FULL = 0, X_FREE = 4, W_FULL = 8, W_FREE = 10, A_FULL = 12, A_FREE = 16, D_INIT = 20, T_FULL = 22, T_EMPTY = 24;
+  constexpr int X_FULL = 0, X_FREE = 4, W_FULL = 8, W_FREE = 10, A_FULL = 12, A_FREE = 16, D_INIT = 20, T_FULL = 24, T_EMPTY = 28;
+  constexpr int NACC = S::kAcc;
 
   if (tid == 0) {
     if (smem_u32(smem) & 1023u) { printf("snacb: k_ru_w dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
@@ -135,19 +139,118 @@ __global__ void __launch_bounds__(kRwThreads, 1) k_ru_w(const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(W_FULL + i), 1);
       mbar_init(bar(W_FREE + i), 1);
+    }
+    for (int i = 0; i < NACC; ++i) {
       mbar_init(bar(D_INIT + i), kRwInit);
       mbar_init(bar(T_FULL + i), 1);
-      mbar_init(bar(T_EMPTY + i), kRwEpi);
+      mbar_init(bar(T_EMPTY + i), kRwEpi + kRwInit);  // both epilogue teams
     }
     for (int i = 0; i < kRwKB; ++i) { mbar_init(bar(A_FULL + i), kRwWorkers); mbar_init(bar(A_FREE + i), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * C);
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), NACC * C);
+  float* sSn = reinterpret_cast<float*>(smem + S::kOffSn);
+  if (a.out16 != nullptr && a.sn_alpha != nullptr)
+    for (int c = tid; c < C; c += kRwThreads) { sSn[c] = a.sn_alpha[c]; sSn[C + c] = a.sn_inv[c]; }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int n_my = ((int)a.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  // ---- epilogue of one tile, shared by two TEAMS of four warps (one warp per TMEM lane quarter each): the dedicated
+  // epilogue warps take the even 128-byte column slabs, the init warps - idle most of the time - the odd ones.  (With one
+  // team the epilogue was the slowest stage of the pipeline: skipping it made the fp16-emitting launches 70-100 us
+  // faster.)  D (-> Snake of the next block) goes row per lane into a swizzled staging tile and leaves through ONE TMA
+  // tensor store per slab (fp32: 32 channels, fp16: 64): coalesced, asynchronous, rows beyond the item clipped by the
+  // tensor map.  Each team has its own staging tiles, named barrier and store-issuing thread.
+  auto epilogue_tile = [&](int ti, int team, int et, int& slab_ctr) {
+    constexpr int kTeamBufs = S::kOutBufs / 2;
+    const int hq = warp & 3;  // TMEM lane quarter
+    const int trow = hq * 32 + lane;
+    const bool half_out = a.out16 != nullptr;               // the block's last unit emits the fp16 operand only
+    const int cols_per_store = half_out ? 64 : 32;
+    const int tb = ti % NACC;
+    const int lin = blockIdx.x + ti * gridDim.x;
+    const int item = lin / a.tiles_per_item, row0 = (lin - item * a.tiles_per_item) * BM;
+    const ItemRef it = get_item(a.items, a.base, item, a.out_len);
+    const int t_abs = a.out_lo + row0 + trow + it.shift0 * a.up;
+    const bool live = t_abs >= 0 && t_abs < a.T0 * a.up;
+    const bool all_live = __all_sync(0xffffffffu, live);  // the usual case: no masking instructions at all
+    mbar_wait(bar(T_FULL + tb), (ti / NACC) & 1, 800 + team);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(hq * 32) << 16) + (uint32_t)(tb * C);
+    const int nteams = (a.dbg & 256) ? 1 : 2;
+    for (int c0 = team * cols_per_store; c0 < C; c0 += nteams * cols_per_store, ++slab_ctr) {
+      if ((a.dbg & 4) || team >= nteams) break;
+      uint8_t* stage = sOut + (team * kTeamBufs + slab_ctr % kTeamBufs) * S::kOutBytes;
+      uint8_t* rowp = stage + trow * 128;
+      // the store that last used this staging tile (kTeamBufs slabs of this team ago) has finished READING it
+      if (et == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kTeamBufs - 1) : "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory");
+      if (!half_out) {
+        // fp32: the accumulator already holds x + b + W s: 32 columns = 8 chunks straight from tensor memory to the
+        // staging row (the bias went in with the init, rows outside the sequence are zeroed only where there are any)
+        uint32_t r0[16], r1[16];
+        tmem_ld16_nowait(taddr + c0, r0);
+        tmem_ld16_nowait(taddr + c0 + 16, r1);
+        tmem_ld_wait();
+        if (!all_live && !live) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { r0[j] = 0u; r1[j] = 0u; }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          *reinterpret_cast<uint4*>(rowp + ((((j) ^ trow) & 7) << 4)) = make_uint4(r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]);
+          *reinterpret_cast<uint4*>(rowp + ((((4 + j) ^ trow) & 7) << 4)) = make_uint4(r1[4 * j], r1[4 * j + 1], r1[4 * j + 2], r1[4 * j + 3]);
+        }
+      } else {
+        // fp16 (the next block's Snake applied): 64 columns = 8 chunks of 8 halves
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int col = c0 + g * 16;
+          uint32_t r[16];
+          tmem_ld16(taddr + col, r);
+          float4 x[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            x[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                               __uint_as_float(r[4 * j + 3]));
+            if (a.sn_alpha && !(a.dbg & 8)) {
+              const float4 al = *reinterpret_cast<const float4*>(sSn + col + 4 * j);      // broadcast reads
+              const float4 iv = *reinterpret_cast<const float4*>(sSn + C + col + 4 * j);
+              const float2 lo = snake2(make_float2(x[j].x, x[j].y), make_float2(al.x, al.y), make_float2(iv.x, iv.y));
+              const float2 hi = snake2(make_float2(x[j].z, x[j].w), make_float2(al.z, al.w), make_float2(iv.z, iv.w));
+              x[j] = make_float4(lo.x, lo.y, hi.x, hi.y);
+            }
+            if (!all_live && !live) x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const __half2 h0 = f2h2_sat(x[2 * j].x, x[2 * j].y), h1 = f2h2_sat(x[2 * j].z, x[2 * j].w);
+            const __half2 h2 = f2h2_sat(x[2 * j + 1].x, x[2 * j + 1].y), h3 = f2h2_sat(x[2 * j + 1].z, x[2 * j + 1].w);
+            uint4 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<const uint32_t*>(&h2); pk.w = *reinterpret_cast<const uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(rowp + ((((g * 2 + j) ^ trow) & 7) << 4)) = pk;
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory");
+      if (et == 0 && !(a.dbg & 16)) {
+        const CUtensorMap* tm = half_out ? &tmO16 : &tmO32;
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                         reinterpret_cast<uint64_t>(tm)),
+                     "r"(smem_u32(stage)), "r"(c0), "r"(row0), "r"(item)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(T_EMPTY + tb)) : "memory");
+  };
 
   if (warp == 0) {
     // ===================================================================== producer
@@ -199,8 +302,8 @@ __global__ void __launch_bounds__(kRwThreads, 1) k_ru_w(const __grid_constant__ 
       constexpr uint32_t idesc = umma_idesc_f16(C);
       int wk = 0;
       for (int ti = 0; ti < n_my; ++ti) {
-        const int tb = ti & 1;
-        mbar_wait(bar(D_INIT + tb), (ti >> 1) & 1, 100);  // the accumulator holds x for the whole tile
+        const int tb = ti % NACC;
+        mbar_wait(bar(D_INIT + tb), (ti / NACC) & 1, 100);  // the accumulator holds x for the whole tile
         tc_fence_after();
         for (int kb = 0; kb < kRwKB; ++kb, ++wk) {
           const int st = wk % NWS;
@@ -221,10 +324,11 @@ __global__ void __launch_bounds__(kRwThreads, 1) k_ru_w(const __grid_constant__ 
     // ===================================================================== init: x -> tensor memory
     const int hq = warp & 3;  // a warp reaches TMEM lanes 32 * (warp % 4) .. + 31
     const int row = hq * 32 + lane + 3 * DIL;  // box row of this thread's tile row
-    int nb = 0;
+    const int it_ = tid - 2 * 32;              // thread of the team (0..127)
+    int nb = 0, slab_ctr = 0;
     for (int ti = 0; ti < n_my; ++ti) {
-      const int tb = ti & 1;
-      mbar_wait(bar(T_EMPTY + tb), ((ti >> 1) & 1) ^ 1, 400);  // the epilogue drained this accumulator
+      const int tb = ti % NACC;
+      mbar_wait(bar(T_EMPTY + tb), ((ti / NACC) & 1) ^ 1, 400);  // both epilogue teams drained this accumulator
       tc_fence_after();
       for (int b = 0; b < kRwNB; ++b, ++nb) {
         const int st = nb % NST;
@@ -255,7 +359,12 @@ __global__ void __launch_bounds__(kRwThreads, 1) k_ru_w(const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(D_INIT + tb)) : "memory");
+      // second duty: the odd column slabs of the PREVIOUS tile's epilogue (its accumulator completes while this tile's
+      // blocks are still being built, and the next init needs that epilogue finished anyway)
+      if (ti >= 1) epilogue_tile(ti - 1, 1, it_, slab_ctr);
     }
+    if (n_my >= 1) epilogue_tile(n_my - 1, 1, it_, slab_ctr);
+    if (it_ == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (warp < 2 + kRwInit + kRwWorkers) {
     // ===================================================================== workers: depthwise units
     const int wt = tid - (2 + kRwInit) * 32;                      // 0..575
@@ -308,109 +417,17 @@ __global__ void __launch_bounds__(kRwThreads, 1) k_ru_w(const __grid_constant__ 
       }
     }
   } else {
-    // ===================================================================== epilogue
-    // D + b (-> Snake of the next block) goes row per lane into a swizzled staging tile and leaves through ONE TMA tensor
-    // store per 128-byte column block (fp32: 32 channels, fp16: 64): coalesced, asynchronous, rows beyond the item
-    // clipped by the tensor map.  (Row-per-lane global stores from these four warps were the kernel's bottleneck:
-    // 0.42 ms per launch against 0.17 ms without them.)
-    const int hq = warp & 3;  // TMEM lane quarter (warps 24..27)
-    const int trow = hq * 32 + lane;
+    // ===================================================================== epilogue, team 0 (even slabs)
     const int et = tid - (2 + kRwInit + kRwWorkers) * 32;  // 0..127
-    const bool half_out = a.out16 != nullptr;               // the block's last unit emits the fp16 operand only
-    const int cols_per_store = half_out ? 64 : 32;
-    // 16-byte chunk c of this thread's staging row sits at swz[c] (SWIZZLE_128B)
-    int swz[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) swz[c] = ((c ^ trow) & 7) << 4;
-    int slab = 0;
-    for (int ti = 0; ti < n_my; ++ti) {
-      const int tb = ti & 1;
-      const int lin = blockIdx.x + ti * gridDim.x;
-      const int item = lin / a.tiles_per_item, row0 = (lin - item * a.tiles_per_item) * BM;
-      const ItemRef it = get_item(a.items, a.base, item, a.out_len);
-      const int t_abs = a.out_lo + row0 + trow + it.shift0 * a.up;
-      const bool live = t_abs >= 0 && t_abs < a.T0 * a.up;
-      const bool all_live = __all_sync(0xffffffffu, live);  // the usual case: no masking instructions at all
-      mbar_wait(bar(T_FULL + tb), (ti >> 1) & 1, 800);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(hq * 32) << 16) + (uint32_t)(tb * C);
-      for (int c0 = 0; c0 < C; c0 += cols_per_store, ++slab) {
-        if (a.dbg & 4) break;
-        uint8_t* stage = sOut + (slab % S::kOutBufs) * S::kOutBytes;
-        uint8_t* rowp = stage + trow * 128;
-        // the store that last used this staging tile (kOutBufs slabs ago) has finished READING it
-        if (et == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(S::kOutBufs - 1) : "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (!half_out) {
-          // fp32: the accumulator already holds x + b + W s: 32 columns = 8 chunks straight from tensor memory to the
-          // staging row (the bias went in with the init, rows outside the sequence are zeroed only where there are any)
-          uint32_t r0[16], r1[16];
-          tmem_ld16_nowait(taddr + c0, r0);
-          tmem_ld16_nowait(taddr + c0 + 16, r1);
-          tmem_ld_wait();
-          if (!all_live && !live) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { r0[j] = 0u; r1[j] = 0u; }
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            *reinterpret_cast<uint4*>(rowp + swz[j]) = make_uint4(r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]);
-            *reinterpret_cast<uint4*>(rowp + swz[4 + j]) = make_uint4(r1[4 * j], r1[4 * j + 1], r1[4 * j + 2], r1[4 * j + 3]);
-          }
-        } else {
-          // fp16 (the next block's Snake applied): 64 columns = 8 chunks of 8 halves
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = c0 + g * 16;
-            uint32_t r[16];
-            tmem_ld16(taddr + col, r);
-            float4 x[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              x[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                                 __uint_as_float(r[4 * j + 3]));
-              if (a.sn_alpha && !(a.dbg & 8)) {
-                const float4 al = __ldg(reinterpret_cast<const float4*>(a.sn_alpha + col + 4 * j));
-                const float4 iv = __ldg(reinterpret_cast<const float4*>(a.sn_inv + col + 4 * j));
-                const float2 lo = snake2(make_float2(x[j].x, x[j].y), make_float2(al.x, al.y), make_float2(iv.x, iv.y));
-                const float2 hi = snake2(make_float2(x[j].z, x[j].w), make_float2(al.z, al.w), make_float2(iv.z, iv.w));
-                x[j] = make_float4(lo.x, lo.y, hi.x, hi.y);
-              }
-              if (!live) x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const __half2 h0 = f2h2_sat(x[2 * j].x, x[2 * j].y), h1 = f2h2_sat(x[2 * j].z, x[2 * j].w);
-              const __half2 h2 = f2h2_sat(x[2 * j + 1].x, x[2 * j + 1].y), h3 = f2h2_sat(x[2 * j + 1].z, x[2 * j + 1].w);
-              uint4 pk;
-              pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-              pk.z = *reinterpret_cast<const uint32_t*>(&h2); pk.w = *reinterpret_cast<const uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(rowp + swz[g * 2 + j]) = pk;
-            }
-          }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (et == 0 && !(a.dbg & 16)) {
-          const CUtensorMap* tm = half_out ? &tmO16 : &tmO32;
-          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                           reinterpret_cast<uint64_t>(tm)),
-                       "r"(smem_u32(stage)), "r"(c0), "r"(row0), "r"(item)
-                       : "memory");
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar(T_EMPTY + tb)) : "memory");
-    }
+    int slab_ctr = 0;
+    for (int ti = 0; ti < n_my; ++ti) epilogue_tile(ti, 0, et, slab_ctr);
     if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every store has landed before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * C);
+    tmem_dealloc(tmem_base, NACC * C);
   }
 }
 
