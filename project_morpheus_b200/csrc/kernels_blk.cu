@@ -46,6 +46,7 @@ struct BlkDev {
   const float* pw_b[3];
   const float* sn_alpha; const float* sn_inv;  // Snake after the block (decoder tail / next block)
   const float* tail_w7; const float* tail_b; int32_t* status; float* wav; int16_t* pcm;
+  int dbg;  // SNACB_BLK_DBG bits (timing experiments, results wrong): 1 no depthwise units, 2 no Snake passes, 4 no tail, 8 no MMA
 };
 
 template <int C> struct BlkSmem {
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(kBlkThreads, 2) k_blk_tail(const __grid_consta
 
     auto ru_step = [&](auto dil_c, int r, const CUtensorMap* next_w) {
       constexpr int DIL = decltype(dil_c)::value;
-      dw_phase<C, DIL>(a, r, sX, sA, warp, lane);
+      if (!(a.dbg & 1)) dw_phase<C, DIL>(a, r, sX, sA, warp, lane);
       __syncthreads();
       if (tid == 0) {
         mbar_wait(bar_w, nstep & 1u);
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(kBlkThreads, 2) k_blk_tail(const __grid_consta
           for (int k = 0; k < C / 16; ++k) {  // one MMA = 16 channels = two 16-byte K chunks of the operand
             const uint64_t da = umma_desc_k_noswz(smem_u32(sA + 2 * k * S::kLbo + sub * (BM * 16)), S::kLbo, 128);
             const uint64_t db = umma_desc_k_sw128(smem_u32(sW + (k / 4) * (C * 128))) + 2 * (k % 4);
-            umma_f16(tmem_base + sub * C, da, db, idesc, 1u);  // D += A W^T on top of the residual stream
+            if (!(a.dbg & 8)) umma_f16(tmem_base + sub * C, da, db, idesc, 1u);  // D += A W^T on top of the residual stream
           }
         umma_commit(bar_mma);
       }
@@ -387,17 +388,20 @@ __global__ void __launch_bounds__(kBlkThreads, 2) k_blk_tail(const __grid_consta
       ++nstep;
     };
     ru_step(IntC<1>{}, 0, &tmW1);
-    if (interior) snake_pass<C, 1, 3, kBlkRows - 3, false>(sX, sConst, tmem_base, warp, lane, t_abs0, t_hi);
+    if (a.dbg & 2) {}
+    else if (interior) snake_pass<C, 1, 3, kBlkRows - 3, false>(sX, sConst, tmem_base, warp, lane, t_abs0, t_hi);
     else snake_pass<C, 1, 3, kBlkRows - 3, true>(sX, sConst, tmem_base, warp, lane, t_abs0, t_hi);
     tc_fence_before();
     __syncthreads();
     ru_step(IntC<3>{}, 1, &tmW2);
-    if (interior) snake_pass<C, 2, 12, kBlkRows - 12, false>(sX, sConst, tmem_base, warp, lane, t_abs0, t_hi);
+    if (a.dbg & 2) {}
+    else if (interior) snake_pass<C, 2, 12, kBlkRows - 12, false>(sX, sConst, tmem_base, warp, lane, t_abs0, t_hi);
     else snake_pass<C, 2, 12, kBlkRows - 12, true>(sX, sConst, tmem_base, warp, lane, t_abs0, t_hi);
     tc_fence_before();
     __syncthreads();
     ru_step(IntC<9>{}, 2, more ? &tmW0 : nullptr);
-    if (interior) snake_pass<C, 3, kBlkHalo, kBlkRows - kBlkHalo, false>(sX, sConst, tmem_base, warp, lane, t_abs0, t_hi);
+    if (a.dbg & 2) {}
+    else if (interior) snake_pass<C, 3, kBlkHalo, kBlkRows - kBlkHalo, false>(sX, sConst, tmem_base, warp, lane, t_abs0, t_hi);
     else snake_pass<C, 3, kBlkHalo, kBlkRows - kBlkHalo, true>(sX, sConst, tmem_base, warp, lane, t_abs0, t_hi);
     tc_fence_before();
     __syncthreads();
@@ -407,7 +411,7 @@ __global__ void __launch_bounds__(kBlkThreads, 2) k_blk_tail(const __grid_consta
     // FIR over the 7 taps as in the depthwise units), then the 11 per-lane partial sums are reduced across the warp.
     // (One thread per output re-reads each row seven times: that version spent half of the kernel's shared-memory
     // wavefronts here and kept only 11 of 16 warps busy.)
-    {
+    if (!(a.dbg & 4)) {
       constexpr int LT = (kTO + kBlkWarps - 1) / kBlkWarps;
       static_assert(C == 64, "tail: one lane per channel pair");
       const int o0 = warp * LT;
@@ -475,6 +479,8 @@ cudaError_t launch_blk_tc(const GroupCtx& g, const BlkTcArgs& a) {
   d.x = a.x; d.in_lo = a.in_r.lo; d.in_rows = a.in_r.n(); d.up = a.up;
   constexpr int kTO = kBlkRows - 2 * kBlkHalo - 6;
   d.o_lo = a.tail_out.lo; d.o_n = a.tail_out.n();
+  static const int dbg = [] { const char* v = getenv("SNACB_BLK_DBG"); return v ? atoi(v) : 0; }();
+  d.dbg = dbg;
   d.tile_stride = kTO; d.row_off = -(kBlkHalo + 3);
   d.tiles_per_item = (d.o_n + kTO - 1) / kTO;
   const long long total = (long long)d.tiles_per_item * g.n_items;
