@@ -185,3 +185,69 @@ def test_stalled_consumer_loses_its_window_not_the_tick(state_dict_w1, ensure_li
     assert first == pcm[0].tobytes()
     ring.close()
     eng.close()
+
+
+def test_adapters_with_gpu_crossfade_equal_host_stitcher_over_the_serial_decoder(state_dict_w1, monkeypatch):
+    """The integrated path with a non-zero overlap: adapters pull from GPU rings that crossfade consecutive windows of a
+    stream (SNACB_RING_OVERLAP_MS = 10) == the native host stitcher applied to the chunks of the serial per-stream
+    decoder (noise off), including the tail flushed at the end of each stream."""
+    import asyncio
+    import importlib
+    import sys
+
+    from oracle import speechpipe_ref as sp
+
+    monkeypatch.setenv("SNACB_NOISE", "off")
+    monkeypatch.setenv("SNACB_PRECISION", "fp16")
+    monkeypatch.setenv("SNACB_RANDOM_INIT", "0:w1")
+    monkeypatch.setenv("SNACB_GPU_RING", "1")
+    monkeypatch.setenv("SNACB_RING_SLOTS", "32")
+    monkeypatch.setenv("SNACB_RING_OVERLAP_MS", "10")
+    monkeypatch.delenv("ORPHEUS_SNAC_PATH", raising=False)
+    sys.modules.pop("project_morpheus_b200.speechpipe", None)
+    speechpipe = importlib.import_module("project_morpheus_b200.speechpipe")
+    from project_morpheus_b200.adapter import SnacB200Adapter
+
+    n = 24
+    streams = [sp.synth_token_strings(900 + i, 3 + (i % 6)) for i in range(n)]
+
+    def source(strings):
+        async def gen(**_):
+            for i, s in enumerate(strings):
+                if i % 5 == 0:
+                    await asyncio.sleep(0)
+                yield s
+        return gen
+
+    async def pull_loop(ad, size):
+        out = bytearray()
+        while True:
+            c = await ad.pull(size)
+            out += c.pcm
+            if c.eos:
+                return bytes(out)
+
+    async def main():
+        ads = [SnacB200Adapter("p", token_source=source(s), seed=i) for i, s in enumerate(streams)]
+        return await asyncio.gather(*[pull_loop(a, (4096, 1000, 333)[i % 3]) for i, a in enumerate(ads)])
+
+    got = asyncio.run(main())
+    assert speechpipe.get_ring().overlap_samples == 240 and len(speechpipe.get_ring()._free) == 32
+
+    async def serial(strings):
+        return [c async for c in speechpipe.tokens_decoder(source(strings)(), ticker=False)]
+
+    for i, s in enumerate(streams):
+        st = egress.Stitcher(24000, 10.0)
+        want = bytearray()
+        for chunk in asyncio.run(serial(s)):
+            if chunk:
+                data, _ = st.push(chunk, False)
+                if data:
+                    want += data
+        want += st.flush() or b""
+        st.close()
+        assert got[i] == bytes(want), (i, len(got[i]), len(want))
+        assert len(want) >= 4096
+    assert sum(len(g) > 3 * 4096 for g in got) >= n // 2   # most streams crossfade several windows
+    sys.modules.pop("project_morpheus_b200.speechpipe", None)
