@@ -64,3 +64,57 @@ def test_decoder_block_matches_dac(stride):
     assert got.shape == want.shape == (2, cout, 40 * stride)
     assert theirs.conv_t1.kernel_size == (2 * stride,) and theirs.conv_t1.padding == (math.ceil(stride / 2),)
     assert torch.allclose(got, want, atol=2e-5), float((got - want).abs().max())
+
+
+@pytest.mark.parametrize("stride", [2, 4, 8])
+def test_encoder_block_matches_dac(stride):
+    """N4 oracle: EncoderBlock (RU d = 1, 3, 9 -> Snake -> strided conv k = 2s, pad ceil(s/2)) against DacEncoderBlock,
+    depthwise convs written into DAC's dense ones as block-diagonal weights."""
+    torch.manual_seed(10 + stride)
+    cin = 16
+    cfg = DacConfig(encoder_hidden_size=cin)
+    theirs = dac.DacEncoderBlock(cfg, stride=stride, stride_index=1).eval()   # dimension = 2 * cin: cin -> 2 cin
+    mine = snac_ref.EncoderBlock(cin, 2 * cin, stride).eval()
+    blk = mine.block
+    with torch.no_grad():
+        for s in (blk[0].block[0], blk[0].block[2], blk[1].block[0], blk[1].block[2], blk[2].block[0], blk[2].block[2], blk[3]):
+            s.alpha.copy_(0.5 + torch.rand_like(s.alpha))
+        for conv in [blk[4]] + [ru.block[i] for ru in (blk[0], blk[1], blk[2]) for i in (1, 3)]:
+            conv.weight_g.mul_(0.8 + 0.4 * torch.rand_like(conv.weight_g))
+        for ru_m, ru_t in ((blk[0], theirs.res_unit1), (blk[1], theirs.res_unit2), (blk[2], theirs.res_unit3)):
+            ru_t.snake1.alpha.copy_(ru_m.block[0].alpha)
+            ru_t.conv1.weight.copy_(_dense_from_depthwise(ru_m.block[1]._w()))
+            ru_t.conv1.bias.copy_(ru_m.block[1].bias)
+            ru_t.snake2.alpha.copy_(ru_m.block[2].alpha)
+            ru_t.conv2.weight.copy_(ru_m.block[3]._w())
+            ru_t.conv2.bias.copy_(ru_m.block[3].bias)
+        theirs.snake1.alpha.copy_(blk[3].alpha)
+        theirs.conv1.weight.copy_(blk[4]._w())
+        theirs.conv1.bias.copy_(blk[4].bias)
+        x = torch.randn(2, cin, 16 * stride)
+        got, want = mine(x), theirs(x)
+    assert got.shape == want.shape
+    assert torch.allclose(got, want, atol=2e-5), float((got - want).abs().max())
+
+
+def test_vector_quantize_matches_dac():
+    """N4 oracle: one residual-VQ level (in_proj -> nearest codeword on L2-normalised vectors -> out_proj) against
+    DacVectorQuantize: same indices, same quantised latent (stride 1: SNAC's pooling / repeat are its own addition)."""
+    torch.manual_seed(3)
+    latent, size, dim = 24, 64, 8
+    cfg = DacConfig(hidden_size=latent, codebook_size=size, codebook_dim=dim)
+    theirs = dac.DacVectorQuantize(cfg).eval()
+    mine = snac_ref.VectorQuantize(latent, size, dim, 1).eval()
+    with torch.no_grad():
+        mine.in_proj.weight_g.mul_(0.8 + 0.4 * torch.rand_like(mine.in_proj.weight_g))
+        mine.out_proj.weight_g.mul_(0.8 + 0.4 * torch.rand_like(mine.out_proj.weight_g))
+        theirs.in_proj.weight.copy_(mine.in_proj._w()); theirs.in_proj.bias.copy_(mine.in_proj.bias)
+        theirs.out_proj.weight.copy_(mine.out_proj._w()); theirs.out_proj.bias.copy_(mine.out_proj.bias)
+        theirs.codebook.weight.copy_(mine.codebook.weight)
+        z = torch.randn(3, latent, 50)
+        z_q, idx = mine.encode(z)
+        out = theirs(z)
+    # DacVectorQuantize.forward -> (quantized [through out_proj], commitment, codebook loss, indices, projected latents)
+    q_t, idx_t = out[0], out[3]
+    assert torch.equal(idx, idx_t)
+    assert torch.allclose(z_q, q_t, atol=1e-5), float((z_q - q_t).abs().max())
