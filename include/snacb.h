@@ -363,6 +363,10 @@ int snacb_egress_flush(snacb_egress* g, int32_t slot, void* stream);
 /* Barge-in / slot reuse: drop unread samples and the kept tail (host-only and immediate, the device state follows with
  * the slot's next push; no push of this slot may be in flight). */
 int snacb_egress_reset(snacb_egress* g, int32_t slot, void* stream);
+/* Zero-call consumers: host addresses of the write cursors (pinned int64 [n_slots], published by the kernels) and the read
+ * cursors (int64 [n_slots]); a consumer copies samples [rpos, min(wpos, rpos + n)) out of snacb_egress_ring_base(slot)
+ * (modulo ring_samples) and advances rpos[slot] itself - what snacb_egress_read does. */
+int snacb_egress_cursors(snacb_egress* g, const int64_t** wpos, int64_t** rpos);
 /* Samples written to the slot since its last reset (as of the last snacb_egress_sync). */
 int64_t snacb_egress_written(const snacb_egress* g, int32_t slot);
 /* One tick from host token buffers into the rings: snacb_decode_windows_host with the PCM going to slot h_slots[i] of

@@ -139,6 +139,7 @@ SIGNATURES = {
     "snacb_egress_flush": (_i32, [_vp, _i32, _vp]),
     "snacb_egress_reset": (_i32, [_vp, _i32, _vp]),
     "snacb_egress_written": (_i64, [_vp, _i32]),
+    "snacb_egress_cursors": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "snacb_decode_windows_to_ring": (_i32, [_vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _u64, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 

@@ -138,8 +138,14 @@ class SnacB200Adapter:
             if want is None:
                 want = speechpipe.snac_device == "cuda" and os.environ.get("SNACB_GPU_RING", "1") != "0"
             if want and not isinstance(self._ring, _GpuSlot):
-                self._ring = _GpuSlot(speechpipe.get_ring())
-                self._high_water = min(self._high_water, 2 * (speechpipe.get_ring().ring_samples - 4096))
+                try:
+                    self._ring = _GpuSlot(speechpipe.get_ring())
+                    self._high_water = min(self._high_water, 2 * (speechpipe.get_ring().ring_samples - 4096))
+                except speechpipe._lib.SnacbError as e:
+                    if self._gpu_ring:  # asked for explicitly
+                        raise
+                    # more live requests than ring slots (SNACB_RING_SLOTS): this request keeps its PCM in host bytes
+                    speechpipe.log.warning("GPU PCM ring unavailable for this request (%s): using the host ring", e)
             if isinstance(self._ring, _GpuSlot):
                 kwargs["ring_slot"] = self._ring.slot
         if self.seed is not None and "stream_key" in inspect.signature(decoder).parameters:

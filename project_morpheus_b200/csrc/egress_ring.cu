@@ -145,7 +145,7 @@ struct snacb_egress {
   int* h_args = nullptr;          // pinned
   int args_cap = 0;
   cudaEvent_t args_free = nullptr;  // the previous push has consumed h_args
-  std::vector<long long> rpos;    // host read cursors
+  std::vector<long long> rpos;    // host read cursors (snacb_egress_cursors hands their address to zero-call consumers)
   std::vector<long long> wbound;  // upper bound of the device write cursor (pushes in flight included)
   std::vector<int> seen;          // duplicate-slot check, tick stamp
   std::vector<char> lazy_reset;   // the slot was reset on the host; the device state follows with its next push
@@ -341,6 +341,18 @@ int snacb_egress_reset(snacb_egress* g, int32_t slot, void* stream) {
   g->h_wpos[slot] = 0;
   g->rpos[(size_t)slot] = 0;
   g->wbound[(size_t)slot] = 0;
+  return SNACB_OK;
+}
+
+// For consumers that read the rings without a call per read (the Python adapter): host addresses of the published write
+// cursors (pinned, int64 [n_slots], samples written since the slot's reset) and of the read cursors (int64 [n_slots]: the
+// consumer advances rpos[slot] itself after copying samples [rpos, rpos + n) out of snacb_egress_ring_base(slot); the
+// room check of the pushes reads them).  Valid for the lifetime of the object.
+int snacb_egress_cursors(snacb_egress* g, const int64_t** wpos, int64_t** rpos) {
+  if (!g || !wpos || !rpos) return SNACB_EINVAL;
+  static_assert(sizeof(long long) == sizeof(int64_t), "cursor width");
+  *wpos = reinterpret_cast<const int64_t*>(g->h_wpos);
+  *rpos = reinterpret_cast<int64_t*>(g->rpos.data());
   return SNACB_OK;
 }
 

@@ -140,8 +140,14 @@ class GpuPcmRing:
         self.n_slots, self.ring_samples, self.device = int(n_slots), int(ring_samples), int(device)
         self.overlap_samples = int(self._lib.snacb_egress_overlap_samples(self._h))
         self._free = list(range(self.n_slots - 1, -1, -1))
-        self._scratch = bytearray(8192)
-        self._scratch_c = (C.c_char * len(self._scratch)).from_buffer(self._scratch)
+        # zero-call reads: views of the pinned rings and of both cursor arrays
+        wp, rp = C.c_void_p(), C.c_void_p()
+        if self._lib.snacb_egress_cursors(self._h, C.byref(wp), C.byref(rp)) != _lib.OK:
+            raise _lib.SnacbError("snacb_egress_cursors failed")
+        self._wpos = np.ctypeslib.as_array((C.c_int64 * self.n_slots).from_address(wp.value))
+        self._rpos = np.ctypeslib.as_array((C.c_int64 * self.n_slots).from_address(rp.value))
+        base = self._lib.snacb_egress_ring_base(self._h, 0)
+        self._ring_mv = memoryview((C.c_char * (2 * self.n_slots * self.ring_samples)).from_address(base)).cast("B")
 
     @property
     def handle(self) -> C.c_void_p:
@@ -149,6 +155,7 @@ class GpuPcmRing:
 
     def close(self) -> None:
         if getattr(self, "_h", None) and self._h.value:
+            self._wpos = self._rpos = self._ring_mv = None  # views into memory the library is about to free
             self._lib.snacb_egress_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -182,9 +189,7 @@ class GpuPcmRing:
 
     def available(self, slot: int) -> int:
         """Unread bytes of the slot."""
-        n = int(self._lib.snacb_egress_available(self._h, int(slot)))
-        self._check(n, "snacb_egress_available")
-        return 2 * n
+        return 2 * (int(self._wpos[slot]) - int(self._rpos[slot]))
 
     def room(self, slot: int) -> int:
         """Samples a tick may still add to the slot."""
@@ -193,17 +198,22 @@ class GpuPcmRing:
         return n
 
     def read(self, slot: int, nbytes: int) -> bytes:
-        """Up to ``nbytes`` (rounded down to whole samples) of the slot's unread PCM."""
-        want = max(0, int(nbytes)) // 2
-        if want <= 0:
+        """Up to ``nbytes`` (rounded down to whole samples) of the slot's unread PCM: one copy out of the pinned ring, no
+        native call (the read cursor lives in memory shared with the library, see ``snacb_egress_cursors``)."""
+        r = int(self._rpos[slot])
+        n = min(max(0, int(nbytes)) // 2, int(self._wpos[slot]) - r)
+        if n <= 0:
             return b""
-        want = min(want, self.ring_samples)
-        if 2 * want > len(self._scratch):
-            self._scratch = bytearray(2 * want)
-            self._scratch_c = (C.c_char * len(self._scratch)).from_buffer(self._scratch)
-        got = int(self._lib.snacb_egress_read(self._h, int(slot), self._scratch_c, want))
-        self._check(got, "snacb_egress_read")
-        return bytes(memoryview(self._scratch)[: 2 * got])
+        R = self.ring_samples
+        off = r % R
+        b0 = 2 * (slot * R + off)
+        if off + n <= R:
+            data = self._ring_mv[b0: b0 + 2 * n].tobytes()
+        else:
+            first = R - off
+            data = self._ring_mv[b0: b0 + 2 * first].tobytes() + self._ring_mv[2 * slot * R: 2 * (slot * R + n - first)].tobytes()
+        self._rpos[slot] = r + n
+        return data
 
     def flush(self, slot: int, stream: Optional[int] = None) -> None:
         """End of the stream without an eos chunk: the kept crossfade tail is emitted."""

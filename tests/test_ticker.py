@@ -42,6 +42,9 @@ class FakeGpuRing:
         self._free = list(range(n - 1, -1, -1))
 
     def acquire(self):
+        if not self._free:
+            from project_morpheus_b200 import _lib
+            raise _lib.SnacbError("all slots are in use")
         return self._free.pop()
 
     def release(self, slot):
@@ -345,3 +348,45 @@ def test_adapters_over_gpu_ring_slots(speechpipe):
     first, again = asyncio.run(barge())
     assert first == want[0][:100] and again == want[0]
     assert len(speechpipe.fake_ring._free) == 128
+
+
+def test_more_requests_than_ring_slots_fall_back_to_the_host_ring(speechpipe, monkeypatch):
+    """Auto mode (gpu_ring=None on a CUDA host): when every ring slot is taken a request keeps its PCM in host bytes
+    instead of failing; asking for the GPU ring explicitly raises."""
+    from project_morpheus_b200 import _lib
+
+    monkeypatch.setattr(speechpipe, "snac_device", "cuda")
+    monkeypatch.setenv("SNACB_GPU_RING", "1")
+    small = FakeGpuRing(2)
+    monkeypatch.setattr(speechpipe, "get_ring", lambda: small)
+    speechpipe.fake_ring.bufs = small.bufs  # the stand-in batch function writes into fake_ring.bufs
+    streams = [sp.synth_token_strings(700 + i, 5) for i in range(4)]
+    want = [b"".join(sp.decode_stream(s, fake_convert)) for s in streams]
+
+    async def drain(ad):
+        out = bytearray()
+        while True:
+            c = await ad.pull(512)
+            out += c.pcm
+            if c.eos:
+                return bytes(out)
+
+    async def main():
+        ads = [SnacB200Adapter("p", token_source=_source(s, gap=3), seed=i) for i, s in enumerate(streams)]
+        res = await asyncio.gather(*[drain(a) for a in ads])
+        return res
+
+    assert asyncio.run(main()) == want
+    assert len(small._free) == 2
+
+    async def explicit():
+        hold = [SnacB200Adapter("p", token_source=_source(streams[0], gap=1), gpu_ring=True) for _ in range(3)]
+        firsts = [await hold[0].pull(8), await hold[1].pull(8)]
+        with pytest.raises(_lib.SnacbError):
+            await hold[2].pull(8)
+        for h in hold[:2]:
+            await h.reset()
+        return firsts
+
+    asyncio.run(explicit())
+    assert len(small._free) == 2
