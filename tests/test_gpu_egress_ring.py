@@ -251,3 +251,68 @@ def test_adapters_with_gpu_crossfade_equal_host_stitcher_over_the_serial_decoder
         assert len(want) >= 4096
     assert sum(len(g) > 3 * 4096 for g in got) >= n // 2   # most streams crossfade several windows
     sys.modules.pop("project_morpheus_b200.speechpipe", None)
+
+
+def test_barge_in_storm_over_gpu_rings(state_dict_w1, monkeypatch):
+    """Slot reuse under fire: 96 adapters on 40 ring slots' worth of concurrency, a third of them reset (barge-in) at a
+    random point while their window may be queued or on the GPU, slots handed straight to new requests.  Every request
+    that runs to its end delivers exactly the bytes of the serial decoder, and every slot comes back."""
+    import asyncio
+    import importlib
+    import random
+    import sys
+
+    from oracle import speechpipe_ref as sp
+
+    monkeypatch.setenv("SNACB_NOISE", "off")
+    monkeypatch.setenv("SNACB_PRECISION", "fp16")
+    monkeypatch.setenv("SNACB_RANDOM_INIT", "0:w1")
+    monkeypatch.setenv("SNACB_GPU_RING", "1")
+    monkeypatch.setenv("SNACB_RING_SLOTS", "40")
+    monkeypatch.setenv("SNACB_RING_OVERLAP_MS", "0")
+    monkeypatch.delenv("ORPHEUS_SNAC_PATH", raising=False)
+    sys.modules.pop("project_morpheus_b200.speechpipe", None)
+    speechpipe = importlib.import_module("project_morpheus_b200.speechpipe")
+    from project_morpheus_b200.adapter import SnacB200Adapter
+
+    rnd = random.Random(7)
+    n = 96
+    streams = [sp.synth_token_strings(1200 + i, 4 + (i % 8)) for i in range(n)]
+
+    def source(strings):
+        async def gen(**_):
+            for i, s in enumerate(strings):
+                if i % 3 == 0:
+                    await asyncio.sleep(0)
+                yield s
+        return gen
+
+    async def request(i, gate):
+        async with gate:  # at most 40 requests alive: one ring slot each
+            ad = SnacB200Adapter("p", token_source=source(streams[i]), seed=i, gpu_ring=True)
+            size = rnd.choice([256, 1000, 4096])
+            if i % 3 == 0:  # barge-in: pull a little, reset, then play the request from the start
+                for _ in range(rnd.randint(0, 6)):
+                    if (await ad.pull(size)).eos:
+                        break
+                await ad.reset()
+            out = bytearray()
+            while True:
+                c = await ad.pull(size)
+                out += c.pcm
+                if c.eos:
+                    return bytes(out)
+
+    async def main():
+        gate = asyncio.Semaphore(40)
+        return await asyncio.gather(*[request(i, gate) for i in range(n)])
+
+    got = asyncio.run(main())
+    assert len(speechpipe.get_ring()._free) == 40
+
+    async def serial(strings):
+        return b"".join([c async for c in speechpipe.tokens_decoder(source(strings)(), ticker=False)])
+
+    for i in range(n):
+        assert got[i] == asyncio.run(serial(streams[i])), i
+    sys.modules.pop("project_morpheus_b200.speechpipe", None)
