@@ -336,7 +336,10 @@ int snacb_stitch_bank_push(snacb_stitch_bank* b, int32_t n, const int32_t* slots
  * float64 arithmetic, done by a kernel right after the decoder tail), orchestrator/ring_buffer.py:27-83 (the byte ring)
  * and the pull(chunk_size) re-chunking of tts_engine/llama_local.py:120-150 (snacb_egress_read).  A ring is
  * `ring_samples` int16 samples (multiple of 8, >= 4096) of pinned host memory per slot that the GPU writes through its
- * device mapping; the PCM matrix of the tick never crosses PCIe as a separate copy. */
+ * device mapping; the PCM matrix of the tick never crosses PCIe as a separate copy.
+ * Threading: pushes / sync / flush belong to ONE producer thread and stream at a time (the tick loop); reads of a slot may
+ * come from another thread (the consumer of that stream) once the tick that wrote the samples has been synchronised; a
+ * slot is reset or re-used only while no push that names it is in flight. */
 typedef struct snacb_egress snacb_egress;
 int snacb_egress_create(snacb_egress** out, int32_t device, int32_t n_slots, int32_t ring_samples, int32_t sample_rate,
                         double overlap_ms);
