@@ -61,6 +61,7 @@ extern "C" {
 #define SNACB_FLAG_NO_CONVT_NOISE_FUSION 2 /* run ConvTranspose1d and NoiseBlock as two GEMM kernels   */
 #define SNACB_FLAG_NO_PERSISTENT_CONVT 16 /* transposed convs through the one-shot (one tile per CTA) kernels  */
 #define SNACB_FLAG_NO_BLOCK_FUSION 64 /* decoder block 3: one kernel per ResidualUnit + tail kernel instead of the whole-block kernel */
+#define SNACB_FLAG_NO_CONVT_NOISE_COMPOSE 128 /* decoder blocks 0 / 1: ConvTranspose1d and NoiseBlock as two kernels instead of one GEMM over the composed weight */
 #define SNACB_FLAG_FUSE_RU256 32 /* decoder block 1 ResidualUnits through the persistent fused kernel (measured on par: off) */
 
 /* fixed geometry of hubertsiuzdak/snac_24khz (the only model the reference loads, speechpipe.py:42) */

@@ -20,6 +20,7 @@ FLAG_TAIL_FUSION = 8
 FLAG_NO_PERSISTENT_CONVT = 16
 FLAG_FUSE_RU256 = 32
 FLAG_NO_BLOCK_FUSION = 64
+FLAG_NO_CONVT_NOISE_COMPOSE = 128
 NOISE_PER_FRAME = 3360
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsnacb.so")

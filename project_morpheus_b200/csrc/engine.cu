@@ -23,7 +23,9 @@ struct RuDev {
 };
 struct BlockDev {
   float *alpha, *inv, *ct_w /*[s*Cout][2*Cin]*/, *ct_b, *noise_w;
+  float* ct_b2;   // W_n b: the NoiseBlock GEMM's share of the conv bias (composed ConvT + NoiseBlock kernel)
   __half *ct16, *noise16;
+  __half* ctn16;  // blocks 0 / 1, fp16 recipe: stacked [conv rows | W_n conv rows] weight, [2 s Cout][2 Cin]; else null
   RuDev ru[3];
 };
 struct DevWeights {
@@ -110,6 +112,7 @@ struct snacb_engine {
   bool ru256 = false;      // decoder block 1 (C = 256) ResidualUnits through the persistent fused kernel (SNACB_RU256 env)
   bool ruw = true;         // decoder block 1 ResidualUnits through k_ru_w (SNACB_RUW=0 falls back to k_dw_tc + k_gemm_ws)
   bool ruw128 = true;      // decoder block 2 ResidualUnits through k_ru_w<128> (SNACB_RUW128=0 falls back to k_ru_tc<128>)
+  bool convt_n2 = true;    // blocks 0 / 1: ConvTranspose1d + NoiseBlock as ONE GEMM over a composed weight (SNACB_CONVT_N2=0: two kernels)
   // CUDA graphs of small host-API ticks (latency mode): key -> instantiated graph
   struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t gen = 0; int calls = 0; bool disabled = false; };
   std::map<std::vector<long long>, GraphEntry> graphs;
@@ -454,7 +457,19 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
         TcGemmArgs a{};
         a.epi = EPI_CONVT; a.A = Ain; a.K = B.Cin; a.a_rows = B.in.n(); a.a_lo = B.in.lo; a.W = Wb.ct16; a.N = B.s * B.Cout;
         a.bias = Wb.ct_b; a.s = B.s; a.p = B.p; a.Cout = B.Cout; a.o_r = B.ct; a.ldo = B.Cout; a.up = B.up_out;
-        if (fuse_cn) {
+        const bool compose = noisy && Wb.ctn16 != nullptr && e->tap_stage != sid + 1 &&
+                             !(e->cfg.flags & (SNACB_FLAG_NO_CONVT_NOISE_FUSION | SNACB_FLAG_NO_CONVT_NOISE_COMPOSE));
+        if (compose) {
+          // blocks 0 / 1: y + n (W_n y) from ONE GEMM over the stacked weight [W_c | W_n W_c] (used for every tick size)
+          a.out32 = X;
+          a.noise = NoiseSrc{nz.mode, nz.tensor, nz.stride, noise_off[b], (unsigned long long)nz.seed, nz.d_keys, b, nz.d_seed};
+          if (ce == cudaSuccess) {
+            const double M = (double)n * a.a_rows;
+            ProfScope ps(e, KC_CONVT, 2.0 * M * a.N * a.K * 2.0 * 2.0,
+                         2.0 * (M * a.K * 2.0 + 2.0 * (double)a.N * a.K * 2.0) + 4.0 * (double)n * B.ct.n() * B.Cout, st);
+            ce = launch_convt_noise2_tc(g, a, Wb.ctn16, Wb.ct_b2);
+          }
+        } else if (fuse_cn) {
           a.out32 = X;
           a.noise = NoiseSrc{nz.mode, nz.tensor, nz.stride, noise_off[b], (unsigned long long)nz.seed, nz.d_keys, b, nz.d_seed};
           if (ce == cudaSuccess) {
@@ -469,7 +484,8 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
           tap(e, sid + 1, noisy ? Y : X, B.ct, B.Cout, n, first, st);
         }
       }
-      if (noisy && !fuse_cn) {
+      if (noisy && !fuse_cn && !(Wb.ctn16 != nullptr && e->tap_stage != sid + 1 &&
+                                 !(e->cfg.flags & (SNACB_FLAG_NO_CONVT_NOISE_FUSION | SNACB_FLAG_NO_CONVT_NOISE_COMPOSE)))) {
         TcGemmArgs a{};
         a.epi = EPI_NOISE; a.A = Y16; a.K = B.Cout; a.a_rows = B.ct.n(); a.a_lo = B.ct.lo; a.W = Wb.noise16; a.N = B.Cout;
         a.out32 = X; a.o_r = B.ct; a.ldo = B.Cout; a.R = Y; a.r_r = B.ct; a.ldr = B.Cout; a.up = B.up_out;
@@ -778,6 +794,8 @@ int snacb_create(snacb_engine** out, const snacb_config* cfg) {
     e->ruw = !(rw && rw[0] == '0');
     const char* rw2 = getenv("SNACB_RUW128");
     e->ruw128 = !(rw2 && rw2[0] == '0');
+    const char* cn2 = getenv("SNACB_CONVT_N2");
+    e->convt_n2 = !(cn2 && cn2[0] == '0') && !(cfg->flags & SNACB_FLAG_NO_CONVT_NOISE_COMPOSE);
     const char* gr = getenv("SNACB_GRAPHS");
     if (gr) e->graph_max_win = atoi(gr);  // 0 disables the CUDA-graph path
   }
@@ -851,6 +869,15 @@ int snacb_load_weights(snacb_engine* e, const snacb_weights* w) {
     fix.push_back({&D.blk[b].ct_w, add_convt(hp, s.convt_w, cin, cout, st)});
     put(&D.blk[b].ct_b, s.convt_b, cout);
     put(&D.blk[b].noise_w, s.noise_w, (size_t)cout * cout);
+    {
+      const size_t off = hp.add(nullptr, cout);
+      for (int o = 0; o < cout; ++o) {
+        double acc = 0.0;
+        for (int c = 0; c < cout; ++c) acc += (double)s.noise_w[(size_t)o * cout + c] * s.convt_b[c];
+        hp.data[off + o] = (float)acc;
+      }
+      fix.push_back({&D.blk[b].ct_b2, off});
+    }
     for (int r = 0; r < 3; ++r) {
       const snacb_ru_weights& u = s.ru[r];
       RuDev& R = D.blk[b].ru[r];
@@ -899,11 +926,36 @@ int snacb_load_weights(snacb_engine* e, const snacb_weights* w) {
       for (int r = 0; r < 3; ++r) hput(&D.blk[b].ru[r].pw16, D.blk[b].ru[r].pw_w, co, 1, co);
       ci = co;
     }
+    // composed ConvT + NoiseBlock weights of the wide blocks (single-pass fp16 recipe only)
+    size_t ctn_off[4] = {0, 0, 0, 0};
+    {
+      int c_in = kDecDim;
+      for (int b = 0; b < 4; ++b) {
+        const int co = c_in / 2;
+        D.blk[b].ctn16 = nullptr;
+        if (!x3 && e->convt_n2 && convt_noise2_supported(c_in, co)) {
+          ctn_off[b] = hoff + 1;  // +1: marks "present"
+          hoff += ((size_t)2 * kRates[b] * co * 2 * c_in + 127) & ~size_t(127);
+        }
+        c_in = co;
+      }
+    }
     CU(e, cudaMalloc((void**)&e->harena, hoff * sizeof(__half)));
     for (const H& h : hs) {
       *h.dst = e->harena + h.off;
       if (x3) launch_split_w(h.src, *h.dst, h.N, h.nseg, h.K, 0);
       else launch_to_half(h.src, *h.dst, (size_t)h.N * h.nseg * h.K, 0);
+    }
+    {
+      int c_in = kDecDim;
+      for (int b = 0; b < 4; ++b) {
+        const int co = c_in / 2;
+        if (ctn_off[b]) {
+          D.blk[b].ctn16 = e->harena + (ctn_off[b] - 1);
+          launch_compose_ctn(D.blk[b].ct_w, D.blk[b].noise_w, co, kRates[b] * co, 2 * c_in, D.blk[b].ctn16, 0);
+        }
+        c_in = co;
+      }
     }
     CU(e, cudaGetLastError());
     CU(e, cudaDeviceSynchronize());

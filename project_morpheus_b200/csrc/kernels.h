@@ -82,6 +82,10 @@ struct TcGemmArgs {
   int split = 0;
 };
 cudaError_t launch_gemm_tc(const GroupCtx& g, const TcGemmArgs& a);
+// composed ConvT + NoiseBlock for the wide blocks (Cout % 256 == 0): one GEMM over a stacked weight [conv rows | W_n conv rows]
+bool convt_noise2_supported(int Cin, int Cout);
+void launch_compose_ctn(const float* ct, const float* wn, int Cout, int N, int K2, __half* out, cudaStream_t st);
+cudaError_t launch_convt_noise2_tc(const GroupCtx& g, const TcGemmArgs& a, const __half* W2, const float* bias2);
 // fp32 [rows][C] (-> optional Snake) -> fp16 [rows][2C] = [hi | lo]: the split operand of the recipe above
 void launch_split16(const float* in, __half* out, size_t rows, int C, const float* alpha, const float* inv, cudaStream_t st,
                     int64_t* launches);

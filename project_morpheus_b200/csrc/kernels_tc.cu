@@ -155,6 +155,7 @@ struct TcDev {
   int up;
   int n_tiles;              // k_gemm_tc: N tiles per M tile (linear grid, N tile fastest)
   int split;                // split-operand recipe: segment = tap * 3 + term, A columns [hi | lo]
+  const float* bias2;       // composed ConvT + NoiseBlock kernel: W_n b (the noise GEMM's share of the conv bias), [Cout]
 };
 
 template <int BN> struct TcSmem {
@@ -845,19 +846,27 @@ template <int BN> struct CtpSmem {
   static constexpr int kStages = 4;
   static constexpr int kStageBytes = BM * BK * 2 + BN * BK * 2;
   static constexpr int kStgBytes = 8 * 32 * 16 * 4;
-  static constexpr int kBytes = kStages * kStageBytes + kStgBytes + 2 * BM * 4 + 256 + 1024;
+  static constexpr int kBytes = kStages * kStageBytes + kStgBytes + 4 * BM * 4 + 256 + 1024;  // meta: [2][BM] rows + [2][BM] noise
 };
 
-template <int BN>
+// N2 (composed ConvT + NoiseBlock, blocks 0 / 1): the NoiseBlock x = y + n[t] * (W_n y) of the conv output y = A W_c^T + b
+// needs no second pass over y: W_n y = A (W_n W_c)^T + W_n b is a GEMM over the SAME operand tiles with a composed weight.
+// The weight matrix handed in is stacked per 128-channel slice: 128 rows of W_c, then the 128 matching rows of W_n W_c -
+// one 256-row operand box, one N = 256 MMA: accumulator columns [0,128) hold the conv, [128,256) the noise GEMM, and the
+// epilogue writes y + b + n[t] * (noise + W_n b) as fp32.  Twice the MMAs of the plain conv (the tensor pipe has room:
+// 54-70 % busy), but the separate noise GEMM kernel, its fp16 operand copy and one fp32 round trip of y are gone.
+template <int BN, bool N2>
 __global__ void __launch_bounds__(kTcThreads, 1) k_convt_p(const __grid_constant__ CUtensorMap tmA,
                                                          const __grid_constant__ CUtensorMap tmW, const TcDev a,
                                                          const int n_tiles, const int total_tiles) {
   using S = CtpSmem<BN>;
+  constexpr int CN = N2 ? BN / 2 : BN;  // output channels per tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
   float* sStg = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes);
   int* meta = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(sStg) + S::kStgBytes);  // [2][BM] output row of each tile row
-  uint64_t* bars = reinterpret_cast<uint64_t*>(meta + 2 * BM);
+  float* meta_nz = reinterpret_cast<float*>(meta + 2 * BM);                              // [2][BM] noise sample of each tile row (N2)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(meta + 4 * BM);
   // bars: [0..3] full, [4..7] empty, [8..9] t_full, [10..11] t_empty
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -880,8 +889,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_convt_p(const __grid_constant
       int it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int nt = t % n_tiles, mt = t / n_tiles;
-        const int n0 = nt * BN, m0 = mt * BM;
-        const int phase = n0 / a.Cout, delta = (phase < a.s - a.p) ? -1 : 1;
+        const int n0 = nt * BN, m0 = mt * BM;  // n0: first row of the (stacked) weight matrix
+        const int phase = (nt * CN) / a.Cout, delta = (phase < a.s - a.p) ? -1 : 1;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int st = it % S::kStages;
           mbar_wait(smem_u32(&bars[4 + st]), ((it / S::kStages) & 1) ^ 1);
@@ -926,13 +935,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_convt_p(const __grid_constant
     int ti = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
       const int nt = t % n_tiles, mt = t / n_tiles;
-      const int n0 = nt * BN, phase = n0 / a.Cout;
+      const int c0 = nt * CN, phase = c0 / a.Cout;  // first output channel (phase-major) of the tile
       const int buf = ti & 1;
       int* m_out = meta + buf * BM;
+      float* m_nz = meta_nz + buf * BM;
       if (half == 0) {
         const int trow = q * 32 + lane;
         const long long gm = (long long)mt * BM + trow;
         int oi = -1;
+        float nz = 0.0f;
         if (gm < Mtot) {
           const int item = (int)(gm / a.a_rows), j = (int)(gm - (long long)item * a.a_rows);
           const ItemRef itr = get_item(a.items, a.base, item, a.out_len);
@@ -941,18 +952,63 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_convt_p(const __grid_constant
           if (orow >= 0 && orow < a.o_rows) {
             const int t_abs = t_rel + itr.shift0 * a.up;
             oi = item * a.o_rows + orow;
-            if (!((t_abs >= 0) && (t_abs < a.T0 * a.up))) oi |= (int)kLiveFlag;
+            const bool live = (t_abs >= 0) && (t_abs < a.T0 * a.up);
+            if (N2 && live) nz = noise_at(a.noise, itr.code_row, t_abs);
+            if (!live) oi |= (int)kLiveFlag;
           }
         }
         m_out[trow] = oi;
+        if (N2) m_nz[trow] = nz;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       int oi4[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) oi4[i] = m_out[q * 32 + r8 + 8 * i];
-      const int ocol0 = n0 - phase * a.Cout + half * (BN / 2) + c4 * 4;
+      const int ocol0 = c0 - phase * a.Cout + half * (CN / 2) + c4 * 4;
       mbar_wait(smem_u32(&bars[8 + buf]), (ti >> 1) & 1);
       tc_fence_after();
+      if (N2) {
+        // row per lane: x = (D1 + b) + n[row] * (D2 + W_n b), then the usual transpose to 64-byte row segments
+        const float2 nz2 = make_float2(m_nz[q * 32 + lane], m_nz[q * 32 + lane]);
+        const uint32_t d1 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * (CN / 2));
+#pragma unroll
+        for (int h = 0; h < CN / 32; ++h) {
+          uint32_t r1[16], r2[16];
+          tmem_ld16_nowait(d1 + (uint32_t)(h * 16), r1);
+          tmem_ld16_nowait(d1 + (uint32_t)(CN + h * 16), r2);
+          tmem_ld_wait();
+          const int colr = c0 - phase * a.Cout + half * (CN / 2) + h * 16;  // this step's first channel (all lanes)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + colr + 4 * j));
+            const float4 b2 = __ldg(reinterpret_cast<const float4*>(a.bias2 + colr + 4 * j));
+            float2 lo = __fadd2_rn(make_float2(__uint_as_float(r1[4 * j]), __uint_as_float(r1[4 * j + 1])), make_float2(b1.x, b1.y));
+            float2 hi = __fadd2_rn(make_float2(__uint_as_float(r1[4 * j + 2]), __uint_as_float(r1[4 * j + 3])), make_float2(b1.z, b1.w));
+            const float2 nlo = __fadd2_rn(make_float2(__uint_as_float(r2[4 * j]), __uint_as_float(r2[4 * j + 1])), make_float2(b2.x, b2.y));
+            const float2 nhi = __fadd2_rn(make_float2(__uint_as_float(r2[4 * j + 2]), __uint_as_float(r2[4 * j + 3])), make_float2(b2.z, b2.w));
+            lo = __ffma2_rn(nz2, nlo, lo);
+            hi = __ffma2_rn(nz2, nhi, hi);
+            *reinterpret_cast<float4*>(st_p + ((j ^ st_x) << 2)) = make_float4(lo.x, lo.y, hi.x, hi.y);
+          }
+          __syncwarp();
+          float4 v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(ld_p + i * 128);
+          __syncwarp();
+          const int ocol = ocol0 + h * 16;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            int oi = oi4[i];
+            if (oi < 0) continue;
+            const bool live = !(oi & (int)kLiveFlag);
+            oi &= (int)(kLiveFlag - 1);
+            *reinterpret_cast<float4*>(a.out32 + (size_t)oi * a.ldo + ocol) = live ? v[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        tc_fence_before();
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[10 + buf])) : "memory");
+        continue;
+      }
 #pragma unroll
       for (int h = 0; h < NH; ++h) {
         uint32_t r[16];
@@ -1414,11 +1470,11 @@ cudaError_t launch_gemm_tc(const GroupCtx& g, const TcGemmArgs& a) {
       static bool attr_set_dev[kMaxDev] = {};
   bool& attr_set = attr_set_dev[cur_dev()];  // kernel attributes are per device
       if (!attr_set) {
-        cudaError_t e0 = cudaFuncSetAttribute(k_convt_p<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, CtpSmem<256>::kBytes);
+        cudaError_t e0 = cudaFuncSetAttribute(k_convt_p<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CtpSmem<256>::kBytes);
         if (e0 != cudaSuccess) return e0;
         attr_set = true;
       }
-      k_convt_p<256><<<sm_count(), kTcThreads, CtpSmem<256>::kBytes, g.stream>>>(ma, mw256, d, n_tiles, (int)total);
+      k_convt_p<256, false><<<sm_count(), kTcThreads, CtpSmem<256>::kBytes, g.stream>>>(ma, mw256, d, n_tiles, (int)total);
       ++*g.launches;
       return cudaGetLastError();
     }
@@ -1428,6 +1484,78 @@ cudaError_t launch_gemm_tc(const GroupCtx& g, const TcGemmArgs& a) {
   cudaError_t e = (bn == 128) ? launch_tc_bn<128>(a.epi, ma, mw, d, grid, g.stream) : launch_tc_bn<64>(a.epi, ma, mw, d, grid, g.stream);
   ++*g.launches;
   return e;
+}
+
+// ---- composed ConvT + NoiseBlock (blocks 0 / 1), see k_convt_p<BN, true>
+namespace {
+// Stacked fp16 weight [2N][K2] from the packed fp32 conv weight ct [N = s * Cout][K2 = 2 Cin] and the NoiseBlock weight
+// wn [Cout][Cout]: per 128-row slice i, rows [256 i, 256 i + 128) = ct rows [128 i, ..), rows [256 i + 128, 256 i + 256) =
+// (W_n ct_phase) rows, (W_n ct_phase)[o][k] = sum_c wn[o][c] * ct[phase * Cout + c][k].  Runs once per weight load.
+__global__ void __launch_bounds__(256) k_compose_ctn(const float* __restrict__ ct, const float* __restrict__ wn, int Cout, int N, int K2,
+                                                     __half* __restrict__ out) {
+  __shared__ float s_wn[8][64];  // 8 output rows x 64 contraction steps
+  const int k = blockIdx.x * 32 + (threadIdx.x & 31), ty = threadIdx.x >> 5;  // 32 columns x 8 rows per block
+  const int n = blockIdx.y * 8 + ty;
+  const int phase = n / Cout, o = n - phase * Cout;  // a block's 8 rows share the phase (Cout % 8 == 0)
+  float acc = 0.0f;
+  for (int c0 = 0; c0 < Cout; c0 += 64) {
+    for (int e = threadIdx.x; e < 8 * 64; e += 256) {
+      const int rr = e >> 6, cc = e & 63;
+      s_wn[rr][cc] = wn[(size_t)(blockIdx.y * 8 + rr - phase * Cout) * Cout + c0 + cc];
+    }
+    __syncthreads();
+    if (k < K2) {
+#pragma unroll 8
+      for (int c = 0; c < 64; ++c) acc = fmaf(s_wn[ty][c], ct[(size_t)(phase * Cout + c0 + c) * K2 + k], acc);
+    }
+    __syncthreads();
+  }
+  if (k < K2) {
+    const size_t row = (size_t)(n >> 7) * 256 + (n & 127);
+    out[row * K2 + k] = __float2half_rn(ct[(size_t)n * K2 + k]);
+    out[(row + 128) * K2 + k] = __float2half_rn(acc);
+  }
+  (void)o;
+}
+
+}  // namespace
+void launch_compose_ctn(const float* ct, const float* wn, int Cout, int N, int K2, __half* out, cudaStream_t st) {
+  dim3 grid((unsigned)((K2 + 31) / 32), (unsigned)(N / 8));
+  k_compose_ctn<<<grid, 256, 0, st>>>(ct, wn, Cout, N, K2, out);
+}
+
+// Block 1 only (Cin = 512, Cout = 256): its conv leaves the tensor pipe 54 % busy, so the doubled MMA work is cheaper than the
+// separate noise GEMM (216 + 185 -> 316 us per 1024-window tick).  Block 0's conv is already 70 % tensor-busy: composed it
+// measured 380 us against 221 + 140.
+bool convt_noise2_supported(int Cin, int Cout) { return Cout == 256 && Cin % BK == 0; }
+
+// a: the EPI_CONVT arguments of the layer (fp32 output only); W2: the stacked weight [2 N][2 K]; bias2 = W_n b.
+cudaError_t launch_convt_noise2_tc(const GroupCtx& g, const TcGemmArgs& a, const __half* W2, const float* bias2) {
+  if (a.epi != EPI_CONVT || !a.out32 || a.out16 || a.sn_alpha || a.split || !W2 || !bias2 || !convt_noise2_supported(a.K, a.Cout) ||
+      a.N != a.s * a.Cout || g.n_items <= 0 || a.a_rows <= 0)
+    return cudaErrorInvalidValue;
+  const long long Mtot = (long long)g.n_items * a.a_rows;
+  CUtensorMap ma, mw;
+  if (!get_tmap(a.A, Mtot, a.K, BM, &ma) || !get_tmap(W2, 2LL * a.N, 2 * a.K, 256, &mw)) return cudaErrorNotSupported;
+  TcDev d{};
+  d.items = g.items; d.base = g.base; d.out_len = g.out_len; d.T0 = g.T0; d.n_items = g.n_items;
+  d.K = a.K; d.nseg = 2; d.a_rows = a.a_rows; d.a_lo = a.a_lo; d.s = a.s; d.p = a.p; d.Cout = a.Cout;
+  d.bias = a.bias; d.bias2 = bias2; d.out32 = a.out32; d.o_lo = a.o_r.lo; d.o_rows = a.o_r.n(); d.ldo = a.ldo;
+  d.noise = a.noise; d.up = a.up;
+  const int n_tiles = a.N / 128, m_tiles = (int)((Mtot + BM - 1) / BM);
+  const long long total = (long long)n_tiles * m_tiles;
+  if (total >= (1LL << 31)) return cudaErrorInvalidValue;
+  static bool attr_set_dev[kMaxDev] = {};
+  bool& attr_set = attr_set_dev[cur_dev()];
+  if (!attr_set) {
+    cudaError_t e0 = cudaFuncSetAttribute(k_convt_p<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CtpSmem<256>::kBytes);
+    if (e0 != cudaSuccess) return e0;
+    attr_set = true;
+  }
+  const int grid = (int)std::min<long long>(total, sm_count());
+  k_convt_p<256, true><<<grid, kTcThreads, CtpSmem<256>::kBytes, g.stream>>>(ma, mw, d, n_tiles, (int)total);
+  ++*g.launches;
+  return cudaGetLastError();
 }
 
 // ============================================================================ depthwise k=7 -> fp16

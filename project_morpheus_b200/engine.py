@@ -30,7 +30,8 @@ class SnacEngine:
     def __init__(self, state_dict: Dict[str, torch.Tensor], device: int = 0, precision: str = "fp16",
                  chunk_items: int = 0, trim: bool = True, fuse_ru: bool = True, lanes: int = 1,
                  persistent_ru: bool = False, fuse_convt_noise: bool = True, fuse_tail: bool = False,
-                 persistent_convt: bool = True, fuse_ru256: bool = False, fuse_block: bool = True):
+                 persistent_convt: bool = True, fuse_ru256: bool = False, fuse_block: bool = True,
+                 compose_convt_noise: bool = True):
         self._lib = _lib.load()
         self._h = C.c_void_p()
         if not torch.cuda.is_available():
@@ -46,7 +47,8 @@ class SnacEngine:
                           | (_lib.FLAG_TAIL_FUSION if fuse_tail else 0)
                           | (0 if persistent_convt else _lib.FLAG_NO_PERSISTENT_CONVT)
                           | (_lib.FLAG_FUSE_RU256 if fuse_ru256 else 0)
-                          | (0 if fuse_block else _lib.FLAG_NO_BLOCK_FUSION), lanes=int(lanes))
+                          | (0 if fuse_block else _lib.FLAG_NO_BLOCK_FUSION)
+                          | (0 if compose_convt_noise else _lib.FLAG_NO_CONVT_NOISE_COMPOSE), lanes=int(lanes))
         torch.cuda.init()
         with torch.cuda.device(self.device):
             torch.zeros(1, device=self.torch_device)  # make sure the primary context exists

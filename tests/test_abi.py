@@ -37,7 +37,7 @@ def test_header_constants_match_the_ctypes_binding():
             assert getattr(_lib, name) == val, name
             checked += 1
     for flag in ("FLAG_NO_RU_FUSION", "FLAG_NO_CONVT_NOISE_FUSION", "FLAG_PERSISTENT_RU", "FLAG_TAIL_FUSION",
-                 "FLAG_NO_PERSISTENT_CONVT", "FLAG_FUSE_RU256", "FLAG_NO_BLOCK_FUSION"):
+                 "FLAG_NO_PERSISTENT_CONVT", "FLAG_FUSE_RU256", "FLAG_NO_BLOCK_FUSION", "FLAG_NO_CONVT_NOISE_COMPOSE"):
         assert flag in defs and getattr(_lib, flag) == defs[flag]
     assert checked >= 10
     assert _lib.PREC_FP16X3 == defs["PREC_FP16X3"] and _lib.WIN_NONFINITE == defs["WIN_NONFINITE"]

@@ -696,14 +696,15 @@ def test_large_tick_persistent_kernels_match_oracle(engines, oracle_w1, persiste
     n, frames = 320, 4
     tok = windows_tokens(n, frames, base_stream=4100)
     noise = snac_ref.make_noise(n, frames, seed=23)
-    eng = engines("fp16", True, persistent_convt=persistent_convt)
+    eng = engines("fp16", True, persistent_convt=persistent_convt, compose_convt_noise=False)
     pcm, st = eng.decode_windows(tok, noise=snac_ref.pack_noise(noise))
     assert (st == _lib.WIN_OK).all()
     idx = [0, 1, 2, 37, 38, 63, 64, 127, 128, 129, 200, 255, 256, 300, 318, 319]
     ref = oracle_decode_windows(oracle_w1, tok[idx], [z[idx] for z in noise])[:, 2048:4096]
     want = pcm_trunc(ref).astype(np.float32) / 32767.0
     _check_wave(want, pcm[idx].astype(np.float32) / 32767.0, TOL_MAX_ABS, TOL_SNR_DB)
-    other, _ = engines("fp16", True, persistent_convt=not persistent_convt).decode_windows(tok, noise=snac_ref.pack_noise(noise))
+    other, _ = engines("fp16", True, persistent_convt=not persistent_convt,
+                       compose_convt_noise=False).decode_windows(tok, noise=snac_ref.pack_noise(noise))
     assert np.array_equal(other, pcm)
 
 
@@ -713,16 +714,17 @@ def test_persistent_and_one_shot_convt_kernels_agree_bitwise(engines, n, frames)
     than one chunk: the persistent transposed-conv kernels and the one-tile-per-CTA kernels produce identical PCM."""
     tok = windows_tokens(n, frames, base_stream=5200)
     keys = list(range(n))
-    a, sa = engines("fp16", True, persistent_convt=True).decode_windows(tok, noise="philox", seed=3, keys=keys)
+    a, sa = engines("fp16", True, persistent_convt=True, compose_convt_noise=False).decode_windows(tok, noise="philox", seed=3, keys=keys)
     a = a.copy()
-    b, sb = engines("fp16", True, persistent_convt=False).decode_windows(tok, noise="philox", seed=3, keys=keys)
+    b, sb = engines("fp16", True, persistent_convt=False, compose_convt_noise=False).decode_windows(tok, noise="philox", seed=3, keys=keys)
     assert np.array_equal(sa, sb) and np.array_equal(a, b)
     if frames > 1:
         assert a.any(axis=1).all()
 
 
 @pytest.mark.parametrize("variant", [dict(persistent_ru=True), dict(fuse_ru=False, fuse_convt_noise=False), dict(lanes=3),
-                                     dict(fuse_tail=True), dict(fuse_ru256=True), dict(persistent_convt=False)])
+                                     dict(fuse_tail=True), dict(fuse_ru256=True), dict(persistent_convt=False),
+                                     dict(compose_convt_noise=False), dict(compose_convt_noise=False, persistent_convt=False)])
 def test_kernel_variants_match_oracle(engines, oracle_w1, variant):
     """Alternative kernel selections of the tensor-core recipe (persistent warp-specialised ResidualUnit
     kernel incl. C = 256; fully unfused layer-per-kernel path; concurrent chunk lanes) meet the same tolerance."""
