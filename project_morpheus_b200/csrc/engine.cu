@@ -112,7 +112,7 @@ struct snacb_engine {
   bool ru256 = false;      // decoder block 1 (C = 256) ResidualUnits through the persistent fused kernel (SNACB_RU256 env)
   bool ruw = true;         // decoder block 1 ResidualUnits through k_ru_w (SNACB_RUW=0 falls back to k_dw_tc + k_gemm_ws)
   bool ruw128 = true;      // decoder block 2 ResidualUnits through k_ru_w<128> (SNACB_RUW128=0 falls back to k_ru_tc<128>)
-  bool convt_n2 = true;    // blocks 0 / 1: ConvTranspose1d + NoiseBlock as ONE GEMM over a composed weight (SNACB_CONVT_N2=0: two kernels)
+  bool convt_n2 = true;    // blocks 1 / 3: ConvTranspose1d + NoiseBlock as ONE GEMM over a composed weight (SNACB_CONVT_N2=0: round-1 kernels)
   // CUDA graphs of small host-API ticks (latency mode): key -> instantiated graph
   struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t gen = 0; int calls = 0; bool disabled = false; };
   std::map<std::vector<long long>, GraphEntry> graphs;
@@ -460,7 +460,7 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
         const bool compose = noisy && Wb.ctn16 != nullptr && e->tap_stage != sid + 1 &&
                              !(e->cfg.flags & (SNACB_FLAG_NO_CONVT_NOISE_FUSION | SNACB_FLAG_NO_CONVT_NOISE_COMPOSE));
         if (compose) {
-          // blocks 0 / 1: y + n (W_n y) from ONE GEMM over the stacked weight [W_c | W_n W_c] (used for every tick size)
+          // blocks 1 / 3: y + n (W_n y) from ONE GEMM over the stacked weight [W_c | W_n W_c] (used for every tick size)
           a.out32 = X;
           a.noise = NoiseSrc{nz.mode, nz.tensor, nz.stride, noise_off[b], (unsigned long long)nz.seed, nz.d_keys, b, nz.d_seed};
           if (ce == cudaSuccess) {
@@ -794,8 +794,8 @@ int snacb_create(snacb_engine** out, const snacb_config* cfg) {
     e->ruw = !(rw && rw[0] == '0');
     const char* rw2 = getenv("SNACB_RUW128");
     e->ruw128 = !(rw2 && rw2[0] == '0');
-    const char* cn2 = getenv("SNACB_CONVT_N2");
-    e->convt_n2 = !(cn2 && cn2[0] == '0') && !(cfg->flags & SNACB_FLAG_NO_CONVT_NOISE_COMPOSE);
+    const char* cn2 = getenv("SNACB_CONVT_N2");  // bit mask over the blocks (kernels_tc.cu), "0" = none
+    e->convt_n2 = !(cn2 && cn2[0] == '0' && cn2[1] == 0) && !(cfg->flags & SNACB_FLAG_NO_CONVT_NOISE_COMPOSE);
     const char* gr = getenv("SNACB_GRAPHS");
     if (gr) e->graph_max_win = atoi(gr);  // 0 disables the CUDA-graph path
   }

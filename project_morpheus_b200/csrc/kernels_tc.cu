@@ -1056,26 +1056,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_convt_p(const __grid_constant
 // one-shot kernel - launch, barrier / TMEM setup, pipeline fill, the W_n load between the two chains -
 // are paid once per SM, and the accumulator pair (D1 conv, D2 noise GEMM) is double-buffered in TMEM so
 // the conv MMAs of tile i+1 run under the two epilogue phases of tile i.
-template <int BN> struct CnpSmem {
-  static constexpr int kStages = (BN == 64) ? 6 : 3;
-  static constexpr int kStageBytes = BM * BK * 2 + BN * BK * 2;
-  static constexpr int kWnBytes = BN * BN * 2;
-  static constexpr int kYBytes = BM * BN * 2;           // fp16 y tile, one per epilogue set; the set's phase-2 transposes alias it
+// CMP (composed weight, see k_convt_p<BN, true>): the operand box of W is [W_c rows | (W_n W_c) rows] of the phase, ONE
+// MMA chain of N = 2 BN fills the accumulator pair, and the kernel loses its first epilogue phase, the y tile, the W_n
+// tile and the second MMA chain: what remains of the epilogue is the final x = (D1 + b) + n (D2 + W_n b).
+template <int BN, bool CMP = false> struct CnpSmem {
+  static constexpr int kStages = (BN == 64) ? (CMP ? 5 : 6) : 3;
+  static constexpr int kStageBytes = BM * BK * 2 + (CMP ? 2 : 1) * BN * BK * 2;
+  static constexpr int kWnBytes = CMP ? 0 : BN * BN * 2;
   static constexpr int kStgBytes = 8 * 32 * 16 * 4;
+  static constexpr int kYBytes = CMP ? kStgBytes : BM * BN * 2;  // fp16 y tile, one per epilogue set; the set's phase-2 transposes alias it
   static constexpr int kMetaBytes = 4 * BM * 4;         // [2][BM] output row + [2][BM] noise sample of each tile row
-  static constexpr int kBytes = kStages * kStageBytes + kWnBytes + 2 * kYBytes + kMetaBytes + BN * 4 + 256 + 1024;
+  static constexpr int kBytes = kStages * kStageBytes + kWnBytes + 2 * kYBytes + kMetaBytes + 2 * BN * 4 + 256 + 1024;
   static_assert(kYBytes >= kStgBytes, "staging aliases the y tile");
+  static_assert(kBytes <= 227 * 1024, "shared memory");
 };
 // warp 0 TMA, warp 1 MMA, warps 2..9 / 10..17 two epilogue sets (even / odd tiles of this CTA, one TMEM accumulator
 // pair each), warps 18..21 output row + Philox noise of upcoming tiles, one row per thread
 constexpr int kCnpThreads = 64 + 2 * 256 + 128;
 
-template <int BN>
+template <int BN, bool CMP>
 __global__ void __launch_bounds__(kCnpThreads, 1) k_convt_noise_p(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmW,
                                                                const __grid_constant__ CUtensorMap tmN, const TcDev a,
                                                                const int total_tiles) {
-  using S = CnpSmem<BN>;
+  using S = CnpSmem<BN, CMP>;
   constexpr int NS = S::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
@@ -1083,8 +1087,8 @@ __global__ void __launch_bounds__(kCnpThreads, 1) k_convt_noise_p(const __grid_c
   uint8_t* sY = sWn + S::kWnBytes;                    // [2 sets][KB2][128 rows][128 B]
   int* meta = reinterpret_cast<int*>(sY + 2 * S::kYBytes);  // [2][BM] output row of each tile row
   float* meta_nz = reinterpret_cast<float*>(meta + 2 * BM);                              // [2][BM] noise sample of each tile row
-  float* sBias = meta_nz + 2 * BM;                                                       // [BN] conv bias (same for every phase)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + BN);
+  float* sBias = meta_nz + 2 * BM;                                                       // [BN] conv bias (same for every phase), [BN] W_n b (CMP)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 2 * BN);
   // bars: [0..NS) full, [NS..2NS) empty, then c1_full[2], c2_full[2], acc_empty[2], y_ready[2], wn_full, meta_full[2], meta_empty[2]
   uint64_t* bx = bars + 2 * NS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bx + 13);
@@ -1105,6 +1109,7 @@ __global__ void __launch_bounds__(kCnpThreads, 1) k_convt_noise_p(const __grid_c
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 4 * BN);
   if (threadIdx.x >= 64 && threadIdx.x < 64 + BN) sBias[threadIdx.x - 64] = a.bias[threadIdx.x - 64];
+  if (CMP && threadIdx.x >= 64 + BN && threadIdx.x < 64 + 2 * BN) sBias[threadIdx.x - 64] = a.bias2[threadIdx.x - 64 - BN];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1112,9 +1117,11 @@ __global__ void __launch_bounds__(kCnpThreads, 1) k_convt_noise_p(const __grid_c
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(smem_u32(&bx[8]), S::kWnBytes);
+      if (!CMP) {
+        mbar_arrive_expect_tx(smem_u32(&bx[8]), S::kWnBytes);
 #pragma unroll
-      for (int kb = 0; kb < KB2; ++kb) tma_load_2d(smem_u32(sWn + kb * BN * 128), &tmN, smem_u32(&bx[8]), kb * BK, 0);
+        for (int kb = 0; kb < KB2; ++kb) tma_load_2d(smem_u32(sWn + kb * BN * 128), &tmN, smem_u32(&bx[8]), kb * BK, 0);
+      }
       int it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int phase = t % a.s, m0 = (t / a.s) * BM;
@@ -1127,12 +1134,32 @@ __global__ void __launch_bounds__(kCnpThreads, 1) k_convt_noise_p(const __grid_c
           const int seg = kb / kb_per_seg, kk = (kb - seg * kb_per_seg) * BK;
           mbar_arrive_expect_tx(full, S::kStageBytes);
           tma_load_2d(sa, &tmA, full, kk, m0 + (seg ? delta : 0));
-          tma_load_2d(sb, &tmW, full, seg * a.K + kk, phase * BN);
+          tma_load_2d(sb, &tmW, full, seg * a.K + kk, phase * (CMP ? 2 * BN : BN));
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (CMP && lane == 0) {
+      // composed weight: one chain of N = 2 BN fills [D1 | D2]
+      constexpr uint32_t idesc2 = umma_idesc_f16(2 * BN);
+      int it = 0;
+      for (int ti = 0; ti < n_my; ++ti) {
+        const int buf = ti & 1;
+        mbar_wait(smem_u32(&bx[4 + buf]), ((ti >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int st = it % NS;
+          mbar_wait(smem_u32(&bars[st]), (it / NS) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + st * S::kStageBytes), sb = sa + BM * BK * 2;
+          const uint64_t da = umma_desc_k_sw128(sa), db = umma_desc_k_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_base + buf * 2 * BN, da + 2 * k, db + 2 * k, idesc2, (kb | k) ? 1u : 0u);
+          umma_commit(smem_u32(&bars[NS + st]));
+        }
+        umma_commit(smem_u32(&bx[2 + buf]));
+      }
+    } else if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(BN);
       int it = 0;
       // The noise GEMM of tile i is two to eight MMAs that the epilogue warps are waiting for, the conv chain of
@@ -1227,6 +1254,7 @@ __global__ void __launch_bounds__(kCnpThreads, 1) k_convt_noise_p(const __grid_c
       const int my_oi = m_out[trow];
       const float my_nz = meta_nz[buf * BM + trow];
       const uint32_t d1_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN + colbase);
+      if (!CMP) {
       mbar_wait(smem_u32(&bx[buf]), (ti >> 1) & 1);
       tc_fence_after();
       asm volatile("bar.sync %0, 256;" ::"r"(1 + set) : "memory");  // the set is done with its transposes (they alias the y tile)
@@ -1255,6 +1283,7 @@ __global__ void __launch_bounds__(kCnpThreads, 1) k_convt_noise_p(const __grid_c
       tc_fence_before();
       asm volatile("bar.sync %0, 256;" ::"r"(1 + set) : "memory");
       if (ew == 0 && lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bx[6 + buf])) : "memory");
+      }  // !CMP
       // ---- phase 2: x = (D1 + b) + n * D2, transposed through the staging tile, stored coalesced
       int oi4[4];
 #pragma unroll
@@ -1278,8 +1307,15 @@ __global__ void __launch_bounds__(kCnpThreads, 1) k_convt_noise_p(const __grid_c
           const float4 b4 = *reinterpret_cast<const float4*>(sBias + col + 4 * j);
           float2 lo = __fadd2_rn(make_float2(__uint_as_float(d1[4 * j]), __uint_as_float(d1[4 * j + 1])), make_float2(b4.x, b4.y));
           float2 hi = __fadd2_rn(make_float2(__uint_as_float(d1[4 * j + 2]), __uint_as_float(d1[4 * j + 3])), make_float2(b4.z, b4.w));
-          lo = __ffma2_rn(nz2, make_float2(__uint_as_float(d2[4 * j]), __uint_as_float(d2[4 * j + 1])), lo);
-          hi = __ffma2_rn(nz2, make_float2(__uint_as_float(d2[4 * j + 2]), __uint_as_float(d2[4 * j + 3])), hi);
+          float2 n_lo = make_float2(__uint_as_float(d2[4 * j]), __uint_as_float(d2[4 * j + 1]));
+          float2 n_hi = make_float2(__uint_as_float(d2[4 * j + 2]), __uint_as_float(d2[4 * j + 3]));
+          if (CMP) {  // the composed GEMM lacks the conv bias's way through W_n
+            const float4 c4b = *reinterpret_cast<const float4*>(sBias + BN + col + 4 * j);
+            n_lo = __fadd2_rn(n_lo, make_float2(c4b.x, c4b.y));
+            n_hi = __fadd2_rn(n_hi, make_float2(c4b.z, c4b.w));
+          }
+          lo = __ffma2_rn(nz2, n_lo, lo);
+          hi = __ffma2_rn(nz2, n_hi, hi);
           d1[4 * j] = __float_as_uint(lo.x); d1[4 * j + 1] = __float_as_uint(lo.y);
           d1[4 * j + 2] = __float_as_uint(hi.x); d1[4 * j + 3] = __float_as_uint(hi.y);
         }
@@ -1377,11 +1413,23 @@ cudaError_t launch_cnp_t(const CUtensorMap& ma, const CUtensorMap& mw, const CUt
   static bool attr_set_dev[kMaxDev] = {};
   bool& attr_set = attr_set_dev[cur_dev()];  // kernel attributes are per device
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_convt_noise_p<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, CnpSmem<BN>::kBytes);
+    cudaError_t e = cudaFuncSetAttribute(k_convt_noise_p<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CnpSmem<BN>::kBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  k_convt_noise_p<BN><<<std::min(total, sm_count()), kCnpThreads, CnpSmem<BN>::kBytes, st>>>(ma, mw, mn, d, total);
+  k_convt_noise_p<BN, false><<<std::min(total, sm_count()), kCnpThreads, CnpSmem<BN>::kBytes, st>>>(ma, mw, mn, d, total);
+  return cudaGetLastError();
+}
+template <int BN>
+cudaError_t launch_cnp2_t(const CUtensorMap& ma, const CUtensorMap& mw, const TcDev& d, int total, cudaStream_t st) {
+  static bool attr_set_dev[kMaxDev] = {};
+  bool& attr_set = attr_set_dev[cur_dev()];
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_convt_noise_p<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CnpSmem<BN, true>::kBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  k_convt_noise_p<BN, true><<<std::min(total, sm_count()), kCnpThreads, CnpSmem<BN, true>::kBytes, st>>>(ma, mw, mw, d, total);
   return cudaGetLastError();
 }
 
@@ -1489,10 +1537,10 @@ cudaError_t launch_gemm_tc(const GroupCtx& g, const TcGemmArgs& a) {
 // ---- composed ConvT + NoiseBlock (blocks 0 / 1), see k_convt_p<BN, true>
 namespace {
 // Stacked fp16 weight [2N][K2] from the packed fp32 conv weight ct [N = s * Cout][K2 = 2 Cin] and the NoiseBlock weight
-// wn [Cout][Cout]: per 128-row slice i, rows [256 i, 256 i + 128) = ct rows [128 i, ..), rows [256 i + 128, 256 i + 256) =
-// (W_n ct_phase) rows, (W_n ct_phase)[o][k] = sum_c wn[o][c] * ct[phase * Cout + c][k].  Runs once per weight load.
+// wn [Cout][Cout]: per slice i of `slice` = min(Cout, 128) rows, rows [2 slice i, 2 slice i + slice) = ct rows [slice i, ..),
+// the next `slice` rows = the matching (W_n ct_phase) rows, (W_n ct_phase)[o][k] = sum_c wn[o][c] * ct[phase * Cout + c][k].  Runs once per weight load.
 __global__ void __launch_bounds__(256) k_compose_ctn(const float* __restrict__ ct, const float* __restrict__ wn, int Cout, int N, int K2,
-                                                     __half* __restrict__ out) {
+                                                     int slice, __half* __restrict__ out) {
   __shared__ float s_wn[8][64];  // 8 output rows x 64 contraction steps
   const int k = blockIdx.x * 32 + (threadIdx.x & 31), ty = threadIdx.x >> 5;  // 32 columns x 8 rows per block
   const int n = blockIdx.y * 8 + ty;
@@ -1511,9 +1559,9 @@ __global__ void __launch_bounds__(256) k_compose_ctn(const float* __restrict__ c
     __syncthreads();
   }
   if (k < K2) {
-    const size_t row = (size_t)(n >> 7) * 256 + (n & 127);
+    const size_t row = (size_t)(n / slice) * 2 * slice + (n % slice);
     out[row * K2 + k] = __float2half_rn(ct[(size_t)n * K2 + k]);
-    out[(row + 128) * K2 + k] = __float2half_rn(acc);
+    out[(row + slice) * K2 + k] = __float2half_rn(acc);
   }
   (void)o;
 }
@@ -1521,41 +1569,65 @@ __global__ void __launch_bounds__(256) k_compose_ctn(const float* __restrict__ c
 }  // namespace
 void launch_compose_ctn(const float* ct, const float* wn, int Cout, int N, int K2, __half* out, cudaStream_t st) {
   dim3 grid((unsigned)((K2 + 31) / 32), (unsigned)(N / 8));
-  k_compose_ctn<<<grid, 256, 0, st>>>(ct, wn, Cout, N, K2, out);
+  k_compose_ctn<<<grid, 256, 0, st>>>(ct, wn, Cout, N, K2, std::min(Cout, 128), out);
 }
 
-// Block 1 only (Cin = 512, Cout = 256): its conv leaves the tensor pipe 54 % busy, so the doubled MMA work is cheaper than the
-// separate noise GEMM (216 + 185 -> 316 us per 1024-window tick).  Block 0's conv is already 70 % tensor-busy: composed it
-// measured 380 us against 221 + 140.
-bool convt_noise2_supported(int Cin, int Cout) { return Cout == 256 && Cin % BK == 0; }
+// Which blocks take the composed kernel: SNACB_CONVT_N2 = bit mask over the decoder blocks (default 10 = blocks 1 and 3).
+// Block 1 (Cin 512 -> Cout 256): its conv leaves the tensor pipe 54 % busy, so the doubled MMA work is cheaper than the
+// separate noise GEMM (216 + 185 -> 316 us per 1024-window tick).  Block 3 (128 -> 64, k_convt_noise_p<64, composed>):
+// 258 -> 205 us, the kernel loses its first epilogue phase and the second MMA chain.  Block 0's conv is already 70 %
+// tensor-busy (380 us composed against 221 + 140) and block 2's composed operand stream (48 KB per k-block, three stages)
+// is slower than the two-chain kernel (291 against 267 us): both keep their round-1 kernels.
+bool convt_noise2_supported(int Cin, int Cout) {
+  static const int mask = [] { const char* v = getenv("SNACB_CONVT_N2"); return v ? atoi(v) : 10; }();
+  const int b = (Cout == 512) ? 0 : (Cout == 256) ? 1 : (Cout == 128) ? 2 : (Cout == 64) ? 3 : -1;
+  return b >= 0 && ((mask >> b) & 1) && Cin == 2 * Cout && Cin % BK == 0;
+}
+
+namespace {
+template <int BN>
+cudaError_t launch_ctn2_t(const CUtensorMap& ma, const CUtensorMap& mw, const TcDev& d, int n_tiles, long long total, cudaStream_t st) {
+  static bool attr_set_dev[kMaxDev] = {};
+  bool& attr_set = attr_set_dev[cur_dev()];
+  if (!attr_set) {
+    cudaError_t e0 = cudaFuncSetAttribute(k_convt_p<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CtpSmem<BN>::kBytes);
+    if (e0 != cudaSuccess) return e0;
+    attr_set = true;
+  }
+  const int grid = (int)std::min<long long>(total, sm_count());
+  k_convt_p<BN, true><<<grid, kTcThreads, CtpSmem<BN>::kBytes, st>>>(ma, mw, d, n_tiles, (int)total);
+  return cudaGetLastError();
+}
+}  // namespace
 
 // a: the EPI_CONVT arguments of the layer (fp32 output only); W2: the stacked weight [2 N][2 K]; bias2 = W_n b.
 cudaError_t launch_convt_noise2_tc(const GroupCtx& g, const TcGemmArgs& a, const __half* W2, const float* bias2) {
-  if (a.epi != EPI_CONVT || !a.out32 || a.out16 || a.sn_alpha || a.split || !W2 || !bias2 || !convt_noise2_supported(a.K, a.Cout) ||
-      a.N != a.s * a.Cout || g.n_items <= 0 || a.a_rows <= 0)
+  if (a.epi != EPI_CONVT || !a.out32 || a.out16 || a.sn_alpha || a.split || !W2 || !bias2 || a.K != 2 * a.Cout || a.K % BK ||
+      a.N != a.s * a.Cout || g.n_items <= 0 || a.a_rows <= 0 || (a.Cout != 512 && a.Cout != 256 && a.Cout != 128 && a.Cout != 64))
     return cudaErrorInvalidValue;
   const long long Mtot = (long long)g.n_items * a.a_rows;
+  const int CN = std::min(a.Cout, 128), BN2 = 2 * CN;  // output channels / accumulator columns per tile
   CUtensorMap ma, mw;
-  if (!get_tmap(a.A, Mtot, a.K, BM, &ma) || !get_tmap(W2, 2LL * a.N, 2 * a.K, 256, &mw)) return cudaErrorNotSupported;
+  if (!get_tmap(a.A, Mtot, a.K, BM, &ma) || !get_tmap(W2, 2LL * a.N, 2 * a.K, BN2, &mw)) return cudaErrorNotSupported;
   TcDev d{};
   d.items = g.items; d.base = g.base; d.out_len = g.out_len; d.T0 = g.T0; d.n_items = g.n_items;
   d.K = a.K; d.nseg = 2; d.a_rows = a.a_rows; d.a_lo = a.a_lo; d.s = a.s; d.p = a.p; d.Cout = a.Cout;
   d.bias = a.bias; d.bias2 = bias2; d.out32 = a.out32; d.o_lo = a.o_r.lo; d.o_rows = a.o_r.n(); d.ldo = a.ldo;
   d.noise = a.noise; d.up = a.up;
-  const int n_tiles = a.N / 128, m_tiles = (int)((Mtot + BM - 1) / BM);
+  const int n_tiles = a.N / CN, m_tiles = (int)((Mtot + BM - 1) / BM);
   const long long total = (long long)n_tiles * m_tiles;
   if (total >= (1LL << 31)) return cudaErrorInvalidValue;
-  static bool attr_set_dev[kMaxDev] = {};
-  bool& attr_set = attr_set_dev[cur_dev()];
-  if (!attr_set) {
-    cudaError_t e0 = cudaFuncSetAttribute(k_convt_p<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CtpSmem<256>::kBytes);
-    if (e0 != cudaSuccess) return e0;
-    attr_set = true;
+  cudaError_t e;
+  if (a.Cout <= 128) {
+    // narrow blocks: the two-epilogue-set kernel (one tile = one phase of one m tile, all Cout channels)
+    const long long tot = (long long)m_tiles * a.s;
+    if (tot >= (1LL << 31)) return cudaErrorInvalidValue;
+    e = (a.Cout == 128) ? launch_cnp2_t<128>(ma, mw, d, (int)tot, g.stream) : launch_cnp2_t<64>(ma, mw, d, (int)tot, g.stream);
+  } else {
+    e = (BN2 == 256) ? launch_ctn2_t<256>(ma, mw, d, n_tiles, total, g.stream) : launch_ctn2_t<128>(ma, mw, d, n_tiles, total, g.stream);
   }
-  const int grid = (int)std::min<long long>(total, sm_count());
-  k_convt_p<256, true><<<grid, kTcThreads, CtpSmem<256>::kBytes, g.stream>>>(ma, mw, d, n_tiles, (int)total);
   ++*g.launches;
-  return cudaGetLastError();
+  return e;
 }
 
 // ============================================================================ depthwise k=7 -> fp16
