@@ -453,12 +453,13 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
       __half* Y16 = Aother;  // transposed-conv output as the noise GEMM operand
       const bool fuse_cn = noisy && convt_noise_supported(B.Cin, B.Cout) && !(e->cfg.flags & SNACB_FLAG_NO_CONVT_NOISE_FUSION) &&
                            e->tap_stage != sid + 1;
+      // blocks 1 / 3: ConvT + NoiseBlock as one GEMM over the composed stacked weight (built at load time when enabled)
+      const bool compose = noisy && Wb.ctn16 != nullptr && e->tap_stage != sid + 1 &&
+                           !(e->cfg.flags & (SNACB_FLAG_NO_CONVT_NOISE_FUSION | SNACB_FLAG_NO_CONVT_NOISE_COMPOSE));
       {
         TcGemmArgs a{};
         a.epi = EPI_CONVT; a.A = Ain; a.K = B.Cin; a.a_rows = B.in.n(); a.a_lo = B.in.lo; a.W = Wb.ct16; a.N = B.s * B.Cout;
         a.bias = Wb.ct_b; a.s = B.s; a.p = B.p; a.Cout = B.Cout; a.o_r = B.ct; a.ldo = B.Cout; a.up = B.up_out;
-        const bool compose = noisy && Wb.ctn16 != nullptr && e->tap_stage != sid + 1 &&
-                             !(e->cfg.flags & (SNACB_FLAG_NO_CONVT_NOISE_FUSION | SNACB_FLAG_NO_CONVT_NOISE_COMPOSE));
         if (compose) {
           // blocks 1 / 3: y + n (W_n y) from ONE GEMM over the stacked weight [W_c | W_n W_c] (used for every tick size)
           a.out32 = X;
@@ -484,8 +485,7 @@ int run_group_tc(snacb_engine* e, const Plan& P, const Item* d_items, int n_tota
           tap(e, sid + 1, noisy ? Y : X, B.ct, B.Cout, n, first, st);
         }
       }
-      if (noisy && !fuse_cn && !(Wb.ctn16 != nullptr && e->tap_stage != sid + 1 &&
-                                 !(e->cfg.flags & (SNACB_FLAG_NO_CONVT_NOISE_FUSION | SNACB_FLAG_NO_CONVT_NOISE_COMPOSE)))) {
+      if (noisy && !fuse_cn && !compose) {
         TcGemmArgs a{};
         a.epi = EPI_NOISE; a.A = Y16; a.K = B.Cout; a.a_rows = B.ct.n(); a.a_lo = B.ct.lo; a.W = Wb.noise16; a.N = B.Cout;
         a.out32 = X; a.o_r = B.ct; a.ldo = B.Cout; a.R = Y; a.r_r = B.ct; a.ldr = B.Cout; a.up = B.up_out;
